@@ -1,0 +1,79 @@
+/*
+ * include/smatrix_b200.h — device-side controls and measurement hooks of the B200 build.
+ * Nothing here exists in the reference; bindings do not need it.  bench.py, the tests and the
+ * multi-GPU router use it (through ctypes).
+ */
+#ifndef SMATRIX_B200_H
+#define SMATRIX_B200_H
+
+#include "smatrix.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* smatrix_open on an explicit CUDA device ordinal (smatrix_open uses $SMATRIX_DEVICE, default 0). */
+smatrix_t* smatrix_b200_open(const char* fname, int device);
+
+int   smatrix_b200_device(smatrix_t* self);   /* CUDA device ordinal                            */
+void* smatrix_b200_stream(smatrix_t* self);   /* the cudaStream_t every kernel is launched on   */
+void  smatrix_b200_sync(smatrix_t* self);     /* cudaStreamSynchronize on that stream            */
+
+/* CUDA-event timer on the library's own stream (torch.cuda.Event only sees torch's stream). */
+void  smatrix_b200_timer_start(smatrix_t* self);
+float smatrix_b200_timer_stop_ms(smatrix_t* self);   /* records, synchronises, returns elapsed ms */
+
+enum {
+  SMX_STAT_ROWS = 0,        /* rows in the directory                                      */
+  SMX_STAT_NNZ = 1,         /* live cells incl. non-zero column 0 (scans the directory)   */
+  SMX_STAT_DIR_CAP = 2,     /* directory capacity in entries                              */
+  SMX_STAT_SLAB_BYTES = 3,  /* bytes handed out by the slab allocator                     */
+  SMX_STAT_DEVICE_BYTES = 4,/* bytes of device memory held (directory + slab segments + scratch) */
+  SMX_STAT_LAUNCHES = 5,    /* kernels launched by this handle so far                     */
+  SMX_STAT_ROUNDS = 6,      /* upsert rounds (1 per pass + 1 per growth retry) so far     */
+  SMX_STAT_ROW_GROWS = 7,   /* row growth (rehash) events so far                          */
+  SMX_STAT_DIR_GROWS = 8,   /* directory rehash events so far                             */
+  SMX_STAT_KERNEL_NS = 9    /* device time of the dominant (update / get) kernels, ns, when timing is on */
+};
+uint64_t smatrix_b200_stat(smatrix_t* self, int which);
+
+/* When on, every update/get kernel launch is bracketed by CUDA events on the launch stream and
+ * the sum is reported as SMX_STAT_KERNEL_NS (used for the roofline figure). */
+void smatrix_b200_set_kernel_timing(smatrix_t* self, int on);
+
+/* Pinned host memory (cudaHostAlloc) so that host-pointer batches overlap copy and update. */
+void* smatrix_b200_host_alloc(size_t bytes);
+void  smatrix_b200_host_free(void* p);
+
+/* Plain device memory on the matrix's GPU, for callers that build batches on the device. */
+void* smatrix_b200_dev_alloc(smatrix_t* self, size_t bytes);
+void  smatrix_b200_dev_free(smatrix_t* self, void* p);
+void  smatrix_b200_memcpy(smatrix_t* self, void* dst, const void* src, size_t bytes); /* any direction, synchronous */
+
+/* Synthetic streams of SURVEY.md 8(d), generated on the device (r = splitmix64(seed + i)):
+ * C2 build ops [first, first+count) and C2 queries (odd j -> guaranteed miss). Device arrays. */
+void smatrix_b200_gen_c2_ops(smatrix_t* self, uint64_t seed, uint64_t first, size_t count,
+                             uint32_t rows, uint32_t ycols, uint32_t* d_xs, uint32_t* d_ys);
+void smatrix_b200_gen_c2_queries(smatrix_t* self, uint64_t seed_get, uint64_t seed_build,
+                                 uint64_t first, size_t count, uint64_t n_build, uint32_t rows,
+                                 uint32_t ycols, uint32_t* d_xs, uint32_t* d_ys);
+
+/* Roofline denominators measured in the same process: random 32 B-sector reads and random 4 B
+ * atomic adds over a `footprint_bytes` device buffer (`accesses` of them, counter-based
+ * addresses).  Return achieved accesses per second. `width` = bytes per access (4/8/16/32). */
+double smatrix_b200_probe_random_read(smatrix_t* self, size_t footprint_bytes, size_t accesses, int width);
+double smatrix_b200_probe_random_atomic(smatrix_t* self, size_t footprint_bytes, size_t accesses);
+
+/* Multi-GPU router, device side (K8): bucket a batch by owner rank = smx_owner(x, world).
+ * counts[world] (device or host uint64) receives the ops per owner; the permuted batch is
+ * written to out_* grouped by owner in rank order. All arrays are DEVICE pointers. */
+uint32_t smatrix_b200_owner(uint32_t x, uint32_t world);
+void smatrix_b200_partition(smatrix_t* self, const uint32_t* d_xs, const uint32_t* d_ys,
+                            const uint32_t* d_vals, size_t n, uint32_t world, uint64_t* h_counts,
+                            uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
+                            uint32_t* d_out_src /* nullable: original index of each routed op */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

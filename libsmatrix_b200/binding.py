@@ -1,0 +1,83 @@
+"""ctypes binding of the C-ABI (include/smatrix.h, smatrix_batch.h, smatrix_b200.h).
+
+This is the stub a Python binding of the reference would write; it contains no computation.
+`load()` binds a shared library by path and declares every prototype; the default path is the
+in-tree CUDA build and loading fails loudly if it is missing (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_SO = os.path.join(HERE, "lib", "libsmatrix_b200.so")
+
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+# name -> (restype, argtypes); every symbol the three headers declare
+PROTOTYPES = {
+    # include/smatrix.h (reference src/smatrix.h:87-94)
+    "smatrix_open": (C.c_void_p, [C.c_char_p]),
+    "smatrix_close": (None, [C.c_void_p]),
+    "smatrix_get": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "smatrix_set": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "smatrix_incr": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "smatrix_decr": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "smatrix_rowlen": (C.c_uint32, [C.c_void_p, C.c_uint32]),
+    "smatrix_getrow": (C.c_uint32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    # include/smatrix_batch.h
+    "smatrix_incr_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_decr_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_set_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_get_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_rowlen_batch": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_getrow_batch": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                          C.c_uint64]),
+    # include/smatrix_b200.h
+    "smatrix_b200_open": (C.c_void_p, [C.c_char_p, C.c_int]),
+    "smatrix_b200_device": (C.c_int, [C.c_void_p]),
+    "smatrix_b200_stream": (C.c_void_p, [C.c_void_p]),
+    "smatrix_b200_sync": (None, [C.c_void_p]),
+    "smatrix_b200_timer_start": (None, [C.c_void_p]),
+    "smatrix_b200_timer_stop_ms": (C.c_float, [C.c_void_p]),
+    "smatrix_b200_stat": (C.c_uint64, [C.c_void_p, C.c_int]),
+    "smatrix_b200_set_kernel_timing": (None, [C.c_void_p, C.c_int]),
+    "smatrix_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "smatrix_b200_host_free": (None, [C.c_void_p]),
+    "smatrix_b200_dev_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "smatrix_b200_dev_free": (None, [C.c_void_p, C.c_void_p]),
+    "smatrix_b200_memcpy": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_b200_gen_c2_ops": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32,
+                                       C.c_uint32, C.c_void_p, C.c_void_p]),
+    "smatrix_b200_gen_c2_queries": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t,
+                                           C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "smatrix_b200_probe_random_read": (C.c_double, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
+    "smatrix_b200_probe_random_atomic": (C.c_double, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "smatrix_b200_owner": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "smatrix_b200_partition": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+}
+
+STAT = {"rows": 0, "nnz": 1, "dir_cap": 2, "slab_bytes": 3, "device_bytes": 4, "launches": 5,
+        "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9}
+
+_cache: dict[str, C.CDLL] = {}
+
+
+def load(path: str | None = None) -> C.CDLL:
+    path = os.path.abspath(path or DEFAULT_SO)
+    lib = _cache.get(path)
+    if lib is None:
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} not found: build the CUDA library first "
+                "(python -m libsmatrix_b200.build). There is no CPU fallback.")
+        lib = C.CDLL(path)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError = a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _cache[path] = lib
+    return lib

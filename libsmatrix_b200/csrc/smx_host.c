@@ -1,0 +1,885 @@
+/*
+ * smx_host.c — the host side of the B200 libsmatrix hot path, in C like the reference.
+ *
+ * Exports the reference's 8-function API (include/smatrix.h, reference src/smatrix.h:87-94),
+ * the batched entry points (include/smatrix_batch.h) and the device controls
+ * (include/smatrix_b200.h).  All computation happens in the CUDA kernels of smx_kernels.cu;
+ * this file only owns memory, ordering and the retry/growth loop.  There is no CPU compute
+ * path: if CUDA is unusable, smatrix_open fails.
+ *
+ * One write batch ("chunk", <= SMATRIX_CHUNK ops) is applied as
+ *     COL0 pass  -> column-0 ops (they live in the row header and define t0)
+ *     EARLY pass -> all other ops, except those ordered after t0 in a row whose column 0
+ *                   turns non-zero inside this chunk
+ *     LATE pass  -> those parked ops
+ *     (set only) max-index + commit passes: last writer in input order wins
+ * and every pass is a loop of rounds: launch, read the control block, and if ops were turned
+ * away (bucket or directory at its load limit) grow and re-run only those ops.
+ */
+#define _GNU_SOURCE
+#include <cuda_runtime_api.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/smatrix.h"
+#include "../../include/smatrix_b200.h"
+#include "../../include/smatrix_batch.h"
+#include "smx_internal.h"
+
+#define SMX_DIR_LOG_DEFAULT 20u
+#define SMX_CHUNK_DEFAULT (1u << 26)
+#define SMX_STAGE_MAX (1u << 24)
+#define SMX_SEG_MIN ((size_t)64 << 20)
+#define SMX_SEG_MAX ((size_t)8 << 30)
+#define SMX_MAX_ROUNDS 128
+
+typedef struct {
+  char* base;
+  size_t size;
+  size_t used;
+} smx_seg_t;
+
+struct smatrix_s {
+  int device;
+  cudaStream_t stream;
+  cudaStream_t copy_stream;
+  pthread_mutex_t mu;
+
+  smx_row_t* dir;
+  uint64_t dir_cap;
+  uint32_t dir_log_min;
+  smx_ctl_t* d_ctl;
+  smx_ctl_t* h_ctl; /* pinned */
+
+  smx_seg_t* segs;
+  int nsegs, segs_cap;
+  size_t slab_bytes; /* handed out */
+  size_t seg_bytes;  /* held */
+
+  uint32_t chunk_max;
+  uint32_t list_cap;
+  uint32_t* defer[2];
+  smx_lists_t lists;
+  uint64_t* addrs;
+  uint32_t addrs_cap;
+
+  uint32_t stage_cap;
+  uint32_t* stage[2][3];
+  cudaEvent_t stage_ready[2];
+
+  uint32_t* d_small; /* 64 words */
+  uint32_t* h_small; /* pinned, 64 words */
+
+  uint32_t* d_tmp;   /* general temp (counts / outputs), grows */
+  size_t d_tmp_bytes;
+  uint64_t* d_tmp64;
+  size_t d_tmp64_bytes;
+  uint32_t* d_rowbuf;
+  size_t d_rowbuf_bytes;
+
+  uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows;
+  int timing;
+  cudaEvent_t ev0, ev1, t_start, t_stop;
+  double kernel_ns;
+  int preagg;
+  char* fname;
+};
+
+/* ------------------------------------------------------------------------------ errors */
+static void smx_die(const char* fmt, ...) { /* reference src/smatrix.c:891-894 */
+  va_list ap;
+  printf("libsmatrix error: ");
+  va_start(ap, fmt);
+  vprintf(fmt, ap);
+  va_end(ap);
+  printf("\n");
+  fflush(stdout);
+  abort();
+}
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) smx_die("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                   __FILE__, __LINE__);                                 \
+  } while (0)
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return (uint32_t)strtoul(v, NULL, 0);
+}
+
+static void* dmalloc(smatrix_t* s, size_t bytes) {
+  void* p = NULL;
+  (void)s;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
+  if (e != cudaSuccess) smx_die("out of device memory (%zu bytes): %s", bytes, cudaGetErrorString(e));
+  return p;
+}
+
+static inline smx_view_t view_of(smatrix_t* s) {
+  smx_view_t v;
+  v.dir = s->dir;
+  v.dir_cap = s->dir_cap;
+  v.dir_limit = s->dir_cap / 2;
+  v.ctl = s->d_ctl;
+  return v;
+}
+
+static void read_ctl(smatrix_t* s) {
+  CK(cudaMemcpyAsync(s->h_ctl, s->d_ctl, sizeof(smx_ctl_t), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+}
+
+/* ------------------------------------------------------------------------------ slab */
+/* A contiguous, 128-byte aligned device region of `bytes` (not zeroed). */
+static char* slab_reserve(smatrix_t* s, size_t bytes) {
+  bytes = (bytes + 127) & ~(size_t)127;
+  if (s->nsegs) {
+    smx_seg_t* g = &s->segs[s->nsegs - 1];
+    if (g->size - g->used >= bytes) {
+      char* p = g->base + g->used;
+      g->used += bytes;
+      s->slab_bytes += bytes;
+      return p;
+    }
+  }
+  size_t want = s->seg_bytes; /* geometric: each new segment doubles what is held */
+  if (want < SMX_SEG_MIN) want = SMX_SEG_MIN;
+  if (want > SMX_SEG_MAX) want = SMX_SEG_MAX;
+  if (want < bytes) want = bytes;
+  if (s->nsegs == s->segs_cap) {
+    s->segs_cap = s->segs_cap ? s->segs_cap * 2 : 16;
+    s->segs = (smx_seg_t*)realloc(s->segs, sizeof(smx_seg_t) * (size_t)s->segs_cap);
+    if (!s->segs) smx_die("out of host memory");
+  }
+  smx_seg_t* g = &s->segs[s->nsegs++];
+  g->base = (char*)dmalloc(s, want);
+  g->size = want;
+  g->used = bytes;
+  s->seg_bytes += want;
+  s->slab_bytes += bytes;
+  return g->base;
+}
+
+/* ------------------------------------------------------------------------------ scratch */
+static void ensure_lists(smatrix_t* s, uint32_t n) {
+  if (n <= s->list_cap) return;
+  uint32_t cap = s->list_cap ? s->list_cap : 1024;
+  while (cap < n) cap *= 2;
+  if (cap > s->chunk_max) cap = s->chunk_max > n ? s->chunk_max : n;
+  if (s->list_cap) {
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->defer[0]); cudaFree(s->defer[1]); cudaFree(s->lists.late); cudaFree(s->lists.grow);
+    cudaFree(s->lists.t0rows); cudaFree(s->lists.plan); cudaFree(s->lists.big);
+  }
+  s->defer[0] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->defer[1] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->lists.late = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->lists.grow = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->lists.t0rows = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->lists.plan = (smx_plan_t*)dmalloc(s, (size_t)cap * sizeof(smx_plan_t));
+  s->lists.big = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->list_cap = cap;
+}
+
+static void ensure_tmp(smatrix_t* s, size_t bytes32, size_t bytes64) {
+  if (bytes32 > s->d_tmp_bytes) {
+    if (s->d_tmp) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_tmp); }
+    s->d_tmp_bytes = bytes32 + bytes32 / 4;
+    s->d_tmp = (uint32_t*)dmalloc(s, s->d_tmp_bytes);
+  }
+  if (bytes64 > s->d_tmp64_bytes) {
+    if (s->d_tmp64) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_tmp64); }
+    s->d_tmp64_bytes = bytes64 + bytes64 / 4;
+    s->d_tmp64 = (uint64_t*)dmalloc(s, s->d_tmp64_bytes);
+  }
+}
+
+static void ensure_stage(smatrix_t* s, uint32_t n) {
+  if (n <= s->stage_cap) return;
+  uint32_t cap = n < 4096 ? 4096 : n;
+  if (s->stage_cap) {
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaStreamSynchronize(s->copy_stream));
+    for (int b = 0; b < 2; b++)
+      for (int a = 0; a < 3; a++) cudaFree(s->stage[b][a]);
+  }
+  for (int b = 0; b < 2; b++)
+    for (int a = 0; a < 3; a++) s->stage[b][a] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->stage_cap = cap;
+}
+
+/* ------------------------------------------------------------------------------ growth */
+static void timed_begin(smatrix_t* s) {
+  if (s->timing) CK(cudaEventRecord(s->ev0, s->stream));
+}
+static void timed_end(smatrix_t* s) {
+  if (s->timing) CK(cudaEventRecord(s->ev1, s->stream));
+}
+static void timed_collect(smatrix_t* s) { /* call after the stream has been synchronised */
+  if (s->timing) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->kernel_ns += (double)ms * 1e6;
+  }
+}
+
+static void grow_rows(smatrix_t* s, uint32_t n_grow) {
+  smx_view_t v = view_of(s);
+  smx_launch_grow_plan(s->stream, v, s->lists, n_grow);
+  s->n_launches++;
+  read_ctl(s);
+  const size_t bytes = (size_t)s->h_ctl->plan_bytes;
+  const uint32_t n_big = s->h_ctl->n_big;
+  char* region = slab_reserve(s, bytes);
+  CK(cudaMemsetAsync(region, 0, bytes, s->stream));
+  smx_launch_migrate(s->stream, v, s->lists, n_grow, n_big, region);
+  s->n_launches += 1 + (n_big ? 2 : 0);
+  s->n_row_grows += n_grow;
+}
+
+static uint64_t pow2_at_least(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static void resize_dir(smatrix_t* s, uint64_t new_cap) {
+  smx_view_t from = view_of(s);
+  smx_row_t* nd = (smx_row_t*)dmalloc(s, (size_t)new_cap * sizeof(smx_row_t));
+  CK(cudaMemsetAsync(nd, 0, (size_t)new_cap * sizeof(smx_row_t), s->stream));
+  CK(cudaMemsetAsync(&s->d_ctl->dir_used, 0, sizeof(unsigned long long), s->stream));
+  smx_view_t to = from;
+  to.dir = nd;
+  to.dir_cap = new_cap;
+  to.dir_limit = new_cap / 2;
+  smx_launch_dir_rehash(s->stream, from, to);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaFree(s->dir));
+  s->dir = nd;
+  s->dir_cap = new_cap;
+  s->n_dir_grows++;
+}
+
+/* ------------------------------------------------------------------------------ write path */
+static void zero_round_counters(smatrix_t* s) {
+  CK(cudaMemsetAsync(&s->d_ctl->n_defer, 0,
+                     offsetof(smx_ctl_t, scratch) - offsetof(smx_ctl_t, n_defer), s->stream));
+}
+
+/* Run one pass to completion: rounds of (launch, grow, re-run the ops that were turned away). */
+static void run_pass(smatrix_t* s, smx_ops_t ops, int op, int pass, const uint32_t* list, uint32_t m) {
+  int flip = 0;
+  uint32_t prev_defer = 0xFFFFFFFFu;
+  for (int round = 0; m > 0; round++) {
+    if (round >= SMX_MAX_ROUNDS) smx_die("update pass does not converge (%u ops left)", m);
+    zero_round_counters(s);
+    s->lists.defer_out = s->defer[flip];
+    timed_begin(s);
+    smx_launch_upsert(s->stream, view_of(s), ops, s->lists, op, pass, list, m, s->preagg);
+    timed_end(s);
+    s->n_launches++;
+    s->n_rounds++;
+    read_ctl(s);
+    timed_collect(s);
+    const smx_ctl_t c = *s->h_ctl;
+    if (c.n_defer == 0) break;
+    if (c.n_grow) grow_rows(s, c.n_grow);
+    if (c.n_dirfull || c.dir_used >= s->dir_cap / 2) {
+      uint64_t need = 2 * (c.dir_used + (uint64_t)c.n_dirfull);
+      uint64_t cap = pow2_at_least(need);
+      if (cap < s->dir_cap * 2) cap = s->dir_cap * 2;
+      resize_dir(s, cap);
+    } else if (!c.n_grow && c.n_defer >= prev_defer) {
+      smx_die("update pass made no progress (%u ops deferred)", c.n_defer);
+    }
+    prev_defer = c.n_defer;
+    list = s->defer[flip];
+    m = c.n_defer;
+    flip ^= 1;
+  }
+}
+
+/* After a chunk: a directory that was grown for a burst of duplicates goes back to a load
+ * factor in (1/4, 1/2] so that it stays as L2-friendly as the data allows. */
+static void maybe_shrink_dir(smatrix_t* s) {
+  const uint64_t used = s->h_ctl->dir_used;
+  uint64_t fit = pow2_at_least(2 * (used ? used : 1));
+  const uint64_t floor_cap = 1ull << s->dir_log_min;
+  if (fit < floor_cap) fit = floor_cap;
+  if (fit * 4 <= s->dir_cap) resize_dir(s, fit);
+}
+
+static void process_chunk(smatrix_t* s, int api_op, const uint32_t* d_xs, const uint32_t* d_ys,
+                          const uint32_t* d_vs, uint32_t n) {
+  if (n == 0) return;
+  ensure_lists(s, n);
+  smx_ops_t ops;
+  ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.v_const = 1u; ops.n = n;
+  const int op = (api_op == 2) ? SMX_OP_SETZERO : api_op;
+  CK(cudaMemsetAsync(&s->d_ctl->n_late, 0, 2 * sizeof(uint32_t), s->stream));
+  run_pass(s, ops, op, SMX_PASS_COL0, NULL, n);
+  run_pass(s, ops, op, SMX_PASS_EARLY, NULL, n);
+  const uint32_t n_late = s->h_ctl->n_late;
+  if (n_late) run_pass(s, ops, op, SMX_PASS_LATE, s->lists.late, n_late);
+  if (api_op == 2) { /* set: last writer in input order wins */
+    if (n > s->addrs_cap) {
+      if (s->addrs) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->addrs); }
+      s->addrs_cap = s->list_cap > n ? s->list_cap : n;
+      s->addrs = (uint64_t*)dmalloc(s, (size_t)s->addrs_cap * 8);
+    }
+    smx_launch_set_max(s->stream, view_of(s), ops, s->addrs);
+    smx_launch_set_commit(s->stream, ops, s->addrs);
+    s->n_launches += 2;
+  }
+  const uint32_t n_t0 = s->h_ctl->n_t0;
+  if (n_t0) {
+    smx_launch_finalize_t0(s->stream, view_of(s), s->lists.t0rows, n_t0);
+    s->n_launches++;
+  }
+  maybe_shrink_dir(s);
+}
+
+static int is_device_ptr(const void* p) {
+  struct cudaPointerAttributes a;
+  if (!p) return 0;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError(); /* plain host memory on old drivers */
+    return 0;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static void enter(smatrix_t* s) {
+  if (!s) smx_die("NULL matrix handle");
+  pthread_mutex_lock(&s->mu);
+  CK(cudaSetDevice(s->device));
+}
+static void leave(smatrix_t* s) { pthread_mutex_unlock(&s->mu); }
+
+static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint32_t* ys,
+                        const uint32_t* vs, size_t n) {
+  if (n == 0) return;
+  enter(s);
+  const int dev = is_device_ptr(xs);
+  if (is_device_ptr(ys) != dev || (vs && is_device_ptr(vs) != dev))
+    smx_die("batch arrays must be all host or all device pointers");
+  if (dev) {
+    for (size_t off = 0; off < n; off += s->chunk_max) {
+      const uint32_t len = (uint32_t)((n - off < s->chunk_max) ? n - off : s->chunk_max);
+      process_chunk(s, api_op, xs + off, ys + off, vs ? vs + off : NULL, len);
+    }
+    CK(cudaStreamSynchronize(s->stream));
+  } else {
+    /* host arrays: double-buffered upload on the copy stream overlaps the previous chunk's update */
+    uint32_t step = s->chunk_max < SMX_STAGE_MAX ? s->chunk_max : SMX_STAGE_MAX;
+    if (n < step) step = (uint32_t)n;
+    ensure_stage(s, step);
+    size_t off = 0;
+    int b = 0;
+    uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
+    const uint32_t* src[3] = {xs, ys, vs};
+    for (int a = 0; a < 3; a++)
+      if (src[a]) CK(cudaMemcpyAsync(s->stage[b][a], src[a] + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->copy_stream));
+    CK(cudaEventRecord(s->stage_ready[b], s->copy_stream));
+    while (off < n) {
+      const size_t next = off + len;
+      uint32_t next_len = 0;
+      if (next < n) { /* start uploading the next chunk into the other buffer */
+        next_len = (uint32_t)((n - next < step) ? n - next : step);
+        for (int a = 0; a < 3; a++)
+          if (src[a]) CK(cudaMemcpyAsync(s->stage[b ^ 1][a], src[a] + next, (size_t)next_len * 4, cudaMemcpyHostToDevice, s->copy_stream));
+        CK(cudaEventRecord(s->stage_ready[b ^ 1], s->copy_stream));
+      }
+      CK(cudaStreamWaitEvent(s->stream, s->stage_ready[b], 0));
+      process_chunk(s, api_op, s->stage[b][0], s->stage[b][1], vs ? s->stage[b][2] : NULL, len);
+      CK(cudaStreamSynchronize(s->stream));
+      off = next;
+      len = next_len;
+      b ^= 1;
+    }
+  }
+  leave(s);
+}
+
+void smatrix_incr_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
+                        const uint32_t* vals, size_t n) {
+  write_batch(self, 0, xs, ys, vals, n);
+}
+void smatrix_decr_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
+                        const uint32_t* vals, size_t n) {
+  write_batch(self, 1, xs, ys, vals, n);
+}
+void smatrix_set_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
+                       const uint32_t* vals, size_t n) {
+  write_batch(self, 2, xs, ys, vals, n);
+}
+
+/* ------------------------------------------------------------------------------ read path */
+#define READ_STEP (1u << 26)
+
+void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, size_t n,
+                       uint32_t* out) {
+  if (n == 0) return;
+  enter(s);
+  const int dev = is_device_ptr(xs);
+  if (is_device_ptr(ys) != dev || is_device_ptr(out) != dev)
+    smx_die("batch arrays must be all host or all device pointers");
+  if (dev) {
+    for (size_t off = 0; off < n; off += READ_STEP) {
+      const uint32_t len = (uint32_t)((n - off < READ_STEP) ? n - off : READ_STEP);
+      timed_begin(s);
+      smx_launch_get(s->stream, view_of(s), xs + off, ys + off, len, out + off);
+      timed_end(s);
+      s->n_launches++;
+      CK(cudaStreamSynchronize(s->stream));
+      timed_collect(s);
+    }
+  } else {
+    uint32_t step = n < SMX_STAGE_MAX ? (uint32_t)n : SMX_STAGE_MAX;
+    ensure_stage(s, step);
+    int b = 0;
+    for (size_t off = 0; off < n; off += step, b ^= 1) {
+      const uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
+      /* everything in stream order: upload, look up, download (buffer b is free again: the
+       * download of two chunks ago was enqueued on the same stream) */
+      CK(cudaMemcpyAsync(s->stage[b][0], xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
+      CK(cudaMemcpyAsync(s->stage[b][1], ys + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
+      smx_launch_get(s->stream, view_of(s), s->stage[b][0], s->stage[b][1], len, s->stage[b][2]);
+      s->n_launches++;
+      CK(cudaMemcpyAsync(out + off, s->stage[b][2], (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+void smatrix_rowlen_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint32_t* out) {
+  if (n == 0) return;
+  enter(s);
+  const int dev = is_device_ptr(xs);
+  if (is_device_ptr(out) != dev) smx_die("batch arrays must be all host or all device pointers");
+  for (size_t off = 0; off < n; off += READ_STEP) {
+    const uint32_t len = (uint32_t)((n - off < READ_STEP) ? n - off : READ_STEP);
+    if (dev) {
+      smx_launch_rowlen(s->stream, view_of(s), xs + off, len, out + off);
+    } else {
+      ensure_tmp(s, (size_t)len * 8, 0);
+      CK(cudaMemcpyAsync(s->d_tmp, xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
+      smx_launch_rowlen(s->stream, view_of(s), s->d_tmp, len, s->d_tmp + len);
+      CK(cudaMemcpyAsync(out + off, s->d_tmp + len, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    s->n_launches++;
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+/* counts + scan for rows xs[0..n) (device array); leaves offsets in d_tmp64[0..n], returns total */
+static uint64_t plan_rows(smatrix_t* s, const uint32_t* d_xs, uint32_t n, uint32_t* d_counts) {
+  const uint32_t tiles = smx_scan_scratch_items(n);
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, n, d_counts);
+  smx_launch_scan(s->stream, d_counts, n, 0, s->d_tmp64, s->d_tmp64 + (size_t)n + 1);
+  (void)tiles;
+  s->n_launches += 4;
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&s->h_small[32], s->d_tmp64 + n, 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  memcpy(&total, &s->h_small[32], 8);
+  return total;
+}
+
+uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64_t* offsets,
+                              uint32_t* pairs, uint64_t pairs_cap) {
+  if (n == 0) {
+    if (offsets) {
+      uint64_t zero = 0;
+      enter(s);
+      CK(cudaMemcpy(offsets, &zero, 8, cudaMemcpyDefault));
+      leave(s);
+    }
+    return 0;
+  }
+  if (n >= 0xFFFFFFFFull) smx_die("getrow_batch: too many rows in one call");
+  enter(s);
+  const uint32_t nn = (uint32_t)n;
+  const int dev = is_device_ptr(xs);
+  const uint32_t tiles = smx_scan_scratch_items(nn);
+  ensure_tmp(s, (size_t)nn * 8, ((size_t)nn + 1 + tiles) * 8);
+  const uint32_t* d_xs = xs;
+  uint32_t* d_counts = s->d_tmp + nn;
+  if (!dev) {
+    CK(cudaMemcpyAsync(s->d_tmp, xs, (size_t)nn * 4, cudaMemcpyHostToDevice, s->stream));
+    d_xs = s->d_tmp;
+  }
+  const uint64_t total = plan_rows(s, d_xs, nn, d_counts);
+  if (offsets)
+    CK(cudaMemcpyAsync(offsets, s->d_tmp64, ((size_t)nn + 1) * 8, cudaMemcpyDefault, s->stream));
+  if (pairs && total <= pairs_cap && total > 0) {
+    if (is_device_ptr(pairs)) {
+      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, pairs);
+      s->n_launches++;
+    } else {
+      if (total * 8 > s->d_rowbuf_bytes) {
+        if (s->d_rowbuf) cudaFree(s->d_rowbuf);
+        s->d_rowbuf_bytes = (size_t)total * 8;
+        s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
+      }
+      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, s->d_rowbuf);
+      s->n_launches++;
+      CK(cudaMemcpyAsync(pairs, s->d_rowbuf, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+  return total;
+}
+
+/* ------------------------------------------------------------------------------ single ops */
+static uint32_t single_write(smatrix_t* s, int api_op, uint32_t x, uint32_t y, uint32_t v) {
+  enter(s);
+  s->h_small[0] = x; s->h_small[1] = y; s->h_small[2] = v;
+  CK(cudaMemcpyAsync(s->d_small, s->h_small, 12, cudaMemcpyHostToDevice, s->stream));
+  process_chunk(s, api_op, s->d_small, s->d_small + 1, s->d_small + 2, 1);
+  smx_launch_get(s->stream, view_of(s), s->d_small, s->d_small + 1, 1, s->d_small + 3);
+  s->n_launches++;
+  CK(cudaMemcpyAsync(&s->h_small[3], s->d_small + 3, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const uint32_t r = s->h_small[3];
+  leave(s);
+  return r;
+}
+
+uint32_t smatrix_set(smatrix_t* self, uint32_t x, uint32_t y, uint32_t value) {
+  return single_write(self, 2, x, y, value);
+}
+uint32_t smatrix_incr(smatrix_t* self, uint32_t x, uint32_t y, uint32_t value) {
+  return single_write(self, 0, x, y, value);
+}
+uint32_t smatrix_decr(smatrix_t* self, uint32_t x, uint32_t y, uint32_t value) {
+  return single_write(self, 1, x, y, value);
+}
+
+uint32_t smatrix_get(smatrix_t* s, uint32_t x, uint32_t y) {
+  enter(s);
+  s->h_small[0] = x; s->h_small[1] = y;
+  CK(cudaMemcpyAsync(s->d_small, s->h_small, 8, cudaMemcpyHostToDevice, s->stream));
+  smx_launch_get(s->stream, view_of(s), s->d_small, s->d_small + 1, 1, s->d_small + 3);
+  s->n_launches++;
+  CK(cudaMemcpyAsync(&s->h_small[3], s->d_small + 3, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const uint32_t r = s->h_small[3];
+  leave(s);
+  return r;
+}
+
+uint32_t smatrix_rowlen(smatrix_t* s, uint32_t x) {
+  enter(s);
+  s->h_small[0] = x;
+  CK(cudaMemcpyAsync(s->d_small, s->h_small, 4, cudaMemcpyHostToDevice, s->stream));
+  smx_launch_rowlen(s->stream, view_of(s), s->d_small, 1, s->d_small + 3);
+  s->n_launches++;
+  CK(cudaMemcpyAsync(&s->h_small[3], s->d_small + 3, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const uint32_t r = s->h_small[3];
+  leave(s);
+  return r;
+}
+
+uint32_t smatrix_getrow(smatrix_t* s, uint32_t x, uint32_t* ret, size_t ret_len) {
+  enter(s);
+  s->h_small[0] = x;
+  CK(cudaMemcpyAsync(s->d_small, s->h_small, 4, cudaMemcpyHostToDevice, s->stream));
+  ensure_tmp(s, 64, (2 + smx_scan_scratch_items(1)) * 8);
+  const uint64_t total = plan_rows(s, s->d_small, 1, s->d_small + 4);
+  /* reference loop (src/smatrix.c:196-205): emit, then stop once num*8 >= ret_len */
+  uint64_t room = (ret_len + 7) / 8;
+  if (room < 1) room = 1;
+  const uint64_t n = total < room ? total : room;
+  if (n > 0) {
+    if (total * 8 > s->d_rowbuf_bytes) {
+      if (s->d_rowbuf) cudaFree(s->d_rowbuf);
+      s->d_rowbuf_bytes = (size_t)total * 8;
+      s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
+    }
+    smx_launch_getrow_fill(s->stream, view_of(s), s->d_small, 1, s->d_tmp64, 0, s->d_rowbuf);
+    s->n_launches++;
+    CK(cudaMemcpyAsync(ret, s->d_rowbuf, (size_t)n * 8, cudaMemcpyDefault, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  leave(s);
+  return (uint32_t)n;
+}
+
+/* ------------------------------------------------------------------------------ open / close */
+smatrix_t* smatrix_b200_open(const char* fname, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "libsmatrix: no usable CUDA device (this build has no CPU path)\n");
+    return NULL;
+  }
+  if (device < 0 || device >= ndev) {
+    fprintf(stderr, "libsmatrix: CUDA device %d out of range (0..%d)\n", device, ndev - 1);
+    return NULL;
+  }
+  if (fname) {
+    fprintf(stderr, "libsmatrix: file-backed mode (%s) is not available in this build yet\n", fname);
+    return NULL;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return NULL;
+  smatrix_t* s = (smatrix_t*)calloc(1, sizeof(smatrix_t));
+  if (!s) return NULL;
+  s->device = device;
+  pthread_mutex_init(&s->mu, NULL);
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s->stage_ready[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s->stage_ready[1], cudaEventDisableTiming));
+  CK(cudaEventCreate(&s->ev0));
+  CK(cudaEventCreate(&s->ev1));
+  CK(cudaEventCreate(&s->t_start));
+  CK(cudaEventCreate(&s->t_stop));
+  s->dir_log_min = env_u32("SMATRIX_DIR_LOG2", SMX_DIR_LOG_DEFAULT);
+  if (s->dir_log_min < 4) s->dir_log_min = 4;
+  if (s->dir_log_min > 31) s->dir_log_min = 31;
+  s->chunk_max = env_u32("SMATRIX_CHUNK", SMX_CHUNK_DEFAULT);
+  if (s->chunk_max < 1) s->chunk_max = 1;
+  if (s->chunk_max > (1u << 30)) s->chunk_max = 1u << 30;
+  s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
+  s->dir_cap = 1ull << s->dir_log_min;
+  s->dir = (smx_row_t*)dmalloc(s, (size_t)s->dir_cap * sizeof(smx_row_t));
+  CK(cudaMemsetAsync(s->dir, 0, (size_t)s->dir_cap * sizeof(smx_row_t), s->stream));
+  s->d_ctl = (smx_ctl_t*)dmalloc(s, sizeof(smx_ctl_t));
+  CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(smx_ctl_t), s->stream));
+  CK(cudaHostAlloc((void**)&s->h_ctl, sizeof(smx_ctl_t), cudaHostAllocDefault));
+  memset(s->h_ctl, 0, sizeof(smx_ctl_t));
+  s->d_small = (uint32_t*)dmalloc(s, 64 * 4);
+  CK(cudaHostAlloc((void**)&s->h_small, 64 * 4, cudaHostAllocDefault));
+  CK(cudaStreamSynchronize(s->stream));
+  return s;
+}
+
+smatrix_t* smatrix_open(const char* fname) {
+  return smatrix_b200_open(fname, (int)env_u32("SMATRIX_DEVICE", 0));
+}
+
+void smatrix_close(smatrix_t* s) {
+  if (!s) return;
+  enter(s);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaStreamSynchronize(s->copy_stream));
+  for (int i = 0; i < s->nsegs; i++) cudaFree(s->segs[i].base);
+  free(s->segs);
+  cudaFree(s->dir);
+  cudaFree(s->d_ctl);
+  cudaFreeHost(s->h_ctl);
+  cudaFree(s->d_small);
+  cudaFreeHost(s->h_small);
+  if (s->list_cap) {
+    cudaFree(s->defer[0]); cudaFree(s->defer[1]); cudaFree(s->lists.late); cudaFree(s->lists.grow);
+    cudaFree(s->lists.t0rows); cudaFree(s->lists.plan); cudaFree(s->lists.big);
+  }
+  if (s->addrs) cudaFree(s->addrs);
+  if (s->stage_cap)
+    for (int b = 0; b < 2; b++)
+      for (int a = 0; a < 3; a++) cudaFree(s->stage[b][a]);
+  if (s->d_tmp) cudaFree(s->d_tmp);
+  if (s->d_tmp64) cudaFree(s->d_tmp64);
+  if (s->d_rowbuf) cudaFree(s->d_rowbuf);
+  cudaEventDestroy(s->stage_ready[0]); cudaEventDestroy(s->stage_ready[1]);
+  cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+  cudaEventDestroy(s->t_start); cudaEventDestroy(s->t_stop);
+  cudaStreamDestroy(s->stream);
+  cudaStreamDestroy(s->copy_stream);
+  free(s->fname);
+  leave(s);
+  pthread_mutex_destroy(&s->mu);
+  free(s);
+}
+
+/* ------------------------------------------------------------------------------ controls */
+int smatrix_b200_device(smatrix_t* s) { return s->device; }
+void* smatrix_b200_stream(smatrix_t* s) { return (void*)s->stream; }
+void smatrix_b200_sync(smatrix_t* s) {
+  enter(s);
+  CK(cudaStreamSynchronize(s->stream));
+  leave(s);
+}
+void smatrix_b200_timer_start(smatrix_t* s) {
+  enter(s);
+  CK(cudaEventRecord(s->t_start, s->stream));
+  leave(s);
+}
+float smatrix_b200_timer_stop_ms(smatrix_t* s) {
+  float ms = 0.f;
+  enter(s);
+  CK(cudaEventRecord(s->t_stop, s->stream));
+  CK(cudaEventSynchronize(s->t_stop));
+  CK(cudaEventElapsedTime(&ms, s->t_start, s->t_stop));
+  leave(s);
+  return ms;
+}
+void smatrix_b200_set_kernel_timing(smatrix_t* s, int on) {
+  enter(s);
+  s->timing = on;
+  s->kernel_ns = 0.0;
+  leave(s);
+}
+
+uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
+  uint64_t r = 0;
+  enter(s);
+  switch (which) {
+    case SMX_STAT_ROWS:
+      read_ctl(s);
+      r = s->h_ctl->dir_used;
+      break;
+    case SMX_STAT_NNZ:
+      CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
+      smx_launch_count_nnz(s->stream, view_of(s));
+      s->n_launches++;
+      read_ctl(s);
+      r = s->h_ctl->scratch;
+      break;
+    case SMX_STAT_DIR_CAP: r = s->dir_cap; break;
+    case SMX_STAT_SLAB_BYTES: r = s->slab_bytes; break;
+    case SMX_STAT_DEVICE_BYTES:
+      r = s->seg_bytes + s->dir_cap * sizeof(smx_row_t) + (uint64_t)s->list_cap * (6 * 4 + sizeof(smx_plan_t)) +
+          (uint64_t)s->stage_cap * 24 + s->d_tmp_bytes + s->d_tmp64_bytes + s->d_rowbuf_bytes +
+          (uint64_t)s->addrs_cap * 8;
+      break;
+    case SMX_STAT_LAUNCHES: r = s->n_launches; break;
+    case SMX_STAT_ROUNDS: r = s->n_rounds; break;
+    case SMX_STAT_ROW_GROWS: r = s->n_row_grows; break;
+    case SMX_STAT_DIR_GROWS: r = s->n_dir_grows; break;
+    case SMX_STAT_KERNEL_NS: r = (uint64_t)s->kernel_ns; break;
+    default: break;
+  }
+  leave(s);
+  return r;
+}
+
+void* smatrix_b200_host_alloc(size_t bytes) {
+  void* p = NULL;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return NULL;
+  return p;
+}
+void smatrix_b200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+void* smatrix_b200_dev_alloc(smatrix_t* s, size_t bytes) {
+  enter(s);
+  void* p = dmalloc(s, bytes);
+  leave(s);
+  return p;
+}
+void smatrix_b200_dev_free(smatrix_t* s, void* p) {
+  enter(s);
+  CK(cudaStreamSynchronize(s->stream));
+  if (p) CK(cudaFree(p));
+  leave(s);
+}
+void smatrix_b200_memcpy(smatrix_t* s, void* dst, const void* src, size_t bytes) {
+  enter(s);
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  leave(s);
+}
+
+void smatrix_b200_gen_c2_ops(smatrix_t* s, uint64_t seed, uint64_t first, size_t count,
+                             uint32_t rows, uint32_t ycols, uint32_t* d_xs, uint32_t* d_ys) {
+  enter(s);
+  smx_launch_gen_c2_ops(s->stream, seed, first, count, rows, ycols, d_xs, d_ys);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+void smatrix_b200_gen_c2_queries(smatrix_t* s, uint64_t seed_get, uint64_t seed_build,
+                                 uint64_t first, size_t count, uint64_t n_build, uint32_t rows,
+                                 uint32_t ycols, uint32_t* d_xs, uint32_t* d_ys) {
+  enter(s);
+  smx_launch_gen_c2_queries(s->stream, seed_get, seed_build, first, count, n_build, rows, ycols,
+                            d_xs, d_ys);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+double smatrix_b200_probe_random_read(smatrix_t* s, size_t footprint, size_t accesses, int width) {
+  if (width != 4 && width != 8 && width != 16 && width != 32) return 0.0;
+  enter(s);
+  char* buf = (char*)dmalloc(s, footprint);
+  CK(cudaMemsetAsync(buf, 1, footprint, s->stream));
+  float ms = 0.f;
+  smx_launch_probe_read(s->stream, buf, footprint / (size_t)width, accesses / 8, width, s->d_ctl); /* warm-up */
+  CK(cudaEventRecord(s->ev0, s->stream));
+  smx_launch_probe_read(s->stream, buf, footprint / (size_t)width, accesses, width, s->d_ctl);
+  CK(cudaEventRecord(s->ev1, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  CK(cudaFree(buf));
+  s->n_launches += 2;
+  leave(s);
+  return (double)accesses / ((double)ms * 1e-3);
+}
+double smatrix_b200_probe_random_atomic(smatrix_t* s, size_t footprint, size_t accesses) {
+  enter(s);
+  uint32_t* buf = (uint32_t*)dmalloc(s, footprint);
+  CK(cudaMemsetAsync(buf, 0, footprint, s->stream));
+  float ms = 0.f;
+  smx_launch_probe_atomic(s->stream, buf, footprint / 4, accesses / 8);
+  CK(cudaEventRecord(s->ev0, s->stream));
+  smx_launch_probe_atomic(s->stream, buf, footprint / 4, accesses);
+  CK(cudaEventRecord(s->ev1, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  CK(cudaFree(buf));
+  s->n_launches += 2;
+  leave(s);
+  return (double)accesses / ((double)ms * 1e-3);
+}
+
+/* ------------------------------------------------------------------------------ router (K8) */
+uint32_t smatrix_b200_owner(uint32_t x, uint32_t world) { return smx_owner_hash(x) % world; }
+
+void smatrix_b200_partition(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
+                            const uint32_t* d_vals, size_t n, uint32_t world, uint64_t* h_counts,
+                            uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
+                            uint32_t* d_out_src) {
+  if (world == 0 || world > 64) smx_die("partition: world size must be 1..64");
+  if (n > 0xFFFFFFFFull) smx_die("partition: batch too large");
+  enter(s);
+  ensure_tmp(s, 0, 2 * 64 * 8);
+  unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
+  unsigned long long* d_cursors = d_counts + 64;
+  unsigned long long h[64], cur[64];
+  CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
+  smx_launch_partition_count(s->stream, d_xs, (uint32_t)n, world, d_counts);
+  CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  unsigned long long at = 0;
+  for (uint32_t r = 0; r < world; r++) {
+    cur[r] = at;
+    at += h[r];
+    h_counts[r] = h[r];
+  }
+  CK(cudaMemcpyAsync(d_cursors, cur, world * 8, cudaMemcpyHostToDevice, s->stream));
+  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, d_cursors,
+                               d_out_xs, d_out_ys, d_out_vals, d_out_src);
+  s->n_launches += 2;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}

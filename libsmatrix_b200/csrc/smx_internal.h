@@ -1,0 +1,148 @@
+/*
+ * smx_internal.h — layouts shared by the host shim (C) and the kernels (CUDA), plus the
+ * launcher prototypes.  Plain C so that smx_host.c can include it.
+ *
+ * HBM layout (DESIGN.md "Data layout"):
+ *
+ *   row directory   open addressing over 64-byte entries, position = mix_row(x) & (cap-1),
+ *                   linear probing.  Entry = one 32-byte header sector + one 32-byte inline
+ *                   bucket sector (4 cells), so a row with <= 4 columns costs one 64-byte burst.
+ *                   Replaces the reference's cmap + the malloc'ed 48-byte rmap header
+ *                   (src/smatrix.h:40-65).
+ *   column buckets  per row, open addressing over 32-byte sectors of 4 packed cells
+ *                   {u32 column, u32 value} (same 8-byte cell as src/smatrix.h:35-38), position
+ *                   = mix_col(y) & (sectors-1), linear probing over sectors.  Column 0 is NOT
+ *                   stored here: it lives in the header (c0), so cell == 0 is the empty sentinel
+ *                   and a zero-valued cell with column != 0 stays live.
+ *   slab            buckets of 16 * 2^k cells carved from cudaMalloc'ed segments by a bump
+ *                   cursor; growth = allocate the bigger bucket, re-place, recycle the old one.
+ */
+#ifndef SMX_INTERNAL_H
+#define SMX_INTERNAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- row header flags (smx_row_t.meta) ------------------------------------------------- */
+#define SMX_META_CAPLOG 0x3Fu   /* log2(bucket capacity in cells); 2 = the inline bucket     */
+#define SMX_META_USED   0x100u  /* entry holds a row                                         */
+#define SMX_META_ZC     0x200u  /* column 0 was already non-zero when the current batch began */
+#define SMX_META_D      0x400u  /* rowlen = live + 1: a virtual resize counted column 0 (Q1)  */
+#define SMX_META_T0P    0x800u  /* column 0 turns non-zero inside the current batch at t0     */
+#define SMX_META_GROW   0x1000u /* row is queued for growth in the current round              */
+#define SMX_INLINE_LOG  2u
+#define SMX_MIN_SLAB_LOG 4u     /* first slab bucket: 16 cells = 128 B (src/smatrix.h:21)     */
+#define SMX_MAX_CAPLOG  31u
+#define SMX_BIG_LOG     13u     /* buckets >= 2^13 cells are re-placed / compacted grid-wide  */
+
+typedef struct {
+  uint32_t key;    /* row id x                                  } claimed together by one   */
+  uint32_t meta;   /* flags | caplog                            } 64-bit CAS                */
+  uint64_t slots;  /* device address of the slab bucket (caplog > 2)                        */
+  uint32_t live;   /* L: number of columns != 0 ever written                                */
+  uint32_t c0;     /* value of column 0                                                     */
+  uint32_t t0inv;  /* ~(batch index of the first op that makes column 0 non-zero); 0 = none */
+  uint32_t want;   /* ops turned away because the bucket was at its load limit (growth sizing) */
+  uint64_t inl[4]; /* inline bucket                                                          */
+} smx_row_t;       /* 64 bytes */
+
+/* ---- device control block (counters the host reads back after every round) -------------- */
+typedef struct {
+  /* persistent */
+  unsigned long long dir_used;   /* rows in the directory                                    */
+  /* per chunk */
+  uint32_t n_late;               /* ops parked for the LATE pass                             */
+  uint32_t n_t0;                 /* rows whose column 0 turned non-zero in this chunk        */
+  /* per round */
+  uint32_t n_defer;              /* ops turned away this round (re-run after growth)         */
+  uint32_t n_dirfull;            /*   ... because the directory was at its load limit        */
+  uint32_t n_grow;               /* rows queued for growth                                   */
+  uint32_t n_big;                /* of those, rows whose OLD bucket is >= 2^SMX_BIG_LOG      */
+  unsigned long long plan_bytes; /* bytes of new buckets planned by grow_plan                */
+  unsigned long long scratch;    /* misc: reductions (nnz, probe checksums)                  */
+} smx_ctl_t;
+
+typedef struct {
+  smx_row_t* dir;
+  uint64_t dir_cap;    /* entries, power of two                                             */
+  uint64_t dir_limit;  /* new rows are refused once dir_used >= dir_limit                    */
+  smx_ctl_t* ctl;
+} smx_view_t;
+
+typedef struct {
+  const uint32_t* xs;
+  const uint32_t* ys;
+  const uint32_t* vs;  /* NULL: every value is v_const                                       */
+  uint32_t v_const;
+  uint32_t n;
+} smx_ops_t;
+
+typedef struct {
+  uint32_t entry;      /* directory index of the growing row                                 */
+  uint32_t newlog;     /* log2 of the new bucket capacity                                    */
+  uint64_t off;        /* byte offset of the new bucket inside this round's slab region       */
+} smx_plan_t;
+
+typedef struct {
+  uint32_t* defer_out; /* [n]  ops turned away this round                                    */
+  uint32_t* late;      /* [n]  ops parked for the LATE pass                                  */
+  uint32_t* grow;      /* [n]  directory indices of rows queued for growth                   */
+  uint32_t* t0rows;    /* [n]  row ids (x) whose column 0 turned non-zero in this chunk      */
+  smx_plan_t* plan;    /* [n]                                                                */
+  uint32_t* big;       /* [n]  plan indices of big rows                                      */
+} smx_lists_t;
+
+enum { SMX_OP_INCR = 0, SMX_OP_DECR = 1, SMX_OP_SETZERO = 2 };
+enum { SMX_PASS_COL0 = 0, SMX_PASS_EARLY = 1, SMX_PASS_LATE = 2 };
+
+/* ---- launchers (smx_kernels.cu); `stream` is a cudaStream_t ------------------------------ */
+typedef void* smx_stream_t;
+
+void smx_launch_upsert(smx_stream_t stream, smx_view_t v, smx_ops_t ops, smx_lists_t l, int op,
+                       int pass, const uint32_t* list, uint32_t m, int preaggregate);
+void smx_launch_grow_plan(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow);
+void smx_launch_migrate(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow,
+                        uint32_t n_big, void* region_base);
+void smx_launch_dir_rehash(smx_stream_t stream, smx_view_t from, smx_view_t to);
+void smx_launch_finalize_t0(smx_stream_t stream, smx_view_t v, const uint32_t* t0rows, uint32_t n);
+void smx_launch_set_max(smx_stream_t stream, smx_view_t v, smx_ops_t ops, uint64_t* addrs);
+void smx_launch_set_commit(smx_stream_t stream, smx_ops_t ops, const uint64_t* addrs);
+void smx_launch_get(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
+                    uint32_t n, uint32_t* out);
+void smx_launch_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
+                       uint32_t* out);
+void smx_launch_row_counts(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
+                           uint32_t* counts);
+void smx_launch_scan(smx_stream_t stream, const uint32_t* counts, uint32_t n, uint64_t base,
+                     uint64_t* offsets /* n+1 */, uint64_t* block_sums /* scratch */);
+void smx_launch_getrow_fill(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
+                            const uint64_t* offsets, uint64_t offset_bias, uint32_t* pairs);
+void smx_launch_count_nnz(smx_stream_t stream, smx_view_t v);
+void smx_launch_gen_c2_ops(smx_stream_t stream, uint64_t seed, uint64_t first, uint64_t count,
+                           uint32_t rows, uint32_t ycols, uint32_t* xs, uint32_t* ys);
+void smx_launch_gen_c2_queries(smx_stream_t stream, uint64_t seed_get, uint64_t seed_build,
+                               uint64_t first, uint64_t count, uint64_t n_build, uint32_t rows,
+                               uint32_t ycols, uint32_t* xs, uint32_t* ys);
+void smx_launch_probe_read(smx_stream_t stream, const void* buf, uint64_t n_units, uint64_t accesses,
+                           int width, smx_ctl_t* ctl);
+void smx_launch_probe_atomic(smx_stream_t stream, uint32_t* buf, uint64_t n_words, uint64_t accesses);
+void smx_launch_partition_count(smx_stream_t stream, const uint32_t* xs, uint32_t n, uint32_t world,
+                                unsigned long long* counts /* [world], zeroed */);
+void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const uint32_t* ys,
+                                  const uint32_t* vs, uint32_t n, uint32_t world,
+                                  unsigned long long* cursors /* [world] start offsets */,
+                                  uint32_t* oxs, uint32_t* oys, uint32_t* ovs, uint32_t* osrc);
+uint32_t smx_scan_scratch_items(uint32_t n); /* number of uint64 block sums smx_launch_scan needs */
+int smx_grid_blocks(void);                   /* resident grid size used by the streaming kernels */
+
+/* hash used by the router; host-callable */
+uint32_t smx_owner_hash(uint32_t x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

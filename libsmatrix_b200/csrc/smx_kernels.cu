@@ -1,0 +1,941 @@
+/*
+ * smx_kernels.cu — hand-written sm_100a kernels for the libsmatrix in-memory hot path and their
+ * extern "C" launchers.  No tensor cores: nothing on this path is a dense contraction; every
+ * kernel is bound by random 32-byte-sector HBM accesses (update / get) or by streaming HBM
+ * bandwidth (row growth, getrow), so the levers are sector-exact accesses (one 256-bit
+ * LDG per probe), enough resident threads to cover ~1 us dependent-miss chains, and atomics that
+ * resolve in L2.
+ *
+ * Kernel                replaces (reference src/smatrix.c)
+ *   k_upsert            smatrix_lookup(write) + cmap_lookup/insert + rmap_probe/insert + the
+ *                       value update of set/incr/decr  (:225-304, :343-380, :621-713)
+ *   k_grow_plan/migrate smatrix_rmap_resize (:383-416)
+ *   k_dir_rehash        smatrix_cmap_resize (:715-741)
+ *   k_get               smatrix_get (:174-185)
+ *   k_rowlen            smatrix_rowlen (:212-223)
+ *   k_row_counts/scan/getrow_fill   smatrix_getrow (:189-210) for whole batches of rows
+ *   k_set_max/commit    last-writer-wins resolution for smatrix_set batches (:225-234 applied
+ *                       sequentially)
+ *
+ * Concurrency rules the code relies on (DESIGN.md "Concurrency"):
+ *   - cells and directory entries are only ever claimed 0 -> key by a 64-bit CAS and keys never
+ *     change afterwards, so a stale "occupied by another key" view is always still true and a
+ *     stale "empty" view is corrected by the CAS; probing always tries cells in probe order.
+ *   - buckets move only in the k_migrate kernels and k_dir_rehash, which never run concurrently with k_upsert.
+ *   - no thread ever waits for another thread: anything that cannot complete (directory at its
+ *     load limit, bucket at its load limit) is appended to a retry list and the host grows the
+ *     structure between launches.
+ */
+#include "smx_internal.h"
+
+#ifdef SMX_HOSTSIM
+#include "hostsim.h"
+#include "cuda_runtime_api.h"
+#else
+#include <cuda_runtime.h>
+#define SMX_WARP 32
+#define SMX_LAUNCH(kern, grid, block, stream, ...) \
+  kern<<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+typedef unsigned long long ull;
+#define SMX_FULL 0xffffffffu
+#ifdef SMX_HOSTSIM
+#define SMX_BLOCK 1 /* sequential simulation: __syncthreads() is a no-op, so blocks have 1 thread */
+#else
+#define SMX_BLOCK (8 * SMX_WARP) /* 256 threads: 8 blocks/SM = 2048 resident threads */
+#endif
+
+enum { ST_OK = 0, ST_DEFER = 1, ST_LATE = 2 };
+enum { DIR_FOUND = 0, DIR_CREATED = 1, DIR_MISS = 2, DIR_FULL = 3 };
+
+/* ------------------------------------------------------------------------------------------
+ * small device helpers
+ * ---------------------------------------------------------------------------------------- */
+
+/* murmur3 finaliser: row ids are dense or strided in practice (SURVEY.md 8d scrambles them). */
+__host__ __device__ __forceinline__ uint32_t smx_mix_row(uint32_t x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+/* a different bijection for columns, so row and column placement are independent */
+__host__ __device__ __forceinline__ uint32_t smx_mix_col(uint32_t y) {
+  y ^= y >> 16; y *= 0x7feb352du; y ^= y >> 15; y *= 0x846ca68bu; y ^= y >> 16;
+  return y;
+}
+/* and a third one for the owner rank, independent of the directory position */
+__host__ __device__ __forceinline__ uint32_t smx_mix_owner(uint32_t x) {
+  x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+  return x;
+}
+__host__ __device__ __forceinline__ ull smx_splitmix64(ull z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+/* One 32-byte sector with a single 256-bit load that bypasses L1 (coherent at L2). */
+__device__ __forceinline__ void ld_sector(const void* p, ull c[4]) {
+#ifdef SMX_HOSTSIM
+  memcpy(c, p, 32);
+#else
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3])
+               : "l"(p)
+               : "memory");
+#endif
+}
+
+struct Hdr {
+  uint32_t key, meta;
+  ull slots;
+  uint32_t live, c0, t0inv, want;
+};
+__device__ __forceinline__ Hdr ld_hdr(const smx_row_t* e) {
+  ull c[4];
+  ld_sector(e, c);
+  Hdr h;
+  h.key = (uint32_t)c[0];
+  h.meta = (uint32_t)(c[0] >> 32);
+  h.slots = c[1];
+  h.live = (uint32_t)c[2];
+  h.c0 = (uint32_t)(c[2] >> 32);
+  h.t0inv = (uint32_t)c[3];
+  h.want = (uint32_t)(c[3] >> 32);
+  return h;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x % SMX_WARP; }
+
+/* warp-aggregated "give me a unique index": one atomic per converged group of threads */
+__device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {
+  unsigned m = __activemask();
+  uint32_t lane = lane_id();
+  int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ void agg_inc64(ull* ctr) {
+  unsigned m = __activemask();
+  if ((int)lane_id() == __ffs(m) - 1) atomicAdd(ctr, (ull)__popc(m));
+}
+
+/* the n-th distinct non-zero column of a row triggers one of the reference's row resizes
+ * (src/smatrix.c:346, 16 cells doubling) while column 0 is still uncounted: n = 2^j + 2, j >= 3 */
+__device__ __forceinline__ bool is_resize_count(uint32_t n) {
+  return n >= 10u && (((n - 2u) & (n - 3u)) == 0u);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * row directory: find or claim (replaces smatrix_cmap_lookup/probe/insert, :621-713)
+ * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int dir_find(const smx_view_t& V, uint32_t x, bool create,
+                                        smx_row_t** out, Hdr* hdr) {
+  const ull mask = V.dir_cap - 1;
+  ull pos = smx_mix_row(x) & mask;
+  for (ull step = 0; step < V.dir_cap; ++step, pos = (pos + 1) & mask) {
+    smx_row_t* e = V.dir + pos;
+    Hdr h = ld_hdr(e);
+    if (h.meta & SMX_META_USED) {
+      if (h.key == x) { *out = e; *hdr = h; return DIR_FOUND; }
+      continue;
+    }
+    if (!create) return DIR_MISS;
+    if (__ldcg(&V.ctl->dir_used) >= V.dir_limit) return DIR_FULL;
+    const ull fresh = (ull)x | ((ull)(SMX_META_USED | SMX_INLINE_LOG) << 32);
+    ull old = atomicCAS((ull*)e, 0ull, fresh);
+    if (old == 0ull) {
+      agg_inc64(&V.ctl->dir_used);
+      h.key = x; h.meta = SMX_META_USED | SMX_INLINE_LOG;
+      h.slots = 0; h.live = 0; h.c0 = 0; h.t0inv = 0; h.want = 0;
+      *out = e; *hdr = h;
+      return DIR_CREATED;
+    }
+    if ((uint32_t)old == x && ((old >> 32) & SMX_META_USED)) {
+      *out = e; *hdr = ld_hdr(e);
+      return DIR_FOUND;
+    }
+    /* somebody claimed it for another row: keep probing */
+  }
+  return create ? DIR_FULL : DIR_MISS;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * column bucket: find-or-claim + value update (replaces rmap_probe/insert, :343-380, and the
+ * arithmetic of set/incr/decr, :230,:241,:252)
+ * ---------------------------------------------------------------------------------------- */
+template <int OP>
+__device__ __forceinline__ void apply_value(uint32_t* vp, uint32_t v) {
+  if (OP == SMX_OP_INCR) atomicAdd(vp, v);
+  else if (OP == SMX_OP_DECR) atomicAdd(vp, 0u - v);
+  else *(volatile uint32_t*)vp = 0u;
+}
+
+/* returns true when done, false when the bucket is at its load limit (caller defers the op) */
+template <int OP>
+__device__ __forceinline__ bool slot_upsert(smx_row_t* e, const Hdr& h, uint32_t y, uint32_t v,
+                                            bool counts_col0) {
+  const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+  ull* base = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
+  const uint32_t nsec = 1u << (caplog - 2u);
+  const uint32_t limit = (caplog == SMX_INLINE_LOG) ? 4u : (1u << (caplog - 1u));
+  const uint32_t init = (OP == SMX_OP_INCR) ? v : (OP == SMX_OP_DECR) ? (0u - v) : 0u;
+  const ull fresh = (ull)y | ((ull)init << 32);
+  uint32_t s = smx_mix_col(y) & (nsec - 1u);
+  for (uint32_t probe = 0; probe < nsec; ++probe, s = (s + 1u) & (nsec - 1u)) {
+    ull* sec = base + 4ull * s;
+    ull c[4];
+    ld_sector(sec, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((uint32_t)c[k] == y) { /* y != 0, so this is a live cell of ours */
+        apply_value<OP>((uint32_t*)(sec + k) + 1, v);
+        return true;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c[k] != 0ull) continue;
+      if (h.live >= limit) return false;
+      ull old = atomicCAS(sec + k, 0ull, fresh);
+      if (old == 0ull) { /* new column */
+        uint32_t n = atomicAdd(&e->live, 1u) + 1u;
+        if (counts_col0 && is_resize_count(n)) atomicOr(&e->meta, SMX_META_D);
+        return true;
+      }
+      if ((uint32_t)old == y) {
+        apply_value<OP>((uint32_t*)(sec + k) + 1, v);
+        return true;
+      }
+      /* claimed for another column meanwhile: try the next cell in probe order */
+    }
+  }
+  return false;
+}
+
+/* read-only probe: value of column y (y != 0) or 0 */
+__device__ __forceinline__ uint32_t slot_find(const smx_row_t* e, const Hdr& h, uint32_t y,
+                                              uint32_t** where) {
+  const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+  const ull* base = (caplog == SMX_INLINE_LOG) ? (const ull*)e->inl : (const ull*)h.slots;
+  const uint32_t nsec = 1u << (caplog - 2u);
+  uint32_t s = smx_mix_col(y) & (nsec - 1u);
+  for (uint32_t probe = 0; probe < nsec; ++probe, s = (s + 1u) & (nsec - 1u)) {
+    const ull* sec = base + 4ull * s;
+    ull c[4];
+    ld_sector(sec, c);
+    bool hole = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if ((uint32_t)c[k] == y) {
+        if (where) *where = (uint32_t*)(sec + k) + 1;
+        return (uint32_t)(c[k] >> 32);
+      }
+      hole |= (c[k] == 0ull);
+    }
+    if (hole) break; /* cells fill in probe order and never empty again */
+  }
+  if (where) *where = nullptr;
+  return 0u;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K1+K2+K3: the update kernel
+ * ---------------------------------------------------------------------------------------- */
+template <int OP>
+__device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t& S, int pass,
+                                          uint32_t i, uint32_t x, uint32_t y, uint32_t v) {
+  smx_row_t* e;
+  Hdr h;
+  int r = dir_find(V, x, true, &e, &h);
+  if (r == DIR_FULL) {
+    agg_inc(&V.ctl->n_dirfull);
+    return ST_DEFER;
+  }
+  if (pass == SMX_PASS_COL0) {
+    apply_value<OP>(&e->c0, v);
+    /* column 0 of this row turns non-zero inside this batch: remember the first such op
+     * (rowlen depends on whether column 0 was non-zero at each virtual resize) */
+    if (v != 0u && !(h.meta & SMX_META_ZC)) {
+      atomicMax(&e->t0inv, ~i);
+      if (!(h.meta & SMX_META_T0P)) {
+        uint32_t old = atomicOr(&e->meta, SMX_META_T0P);
+        if (!(old & SMX_META_T0P)) S.t0rows[agg_inc(&V.ctl->n_t0)] = x;
+      }
+    }
+    return ST_OK;
+  }
+  if (pass == SMX_PASS_EARLY && (h.meta & SMX_META_T0P)) {
+    if (i > ~h.t0inv) return ST_LATE; /* ordered after column 0 became non-zero */
+  }
+  const bool counts_col0 = (pass == SMX_PASS_LATE) || (h.meta & SMX_META_ZC);
+  if (slot_upsert<OP>(e, h, y, v, counts_col0)) return ST_OK;
+  atomicAdd(&e->want, 1u);
+  if (!(h.meta & SMX_META_GROW)) {
+    uint32_t old = atomicOr(&e->meta, SMX_META_GROW);
+    if (!(old & SMX_META_GROW)) S.grow[agg_inc(&V.ctl->n_grow)] = (uint32_t)(e - V.dir);
+  }
+  return ST_DEFER;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* list, uint32_t m,
+         int preagg) {
+  const uint32_t lane = lane_id();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t m_up = (m + (SMX_WARP - 1)) / SMX_WARP * SMX_WARP; /* whole warps stay in the loop */
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m_up; j += stride) {
+    bool act = j < m;
+    uint32_t i = 0, x = 0, y = 0, v = 0;
+    if (act) {
+      i = list ? list[j] : j;
+      x = O.xs[i];
+      y = O.ys[i];
+      v = O.vs ? O.vs[i] : O.v_const;
+      if (!list) act = (pass == SMX_PASS_COL0) ? (y == 0u) : (y != 0u);
+    }
+    /* K1: collapse duplicate (x,y) keys inside the warp before they reach the table */
+    bool lead = act;
+    uint32_t vsum = v;
+    unsigned peers = 1u << lane;
+    if (preagg) {
+      const ull k64 = ((ull)x << 32) | (ull)y;
+      const unsigned valid = __ballot_sync(SMX_FULL, act);
+      peers = __match_any_sync(SMX_FULL, k64) & valid;
+      const bool dup = act && (peers != (1u << lane));
+      if (__any_sync(SMX_FULL, dup)) {
+        vsum = 0u;
+        for (int src = 0; src < SMX_WARP; ++src) { /* segmented sum, lanes are in input order */
+          uint32_t t = __shfl_sync(SMX_FULL, v, src);
+          if ((peers >> src) & 1u) vsum += t;
+        }
+        lead = act && ((uint32_t)(__ffs(peers) - 1) == lane);
+      }
+    }
+    int status = ST_OK;
+    if (lead) status = upsert_one<OP>(V, S, pass, i, x, y, vsum);
+    if (preagg) { /* members of a group share their leader's fate (retry / late pass) */
+      __syncwarp();
+      const int src = act ? (__ffs(peers) - 1) : (int)lane;
+      const int ls = __shfl_sync(SMX_FULL, status, src);
+      if (act && !lead) status = ls;
+    }
+    if (act && status == ST_DEFER) S.defer_out[agg_inc(&V.ctl->n_defer)] = i;
+    else if (act && status == ST_LATE) S.late[agg_inc(&V.ctl->n_late)] = i;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K7: row growth (replaces smatrix_rmap_resize, :383-416)
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
+  const uint32_t lane = lane_id();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_up = (n_grow + (SMX_WARP - 1)) / SMX_WARP * SMX_WARP;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_up; j += stride) {
+    const bool act = j < n_grow;
+    ull bytes = 0;
+    uint32_t entry = 0, newlog = 0, caplog = 0;
+    if (act) {
+      entry = S.grow[j];
+      Hdr h = ld_hdr(V.dir + entry);
+      caplog = h.meta & SMX_META_CAPLOG;
+      const ull need = 2ull * ((ull)h.live + (ull)h.want); /* load factor <= 1/2 after growth */
+      newlog = caplog + 1u;
+      if (newlog < SMX_MIN_SLAB_LOG) newlog = SMX_MIN_SLAB_LOG;
+      while ((1ull << newlog) < need && newlog < SMX_MAX_CAPLOG) ++newlog;
+      bytes = 8ull << newlog;
+    }
+    ull incl = bytes; /* inclusive warp scan */
+    for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+      ull t = __shfl_up_sync(SMX_FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const ull total = __shfl_sync(SMX_FULL, incl, SMX_WARP - 1);
+    ull base = 0;
+    if (lane == 0 && total) base = atomicAdd(&V.ctl->plan_bytes, total);
+    base = __shfl_sync(SMX_FULL, base, 0);
+    if (act) {
+      smx_plan_t p;
+      p.entry = entry;
+      p.newlog = newlog;
+      p.off = base + incl - bytes;
+      S.plan[j] = p;
+      if (caplog >= SMX_BIG_LOG) S.big[agg_inc(&V.ctl->n_big)] = j;
+    }
+  }
+}
+
+/* place a whole cell into a zeroed / partially filled bucket (keys are unique) */
+__device__ __forceinline__ void place_cell(ull* base, uint32_t caplog, ull cell) {
+  const uint32_t nsec = 1u << (caplog - 2u);
+  uint32_t s = smx_mix_col((uint32_t)cell) & (nsec - 1u);
+  for (uint32_t probe = 0; probe < nsec; ++probe, s = (s + 1u) & (nsec - 1u)) {
+    ull* sec = base + 4ull * s;
+    ull c[4];
+    ld_sector(sec, c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c[k] != 0ull) continue;
+      if (atomicCAS(sec + k, 0ull, cell) == 0ull) return;
+    }
+  }
+}
+
+__device__ __forceinline__ void finish_growth(smx_row_t* e, const Hdr& h, ull* nb, uint32_t newlog) {
+  e->slots = (ull)nb;
+  e->want = 0u;
+  e->meta = (h.meta & ~(SMX_META_CAPLOG | SMX_META_GROW)) | newlog;
+}
+
+/* one warp per growing row (old bucket < 2^SMX_BIG_LOG cells) */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
+  const uint32_t lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
+  const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
+  for (uint32_t j = warp; j < n_grow; j += nwarps) {
+    const smx_plan_t p = S.plan[j];
+    smx_row_t* e = V.dir + p.entry;
+    const Hdr h = ld_hdr(e);
+    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    if (caplog >= SMX_BIG_LOG) continue;
+    ull* ob = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
+    ull* nb = (ull*)(region + p.off);
+    const uint32_t cap = 1u << caplog;
+    for (uint32_t s = lane; s < cap; s += SMX_WARP) {
+      const ull c = ob[s];
+      if (c != 0ull) {
+        place_cell(nb, p.newlog, c);
+        ob[s] = 0ull; /* recycled buckets are always zero */
+      }
+    }
+    __syncwarp();
+    if (lane == 0) finish_growth(e, h, nb, p.newlog);
+  }
+}
+
+/* big rows: the whole grid (x) re-places one row (y) */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_migrate_big(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region) {
+  const smx_plan_t p = S.plan[S.big[big_first + blockIdx.y]];
+  smx_row_t* e = V.dir + p.entry;
+  const Hdr h = ld_hdr(e);
+  const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+  ull* ob = (ull*)h.slots;
+  ull* nb = (ull*)(region + p.off);
+  const ull cap = 1ull << caplog;
+  for (ull s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (ull)gridDim.x * blockDim.x) {
+    const ull c = ob[s];
+    if (c != 0ull) {
+      place_cell(nb, p.newlog, c);
+      ob[s] = 0ull;
+    }
+  }
+}
+__global__ void k_migrate_big_finish(smx_view_t V, smx_lists_t S, uint32_t n_big, char* region) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_big; b += gridDim.x * blockDim.x) {
+    const smx_plan_t p = S.plan[S.big[b]];
+    smx_row_t* e = V.dir + p.entry;
+    const Hdr h = ld_hdr(e);
+    finish_growth(e, h, (ull*)(region + p.off), p.newlog);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * directory growth (replaces smatrix_cmap_resize, :715-741): re-place every entry into `to`
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SMX_BLOCK) k_dir_rehash(smx_view_t from, smx_view_t to) {
+  const ull mask = to.dir_cap - 1;
+  ull moved = 0;
+  for (ull pos = blockIdx.x * blockDim.x + threadIdx.x; pos < from.dir_cap;
+       pos += (ull)gridDim.x * blockDim.x) {
+    const smx_row_t* o = from.dir + pos;
+    ull a[4], b[4];
+    ld_sector(o, a);
+    if (!((a[0] >> 32) & SMX_META_USED)) continue;
+    ld_sector((const char*)o + 32, b);
+    ull q = smx_mix_row((uint32_t)a[0]) & mask;
+    for (;;) {
+      ull* dst = (ull*)(to.dir + q);
+      if (atomicCAS(dst, 0ull, a[0]) == 0ull) {
+        dst[1] = a[1]; dst[2] = a[2]; dst[3] = a[3];
+        dst[4] = b[0]; dst[5] = b[1]; dst[6] = b[2]; dst[7] = b[3];
+        break;
+      }
+      q = (q + 1) & mask;
+    }
+    ++moved;
+  }
+  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) moved += __shfl_xor_sync(SMX_FULL, moved, d);
+  if (lane_id() == 0 && moved) atomicAdd(&to.ctl->dir_used, moved);
+}
+
+/* end of a chunk: column 0 of these rows is now (and stays) non-zero */
+__global__ void k_finalize_t0(smx_view_t V, const uint32_t* t0rows, uint32_t n) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    if (dir_find(V, t0rows[j], false, &e, &h) != DIR_FOUND) continue;
+    e->t0inv = 0u;
+    e->meta = (h.meta & ~SMX_META_T0P) | SMX_META_ZC;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * set: last writer in input order wins.  After k_upsert<SETZERO> created every cell and stored
+ * 0 in it, k_set_max leaves max(i)+1 in the cell and k_set_commit lets that op store its value.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SMX_BLOCK) k_set_max(smx_view_t V, smx_ops_t O, ull* addrs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t* vp = nullptr;
+    if (dir_find(V, O.xs[i], false, &e, &h) == DIR_FOUND) {
+      const uint32_t y = O.ys[i];
+      if (y == 0u) vp = &e->c0;
+      else slot_find(e, h, y, &vp);
+    }
+    if (vp) atomicMax(vp, i + 1u);
+    addrs[i] = (ull)vp;
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK) k_set_commit(smx_ops_t O, const ull* addrs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x) {
+    uint32_t* vp = (uint32_t*)addrs[i];
+    if (vp && __ldcg(vp) == i + 1u) *vp = O.vs ? O.vs[i] : O.v_const;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K4 / K5: point reads
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_get(smx_view_t V, const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t val = 0u;
+    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) {
+      const uint32_t y = ys[i];
+      val = (y == 0u) ? h.c0 : slot_find(e, h, y, nullptr);
+    }
+    out[i] = val;
+  }
+}
+
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_rowlen(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t len = 0u;
+    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND)
+      len = h.live + ((h.meta & SMX_META_D) ? 1u : 0u); /* the reference's `used` (Q1) */
+    out[i] = len;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K6: getrow for a batch of rows -> CSR
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_row_counts(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* counts) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t c = 0u;
+    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) c = h.live + (h.c0 != 0u ? 1u : 0u);
+    counts[i] = c;
+  }
+}
+
+#define SCAN_PER_THREAD 8
+#define SCAN_TILE (SMX_BLOCK * SCAN_PER_THREAD)
+
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_scan_tile_sums(const uint32_t* counts, uint32_t n, ull* tile_sums) {
+  __shared__ ull sh[SMX_BLOCK];
+  const ull first = (ull)blockIdx.x * SCAN_TILE + (ull)threadIdx.x * SCAN_PER_THREAD;
+  ull s = 0;
+  for (int k = 0; k < SCAN_PER_THREAD; ++k)
+    if (first + k < n) s += counts[first + k];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ull t = 0;
+    for (uint32_t k = 0; k < blockDim.x; ++k) t += sh[k];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+/* one block: exclusive scan of the tile sums, total goes to offsets[n] */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_scan_tiles(ull* tile_sums, uint32_t n_tiles, ull base, ull* offsets, uint32_t n) {
+  __shared__ ull sh[SMX_BLOCK];
+  __shared__ ull carry;
+  if (threadIdx.x == 0) carry = base;
+  __syncthreads();
+  for (uint32_t t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
+    const uint32_t t = t0 + threadIdx.x;
+    sh[threadIdx.x] = (t < n_tiles) ? tile_sums[t] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ull run = carry;
+      for (uint32_t k = 0; k < blockDim.x; ++k) {
+        ull v = sh[k];
+        sh[k] = run;
+        run += v;
+      }
+      carry = run;
+    }
+    __syncthreads();
+    if (t < n_tiles) tile_sums[t] = sh[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry;
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_scan_apply(const uint32_t* counts, uint32_t n, const ull* tile_sums, ull* offsets) {
+  __shared__ ull sh[SMX_BLOCK];
+  const ull first = (ull)blockIdx.x * SCAN_TILE + (ull)threadIdx.x * SCAN_PER_THREAD;
+  uint32_t c[SCAN_PER_THREAD];
+  ull s = 0;
+  for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+    c[k] = (first + k < n) ? counts[first + k] : 0u;
+    s += c[k];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ull run = tile_sums[blockIdx.x];
+    for (uint32_t k = 0; k < blockDim.x; ++k) {
+      ull v = sh[k];
+      sh[k] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  ull run = sh[threadIdx.x];
+  for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+    if (first + k < n) offsets[first + k] = run;
+    run += c[k];
+  }
+}
+
+/* one warp per row: 16-byte loads, ballot-free warp prefix over per-lane live counts */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, ull bias,
+              uint32_t* pairs) {
+  const uint32_t lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
+  const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
+  for (uint32_t i = warp; i < n; i += nwarps) {
+    smx_row_t* e;
+    Hdr h;
+    if (dir_find(V, xs[i], false, &e, &h) != DIR_FOUND) continue;
+    ull* out = (ull*)pairs + (offsets[i] - bias);
+    ull pos = 0;
+    if (h.c0 != 0u) {
+      if (lane == 0) out[0] = (ull)h.c0 << 32; /* (column 0, c0) */
+      pos = 1;
+    }
+    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    const ull* base = (caplog == SMX_INLINE_LOG) ? (const ull*)e->inl : (const ull*)h.slots;
+    const ull cap = 1ull << caplog;
+    for (ull s0 = 0; s0 < cap; s0 += 2ull * SMX_WARP) {
+      const ull s = s0 + 2ull * lane;
+      ull a = 0, b = 0;
+      if (s < cap) { /* cap is a multiple of 4, s is even: both cells are in range */
+        a = base[s];
+        b = base[s + 1];
+      }
+      const uint32_t mine = (a != 0ull) + (b != 0ull);
+      uint32_t incl = mine;
+      for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+        uint32_t t = __shfl_up_sync(SMX_FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const uint32_t total = __shfl_sync(SMX_FULL, incl, SMX_WARP - 1);
+      ull w = pos + incl - mine;
+      if (a != 0ull) out[w++] = a;
+      if (b != 0ull) out[w] = b;
+      pos += total;
+    }
+  }
+}
+
+/* nnz = sum over rows of live + (c0 != 0) -> ctl->scratch */
+__global__ void __launch_bounds__(SMX_BLOCK) k_count_nnz(smx_view_t V) {
+  ull acc = 0;
+  for (ull pos = blockIdx.x * blockDim.x + threadIdx.x; pos < V.dir_cap;
+       pos += (ull)gridDim.x * blockDim.x) {
+    Hdr h = ld_hdr(V.dir + pos);
+    if (h.meta & SMX_META_USED) acc += (ull)h.live + (h.c0 != 0u ? 1ull : 0ull);
+  }
+  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(SMX_FULL, acc, d);
+  if (lane_id() == 0 && acc) atomicAdd(&V.ctl->scratch, acc);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * synthetic streams and roofline probes
+ * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void c2_op(ull seed, ull i, uint32_t rows, uint32_t ycols, uint32_t* x,
+                                      uint32_t* y) {
+  const ull r = smx_splitmix64(seed + i);
+  *x = (uint32_t)((r >> 32) % rows) * 2654435761u;
+  *y = 1u + (uint32_t)(r & 0xFFFFFFFFull) % ycols;
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gen_c2_ops(ull seed, ull first, ull count, uint32_t rows, uint32_t ycols, uint32_t* xs,
+             uint32_t* ys) {
+  for (ull i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (ull)gridDim.x * blockDim.x)
+    c2_op(seed, first + i, rows, ycols, &xs[i], &ys[i]);
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gen_c2_queries(ull seed_get, ull seed_build, ull first, ull count, ull n_build, uint32_t rows,
+                 uint32_t ycols, uint32_t* xs, uint32_t* ys) {
+  for (ull i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (ull)gridDim.x * blockDim.x) {
+    const ull j = first + i;
+    const ull k = smx_splitmix64(seed_get + j) % n_build;
+    uint32_t x, y;
+    c2_op(seed_build, k, rows, ycols, &x, &y);
+    if (j & 1ull) y += ycols;
+    xs[i] = x;
+    ys[i] = y;
+  }
+}
+
+/* random reads of `width` bytes at width-aligned addresses; 4 independent loads in flight */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_probe_read(const char* buf, ull n_units, ull accesses, int width, smx_ctl_t* ctl) {
+  ull acc = 0;
+  const ull tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const ull nth = (ull)gridDim.x * blockDim.x;
+  for (ull a = tid; a < accesses; a += nth) {
+    const ull u = smx_splitmix64(a) % n_units;
+    const char* p = buf + u * (ull)width;
+    if (width == 32) {
+      ull c[4];
+      ld_sector(p, c);
+      acc ^= c[0] ^ c[1] ^ c[2] ^ c[3];
+    } else if (width == 16) {
+      const ull* q = (const ull*)p;
+      acc ^= __ldcg(q) ^ __ldcg(q + 1);
+    } else if (width == 8) {
+      acc ^= __ldcg((const ull*)p);
+    } else {
+      acc ^= __ldcg((const uint32_t*)p);
+    }
+  }
+  if (acc == 0x123456789abcdefull) atomicAdd(&ctl->scratch, acc); /* keep the loads alive */
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_probe_atomic(uint32_t* buf, ull n_words, ull accesses) {
+  const ull tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const ull nth = (ull)gridDim.x * blockDim.x;
+  for (ull a = tid; a < accesses; a += nth) atomicAdd(buf + smx_splitmix64(a) % n_words, 1u);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K8: owner-rank bucketing for the multi-GPU router
+ * ---------------------------------------------------------------------------------------- */
+#define SMX_MAX_WORLD 64
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, ull* counts) {
+  __shared__ uint32_t hist[SMX_MAX_WORLD];
+  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    atomicAdd(&hist[smx_mix_owner(xs[i]) % world], 1u);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
+    if (hist[k]) atomicAdd(&counts[k], (ull)hist[k]);
+}
+/* each block reserves a contiguous range per owner, then scatters; order inside an owner's
+ * segment is not the input order (fine for incr/decr/get, see DESIGN.md "Multi-GPU") */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
+                    uint32_t world, ull* cursors, uint32_t* oxs, uint32_t* oys, uint32_t* ovs,
+                    uint32_t* osrc) {
+  __shared__ uint32_t hist[SMX_MAX_WORLD];
+  __shared__ ull start[SMX_MAX_WORLD];
+  const uint32_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t lo = blockIdx.x * per_block;
+  const uint32_t hi = (lo + per_block < n) ? lo + per_block : n;
+  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+    atomicAdd(&hist[smx_mix_owner(xs[i]) % world], 1u);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) {
+    start[k] = hist[k] ? atomicAdd(&cursors[k], (ull)hist[k]) : 0ull;
+    hist[k] = 0u;
+  }
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint32_t x = xs[i];
+    const uint32_t o = smx_mix_owner(x) % world;
+    const ull at = start[o] + atomicAdd(&hist[o], 1u);
+    oxs[at] = x;
+    if (ys) oys[at] = ys[i];
+    if (vs) ovs[at] = vs[i];
+    if (osrc) osrc[at] = i;
+  }
+}
+
+/* ==========================================================================================
+ * launchers
+ * ======================================================================================== */
+static int g_blocks = 0;
+extern "C" int smx_grid_blocks(void) {
+  if (!g_blocks) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    g_blocks = sms * 8; /* 8 x 256 threads = 2048 resident threads per SM */
+  }
+  return g_blocks;
+}
+static inline uint32_t grid_for(ull items) {
+  ull want = (items + SMX_BLOCK - 1) / SMX_BLOCK;
+  ull cap = (ull)smx_grid_blocks();
+  if (want < 1) want = 1;
+  return (uint32_t)(want < cap ? want : cap);
+}
+
+extern "C" void smx_launch_upsert(smx_stream_t st, smx_view_t v, smx_ops_t ops, smx_lists_t l,
+                                  int op, int pass, const uint32_t* list, uint32_t m,
+                                  int preaggregate) {
+  if (m == 0) return;
+  const uint32_t grid = grid_for(m);
+  const int pre = (preaggregate && !list && pass == SMX_PASS_EARLY && SMX_WARP > 1) ? 1 : 0;
+  if (op == SMX_OP_INCR) {
+    auto k = k_upsert<SMX_OP_INCR>;
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, v, ops, l, pass, list, m, pre);
+  } else if (op == SMX_OP_DECR) {
+    auto k = k_upsert<SMX_OP_DECR>;
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, v, ops, l, pass, list, m, pre);
+  } else {
+    auto k = k_upsert<SMX_OP_SETZERO>;
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, v, ops, l, pass, list, m, pre);
+  }
+}
+
+extern "C" void smx_launch_grow_plan(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_grow) {
+  if (!n_grow) return;
+  SMX_LAUNCH(k_grow_plan, grid_for(n_grow), SMX_BLOCK, st, v, l, n_grow);
+}
+
+extern "C" void smx_launch_migrate(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_grow,
+                                   uint32_t n_big, void* region) {
+  if (!n_grow) return;
+  SMX_LAUNCH(k_migrate, grid_for((ull)n_grow * SMX_WARP), SMX_BLOCK, st, v, l, n_grow, (char*)region);
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? 64u : 2u, cnt, 1u);
+    SMX_LAUNCH(k_migrate_big, grid, SMX_BLOCK, st, v, l, first, (char*)region);
+  }
+  if (n_big) SMX_LAUNCH(k_migrate_big_finish, grid_for(n_big), SMX_BLOCK, st, v, l, n_big, (char*)region);
+}
+
+extern "C" void smx_launch_dir_rehash(smx_stream_t st, smx_view_t from, smx_view_t to) {
+  SMX_LAUNCH(k_dir_rehash, grid_for(from.dir_cap), SMX_BLOCK, st, from, to);
+}
+
+extern "C" void smx_launch_finalize_t0(smx_stream_t st, smx_view_t v, const uint32_t* t0rows,
+                                       uint32_t n) {
+  if (!n) return;
+  SMX_LAUNCH(k_finalize_t0, grid_for(n), SMX_BLOCK, st, v, t0rows, n);
+}
+
+extern "C" void smx_launch_set_max(smx_stream_t st, smx_view_t v, smx_ops_t ops, uint64_t* addrs) {
+  if (!ops.n) return;
+  SMX_LAUNCH(k_set_max, grid_for(ops.n), SMX_BLOCK, st, v, ops, (ull*)addrs);
+}
+extern "C" void smx_launch_set_commit(smx_stream_t st, smx_ops_t ops, const uint64_t* addrs) {
+  if (!ops.n) return;
+  SMX_LAUNCH(k_set_commit, grid_for(ops.n), SMX_BLOCK, st, ops, (const ull*)addrs);
+}
+
+extern "C" void smx_launch_get(smx_stream_t st, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
+                               uint32_t n, uint32_t* out) {
+  if (!n) return;
+  SMX_LAUNCH(k_get, grid_for(n), SMX_BLOCK, st, v, xs, ys, n, out);
+}
+extern "C" void smx_launch_rowlen(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
+                                  uint32_t* out) {
+  if (!n) return;
+  SMX_LAUNCH(k_rowlen, grid_for(n), SMX_BLOCK, st, v, xs, n, out);
+}
+extern "C" void smx_launch_row_counts(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
+                                      uint32_t* counts) {
+  if (!n) return;
+  SMX_LAUNCH(k_row_counts, grid_for(n), SMX_BLOCK, st, v, xs, n, counts);
+}
+
+extern "C" uint32_t smx_scan_scratch_items(uint32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+extern "C" void smx_launch_scan(smx_stream_t st, const uint32_t* counts, uint32_t n, uint64_t base,
+                                uint64_t* offsets, uint64_t* tile_sums) {
+  const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (tiles) SMX_LAUNCH(k_scan_tile_sums, tiles, SMX_BLOCK, st, counts, n, (ull*)tile_sums);
+  SMX_LAUNCH(k_scan_tiles, 1, SMX_BLOCK, st, (ull*)tile_sums, tiles, (ull)base, (ull*)offsets, n);
+  if (tiles) SMX_LAUNCH(k_scan_apply, tiles, SMX_BLOCK, st, counts, n, (const ull*)tile_sums, (ull*)offsets);
+}
+
+extern "C" void smx_launch_getrow_fill(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
+                                       const uint64_t* offsets, uint64_t bias, uint32_t* pairs) {
+  if (!n) return;
+  SMX_LAUNCH(k_getrow_fill, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, xs, n,
+             (const ull*)offsets, (ull)bias, pairs);
+}
+
+extern "C" void smx_launch_count_nnz(smx_stream_t st, smx_view_t v) {
+  SMX_LAUNCH(k_count_nnz, grid_for(v.dir_cap), SMX_BLOCK, st, v);
+}
+
+extern "C" void smx_launch_gen_c2_ops(smx_stream_t st, uint64_t seed, uint64_t first, uint64_t count,
+                                      uint32_t rows, uint32_t ycols, uint32_t* xs, uint32_t* ys) {
+  if (!count) return;
+  SMX_LAUNCH(k_gen_c2_ops, grid_for(count), SMX_BLOCK, st, (ull)seed, (ull)first, (ull)count, rows,
+             ycols, xs, ys);
+}
+extern "C" void smx_launch_gen_c2_queries(smx_stream_t st, uint64_t seed_get, uint64_t seed_build,
+                                          uint64_t first, uint64_t count, uint64_t n_build,
+                                          uint32_t rows, uint32_t ycols, uint32_t* xs, uint32_t* ys) {
+  if (!count) return;
+  SMX_LAUNCH(k_gen_c2_queries, grid_for(count), SMX_BLOCK, st, (ull)seed_get, (ull)seed_build,
+             (ull)first, (ull)count, (ull)n_build, rows, ycols, xs, ys);
+}
+
+extern "C" void smx_launch_probe_read(smx_stream_t st, const void* buf, uint64_t n_units,
+                                      uint64_t accesses, int width, smx_ctl_t* ctl) {
+  SMX_LAUNCH(k_probe_read, grid_for(accesses), SMX_BLOCK, st, (const char*)buf, (ull)n_units,
+             (ull)accesses, width, ctl);
+}
+extern "C" void smx_launch_probe_atomic(smx_stream_t st, uint32_t* buf, uint64_t n_words,
+                                        uint64_t accesses) {
+  SMX_LAUNCH(k_probe_atomic, grid_for(accesses), SMX_BLOCK, st, buf, (ull)n_words, (ull)accesses);
+}
+
+extern "C" void smx_launch_partition_count(smx_stream_t st, const uint32_t* xs, uint32_t n,
+                                           uint32_t world, unsigned long long* counts) {
+  if (!n) return;
+  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, n, world, counts);
+}
+extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs, const uint32_t* ys,
+                                             const uint32_t* vs, uint32_t n, uint32_t world,
+                                             unsigned long long* cursors, uint32_t* oxs,
+                                             uint32_t* oys, uint32_t* ovs, uint32_t* osrc) {
+  if (!n) return;
+  SMX_LAUNCH(k_partition_scatter, grid_for(n), SMX_BLOCK, st, xs, ys, vs, n, world, cursors, oxs,
+             oys, ovs, osrc);
+}
+
+extern "C" uint32_t smx_owner_hash(uint32_t x) { return smx_mix_owner(x); }

@@ -1,0 +1,219 @@
+"""SparseMatrix — the host-side mirror of the reference's binding classes over the C-ABI.
+
+Method names and argument meaning follow the reference's Java class
+(src/java/com/paulasmuth/libsmatrix/SparseMatrix.java:17-146: get/set/incr/decr/getRowLength/
+getRow(x[, maxlen])/close/getFilename) and Ruby class (src/smatrix_ruby.c:166-174:
+get/set/incr/decr returning the new value), so the parity tests read like the reference's own
+TestSparseMatrix.java.  The `*_batch` methods call the batched C-ABI entry points; they accept
+numpy arrays (host pointers) or CUDA torch tensors (device pointers, zero-copy).
+
+No computation happens here: every method is one call into libsmatrix_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import binding
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+class SparseMatrix:
+    def __init__(self, file_path: str | None = None, device: int | None = None,
+                 _lib_path: str | None = None):
+        self._lib = binding.load(_lib_path)
+        self.filename = file_path
+        fname = file_path.encode() if file_path is not None else None
+        if device is None:
+            self._h = self._lib.smatrix_open(fname)
+        else:
+            self._h = self._lib.smatrix_b200_open(fname, int(device))
+        if not self._h:
+            # src/smatrix_jni.c:61-62 turns a NULL handle into IllegalArgumentException
+            raise ValueError("smatrix_open() failed")
+
+    # ---- handle plumbing -------------------------------------------------------------------
+    def _handle(self):
+        if not self._h:
+            # src/smatrix_jni.c:15 ERR_PTRNOTFOUND
+            raise ValueError("can't find native object. maybe close() was already called")
+        return self._h
+
+    def close(self):
+        if self._h:
+            self._lib.smatrix_close(self._h)
+            self._h = None
+
+    def __del__(self):  # src/smatrix_ruby.c:157-164: the GC finalizer closes the matrix
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def getFilename(self):
+        return self.filename
+
+    # ---- the reference API -----------------------------------------------------------------
+    def get(self, x: int, y: int) -> int:
+        return self._lib.smatrix_get(self._handle(), x & 0xFFFFFFFF, y & 0xFFFFFFFF)
+
+    def set(self, x: int, y: int, val: int) -> int:
+        return self._lib.smatrix_set(self._handle(), x & 0xFFFFFFFF, y & 0xFFFFFFFF, val & 0xFFFFFFFF)
+
+    def incr(self, x: int, y: int, val: int) -> int:
+        return self._lib.smatrix_incr(self._handle(), x & 0xFFFFFFFF, y & 0xFFFFFFFF, val & 0xFFFFFFFF)
+
+    def decr(self, x: int, y: int, val: int) -> int:
+        return self._lib.smatrix_decr(self._handle(), x & 0xFFFFFFFF, y & 0xFFFFFFFF, val & 0xFFFFFFFF)
+
+    def getRowLength(self, x: int) -> int:
+        return self._lib.smatrix_rowlen(self._handle(), x & 0xFFFFFFFF)
+
+    rowlen = getRowLength
+
+    def getrow_raw(self, x: int, ret_len_bytes: int, slack_pairs: int = 2) -> np.ndarray:
+        """The literal smatrix_getrow call with a `ret_len_bytes` buffer -> (n, 2) pairs."""
+        buf = np.zeros(2 * (ret_len_bytes // 8 + slack_pairs + 1), dtype=np.uint32)
+        n = self._lib.smatrix_getrow(self._handle(), x & 0xFFFFFFFF, buf.ctypes.data, ret_len_bytes)
+        return buf[: 2 * n].reshape(-1, 2).copy()
+
+    def getRow(self, x: int, maxlen: int = 0) -> dict[int, int]:
+        """Like src/smatrix_jni.c:114-149: rowlen -> buffer -> getrow -> (truncated) sorted map."""
+        pairs = self.getrow_raw(x, (self.getRowLength(x) + 2) * 8)
+        if maxlen > 0:
+            pairs = pairs[:maxlen]
+        return dict(sorted((int(k), int(v)) for k, v in pairs))
+
+    # ---- batched entry points --------------------------------------------------------------
+    @staticmethod
+    def _arg(a, keep: list):
+        """-> raw pointer (int) of a uint32 numpy array (host) or CUDA/CPU torch tensor."""
+        if a is None:
+            return None
+        if _is_torch(a):
+            import torch
+            if a.dtype not in (torch.int32, torch.uint32):
+                raise TypeError("torch batch arrays must be int32/uint32")
+            a = a.contiguous()
+            keep.append(a)
+            return a.data_ptr()
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        keep.append(a)
+        return a.ctypes.data
+
+    def _write(self, fn, xs, ys, vals):
+        keep: list = []
+        px, py, pv = self._arg(xs, keep), self._arg(ys, keep), self._arg(vals, keep)
+        n = len(keep[0]) if not _is_torch(keep[0]) else keep[0].numel()
+        fn(self._handle(), px, py, pv, n)
+
+    def incr_batch(self, xs, ys, vals=None):
+        self._write(self._lib.smatrix_incr_batch, xs, ys, vals)
+
+    def decr_batch(self, xs, ys, vals=None):
+        self._write(self._lib.smatrix_decr_batch, xs, ys, vals)
+
+    def set_batch(self, xs, ys, vals=None):
+        self._write(self._lib.smatrix_set_batch, xs, ys, vals)
+
+    def get_batch(self, xs, ys, out=None):
+        keep: list = []
+        px, py = self._arg(xs, keep), self._arg(ys, keep)
+        if _is_torch(keep[0]):
+            import torch
+            n = keep[0].numel()
+            if out is None:
+                out = torch.empty(n, dtype=torch.int32, device=keep[0].device)
+            po = out.data_ptr()
+        else:
+            n = len(keep[0])
+            if out is None:
+                out = np.empty(n, dtype=np.uint32)
+            po = out.ctypes.data
+        self._lib.smatrix_get_batch(self._handle(), px, py, n, po)
+        return out
+
+    def rowlen_batch(self, xs):
+        keep: list = []
+        px = self._arg(xs, keep)
+        if _is_torch(keep[0]):
+            import torch
+            out = torch.empty(keep[0].numel(), dtype=torch.int32, device=keep[0].device)
+            self._lib.smatrix_rowlen_batch(self._handle(), px, keep[0].numel(), out.data_ptr())
+            return out
+        out = np.empty(len(keep[0]), dtype=np.uint32)
+        self._lib.smatrix_rowlen_batch(self._handle(), px, len(keep[0]), out.ctypes.data)
+        return out
+
+    def getrow_batch(self, xs):
+        """-> (offsets[n+1] uint64, pairs[total, 2] uint32), host arrays; rows in table order."""
+        keep: list = []
+        px = self._arg(np.asarray(xs) if not _is_torch(xs) else xs.cpu().numpy(), keep)
+        n = len(keep[0])
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        total = self._lib.smatrix_getrow_batch(self._handle(), px, n, offsets.ctypes.data, None, 0)
+        pairs = np.zeros((int(total), 2), dtype=np.uint32)
+        if total:
+            got = self._lib.smatrix_getrow_batch(self._handle(), px, n, offsets.ctypes.data,
+                                                 pairs.ctypes.data, int(total))
+            assert got == total
+        return offsets, pairs
+
+    # ---- device controls (include/smatrix_b200.h) --------------------------------------------
+    def stat(self, name: str) -> int:
+        return int(self._lib.smatrix_b200_stat(self._handle(), binding.STAT[name]))
+
+    def sync(self):
+        self._lib.smatrix_b200_sync(self._handle())
+
+    def timer_start(self):
+        self._lib.smatrix_b200_timer_start(self._handle())
+
+    def timer_stop_ms(self) -> float:
+        return float(self._lib.smatrix_b200_timer_stop_ms(self._handle()))
+
+    def set_kernel_timing(self, on: bool):
+        self._lib.smatrix_b200_set_kernel_timing(self._handle(), 1 if on else 0)
+
+    @property
+    def device(self) -> int:
+        return int(self._lib.smatrix_b200_device(self._handle()))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.smatrix_b200_stream(self._handle()) or 0)
+
+    def dev_alloc(self, nbytes: int) -> int:
+        return int(self._lib.smatrix_b200_dev_alloc(self._handle(), nbytes))
+
+    def dev_free(self, ptr: int):
+        self._lib.smatrix_b200_dev_free(self._handle(), ptr)
+
+    def memcpy(self, dst: int, src: int, nbytes: int):
+        self._lib.smatrix_b200_memcpy(self._handle(), dst, src, nbytes)
+
+    def gen_c2_ops(self, seed, first, count, rows, ycols, d_xs: int, d_ys: int):
+        self._lib.smatrix_b200_gen_c2_ops(self._handle(), seed, first, count, rows, ycols, d_xs, d_ys)
+
+    def gen_c2_queries(self, seed_get, seed_build, first, count, n_build, rows, ycols, d_xs: int,
+                       d_ys: int):
+        self._lib.smatrix_b200_gen_c2_queries(self._handle(), seed_get, seed_build, first, count,
+                                              n_build, rows, ycols, d_xs, d_ys)
+
+    def probe_random_read(self, footprint_bytes: int, accesses: int, width: int = 32) -> float:
+        return float(self._lib.smatrix_b200_probe_random_read(self._handle(), footprint_bytes,
+                                                              accesses, width))
+
+    def probe_random_atomic(self, footprint_bytes: int, accesses: int) -> float:
+        return float(self._lib.smatrix_b200_probe_random_atomic(self._handle(), footprint_bytes,
+                                                                accesses))

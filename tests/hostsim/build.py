@@ -1,0 +1,35 @@
+"""TEST SCAFFOLDING ONLY: compile the host shim and the kernel file with gcc/g++ against the
+malloc-backed fake runtime (hostsim.h) into tests/hostsim/libsmatrix_hostsim.so.  Used by the
+`-m "not gpu"` tests to check host LOGIC; never built by build(), never loaded by the package."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "libsmatrix_b200", "csrc")
+SO = os.path.join(HERE, "libsmatrix_hostsim.so")
+
+
+def build() -> str:
+    srcs = [os.path.join(CSRC, "smx_kernels.cu"), os.path.join(CSRC, "smx_host.c"),
+            os.path.join(HERE, "fake_runtime.cpp"), os.path.join(HERE, "hostsim.h"),
+            os.path.join(CSRC, "smx_internal.h")]
+    if os.path.exists(SO) and all(os.path.getmtime(s) < os.path.getmtime(SO) for s in srcs):
+        return SO
+    common = ["-O1", "-g", "-fPIC", "-DSMX_HOSTSIM", f"-I{HERE}", f"-I{CSRC}", "-Wall",
+              "-Wno-unknown-pragmas", "-Wno-unused-function"]
+    objs = []
+    for src, cc, extra in ((srcs[0], "g++", ["-x", "c++", "-std=c++17"]),
+                           (srcs[1], "gcc", ["-std=gnu11"]),
+                           (srcs[2], "g++", ["-std=c++17"])):
+        o = os.path.join(HERE, os.path.basename(src) + ".o")
+        subprocess.run([cc] + common + extra + ["-c", src, "-o", o], check=True)
+        objs.append(o)
+    # -Bsymbolic: the fake cuda* symbols must bind inside this library even when a real
+    # libcudart is already loaded in the process (torch)
+    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", SO] + objs + ["-lpthread"], check=True)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build())

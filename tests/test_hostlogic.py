@@ -1,0 +1,97 @@
+"""CPU tests of the HOST LOGIC (round loop, growth, chunking, column-0 phases, set resolution,
+CSR assembly) — the C shim and the kernel sources compiled by gcc/g++ against the serial
+simulator in tests/hostsim/ (warp width 1, one-thread blocks).  This checks logic only; the
+parity tests proper are tests/test_gpu_parity.py on the real CUDA build."""
+import os
+
+import pytest
+
+import parity_suite as ps
+from libsmatrix_b200 import SparseMatrix
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from hostsim import build as hb
+    return hb.build()
+
+
+@pytest.fixture(params=[(6, 1 << 26), (10, 3000), (4, 777)], ids=["dir64", "chunk3000", "dir16-chunk777"])
+def make(request, sim, monkeypatch):
+    dir_log2, chunk = request.param
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", str(dir_log2))   # tiny directory: growth on every test
+    monkeypatch.setenv("SMATRIX_CHUNK", str(chunk))         # small chunks: multi-chunk batches
+    return lambda: SparseMatrix(_lib_path=sim)
+
+
+def test_java_cases(make):
+    ps.scenario_java_cases(make, grid=120)
+
+
+def test_single_op_api(make):
+    ps.scenario_single_op_api(make)
+
+
+def test_example_program(make):
+    ps.scenario_example_program(make)
+
+
+def test_quirks(make):
+    ps.scenario_quirks(make)
+
+
+def test_empty_and_ragged(make):
+    ps.scenario_empty_and_ragged(make)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_streams(make, seed):
+    ps.scenario_random(make, seed, n=8000, n_rows=80, n_cols=70, rounds=4)
+
+
+def test_set_last_writer(make):
+    ps.scenario_set_last_writer(make)
+
+
+def test_hot_keys(make):
+    ps.scenario_hot_keys(make)
+
+
+def test_cf(make):
+    ps.scenario_cf(make, n_baskets=600, n_items=150)
+
+
+def test_col0_ordering(make):
+    ps.scenario_col0_ordering(make)
+
+
+def test_big_row(make):
+    ps.scenario_big_row(make, n_cols=20000)
+
+
+def test_many_rows(make):
+    ps.scenario_many_rows(make, 5000)
+
+
+def test_model_crosscheck(make):
+    ps.scenario_model_crosscheck(make)
+
+
+def test_threads_single_ops(make):
+    ps.scenario_threads_single_ops(make, per_thread=100)
+
+
+def test_golden_fixtures(make):
+    import numpy as np
+    from oracle import cpu
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for f in sorted(x for x in os.listdir(gdir) if x.endswith(".npz")):
+        g = np.load(os.path.join(gdir, f))
+        m = make()
+        for k in range(int(g["n_batches"])):
+            getattr(m, str(g[f"op{k}"]) + "_batch")(g[f"xs{k}"], g[f"ys{k}"], g[f"vs{k}"])
+        assert (np.asarray(m.get_batch(g["qx"], g["qy"])) == g["get"]).all(), f
+        assert (np.asarray(m.rowlen_batch(g["rows"])) == g["rowlen"]).all(), f
+        o, p = m.getrow_batch(g["rows"])
+        assert (o == g["offsets"]).all() and (cpu.sort_rows(o, p) == g["pairs_sorted"]).all(), f
+        m.close()

@@ -191,3 +191,27 @@ def test_pthread_harness_is_exact(kind):
         got = m.get_many((keys >> np.uint64(32)).astype(np.uint32), keys.astype(np.uint32))
         assert (got == counts).all()
         m.bench_c2_get(threads, 3, 2, 0, 50000, 200000, 500, 16)
+
+
+# ------------------------------------------------------------------ committed golden fixtures
+def _replay_golden(make_matrix):
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".npz"))
+    assert len(files) >= 4
+    for f in files:
+        g = np.load(os.path.join(gdir, f))
+        m = make_matrix()
+        for k in range(int(g["n_batches"])):
+            m.apply(str(g[f"op{k}"]), g[f"xs{k}"], g[f"ys{k}"], g[f"vs{k}"])
+        assert (m.get_many(g["qx"], g["qy"]) == g["get"]).all(), f
+        assert (m.rowlen_many(g["rows"]) == g["rowlen"]).all(), f
+        o, p = m.getrow_many(g["rows"])
+        assert (o == g["offsets"]).all() and (cpu.sort_rows(o, p) == g["pairs_sorted"]).all(), f
+        m.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_golden_fixtures(kind):
+    """tests/golden/*.npz were recorded from the unmodified reference (make_golden.py)."""
+    _replay_golden(lambda: cpu.CpuMatrix(kind))
