@@ -28,7 +28,7 @@ _u64p = C.POINTER(C.c_uint64)
 def build(ref: bool = True) -> None:
     """Compile the checkers (gcc only).  `make ref` is a no-op without the reference checkout."""
     targets = ["oracle"] + (["ref"] if ref else [])
-    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
+    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True, stdout=subprocess.DEVNULL)
 
 
 def have_reference() -> bool:

@@ -1,0 +1,60 @@
+"""Worker for tests/test_sharded_cpu.py: one rank of a world_size-2 gloo group driving the
+row-shard router (host logic) on the serial simulator library."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from libsmatrix_b200.sharded import ShardedSparseMatrix  # noqa: E402
+from oracle import cpu  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    sim = sys.argv[1]
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = ShardedSparseMatrix(rank, world, 0, _lib_path=sim)
+    ref = cpu.CpuMatrix("port")
+    rng = np.random.default_rng(123)                 # same stream on every rank
+    n = 40000
+    xs = rng.integers(0, 3000, n).astype(np.uint32) * np.uint32(2654435761)
+    ys = rng.integers(0, 60, n).astype(np.uint32)
+    vs = rng.integers(0, 1000, n).astype(np.uint32)
+    ref.apply("incr", xs, ys, vs)                    # the checker sees the WHOLE batch
+    ref.apply("decr", xs[::3], ys[::3], vs[::3] // 2)
+    mine = slice(rank * n // world, (rank + 1) * n // world)
+    t = lambda a: torch.from_numpy(a.view(np.int32).copy())
+    m.incr_batch(t(xs[mine]), t(ys[mine]), t(vs[mine]))
+    sx, sy, sv = xs[::3], ys[::3], vs[::3] // 2
+    k = len(sx)
+    part = slice(rank * k // world, (rank + 1) * k // world)
+    m.decr_batch(t(sx[part]), t(sy[part]), t(sv[part]))
+    # every rank asks for a different slice of queries and must get input-ordered answers
+    qx = np.concatenate([xs[rank::5], rng.integers(0, 2**32, 300, dtype=np.uint64).astype(np.uint32)])
+    qy = np.concatenate([ys[rank::5], rng.integers(0, 70, 300).astype(np.uint32)])
+    got = m.get_batch(t(qx), t(qy)).numpy().view(np.uint32)
+    assert (got == ref.get_many(qx, qy)).all(), f"rank {rank}: sharded get mismatch"
+    rows = np.unique(xs)[rank::2]
+    got = m.rowlen_batch(t(rows)).numpy().view(np.uint32)
+    assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
+    # the shard holds exactly the rows this rank owns
+    owned = np.array([x for x in np.unique(xs) if m._lib.smatrix_b200_owner(int(x), world) == rank], np.uint32)
+    assert m.stat("rows") == len(owned)
+    tot = torch.tensor([m.stat("rows"), m.stat("nnz")])
+    dist.all_reduce(tot)
+    assert int(tot[0]) == len(np.unique(xs))
+    o, p = ref.getrow_many(np.unique(xs))
+    assert int(tot[1]) == len(p)
+    m.close(); ref.close()
+    dist.destroy_process_group()
+    print(f"rank {rank} ok")
+
+
+if __name__ == "__main__":
+    main()
