@@ -33,7 +33,10 @@ enum {
   SMX_STAT_ROUNDS = 6,      /* upsert rounds (1 per pass + 1 per growth retry) so far     */
   SMX_STAT_ROW_GROWS = 7,   /* row growth (rehash) events so far                          */
   SMX_STAT_DIR_GROWS = 8,   /* directory rehash events so far                             */
-  SMX_STAT_KERNEL_NS = 9    /* device time of the dominant (update / get) kernels, ns, when timing is on */
+  SMX_STAT_KERNEL_NS = 9,   /* device time of the dominant (update / get) kernels, ns, when timing is on */
+  /* host wall-clock per phase of the write path since set_kernel_timing(1), ns */
+  SMX_STAT_NS_PARTITION = 10, SMX_STAT_NS_UPSERT = 11, SMX_STAT_NS_GROW_PLAN = 12,
+  SMX_STAT_NS_SLAB = 13, SMX_STAT_NS_MIGRATE = 14, SMX_STAT_NS_DIR = 15
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 
@@ -72,6 +75,13 @@ void smatrix_b200_partition(smatrix_t* self, const uint32_t* d_xs, const uint32_
                             const uint32_t* d_vals, size_t n, uint32_t world, uint64_t* h_counts,
                             uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
                             uint32_t* d_out_src /* nullable: original index of each routed op */);
+
+/* smatrix_{incr,decr,set}_batch (op = 0, 1, 2) on DEVICE arrays whose "input order" is given
+ * explicitly: d_ords[i] (unique, < 2^32 - 1) is op i's place in the sequential order the result
+ * must be equal to.  Used by the multi-GPU router, where ops arrive permuted: the order decides
+ * which duplicate `set` wins and the history-dependent rowlen.  One chunk per call. */
+void smatrix_b200_apply_ordered(smatrix_t* self, int op, const uint32_t* d_xs, const uint32_t* d_ys,
+                                const uint32_t* d_vals, const uint32_t* d_ords, size_t n);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ PROTOTYPES = {
                                            C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "smatrix_b200_probe_random_read": (C.c_double, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "smatrix_b200_probe_random_atomic": (C.c_double, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "smatrix_b200_apply_ordered": (None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_size_t]),
     "smatrix_b200_owner": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "smatrix_b200_partition": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -61,7 +63,8 @@ PROTOTYPES = {
 }
 
 STAT = {"rows": 0, "nnz": 1, "dir_cap": 2, "slab_bytes": 3, "device_bytes": 4, "launches": 5,
-        "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9}
+        "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9, "ns_partition": 10, "ns_upsert": 11,
+        "ns_grow_plan": 12, "ns_slab": 13, "ns_migrate": 14, "ns_dir": 15}
 
 _cache: dict[str, C.CDLL] = {}
 

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/smatrix.h"
 #include "../../include/smatrix_b200.h"
@@ -70,6 +71,11 @@ struct smatrix_s {
   uint32_t* stage[2][3];
   cudaEvent_t stage_ready[2];
 
+  uint32_t* part[4]; /* chunk partitioned by directory slice: xs, ys, vs, original index */
+  uint32_t part_cap;
+  uint32_t part_min; /* chunks smaller than this are applied in input order */
+  uint32_t slice_log; /* log2(directory entries per slice) */
+
   uint32_t* d_small; /* 64 words */
   uint32_t* h_small; /* pinned, 64 words */
 
@@ -81,6 +87,7 @@ struct smatrix_s {
   size_t d_rowbuf_bytes;
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows;
+  double phase_ns[8];
   int timing;
   cudaEvent_t ev0, ev1, t_start, t_stop;
   double kernel_ns;
@@ -120,19 +127,42 @@ static void* dmalloc(smatrix_t* s, size_t bytes) {
   return p;
 }
 
-static inline smx_view_t view_of(smatrix_t* s) {
+static uint32_t log2_u64(uint64_t v) {
+  uint32_t l = 0;
+  while ((1ull << l) < v) l++;
+  return l;
+}
+
+static inline smx_view_t view_for(smatrix_t* s, smx_row_t* dir, uint64_t cap) {
   smx_view_t v;
-  v.dir = s->dir;
-  v.dir_cap = s->dir_cap;
-  v.dir_limit = s->dir_cap / 2;
+  const uint32_t lg = log2_u64(cap);
+  v.dir = dir;
+  v.dir_cap = cap;
+  uint32_t slices_log = lg > 4 ? lg - 4 : 0;              /* slices of >= 16 entries ...        */
+  if (slices_log > 8) slices_log = 8;                     /* ... at most SMX_DIR_SLICES of them */
+  v.slice_shift = lg - slices_log;
+  v.slice_limit = (uint32_t)((1ull << v.slice_shift) / 2); /* load limit 1/2 in every slice      */
+  if (v.slice_limit < 1) v.slice_limit = 1;
   v.ctl = s->d_ctl;
   return v;
+}
+static inline smx_view_t view_of(smatrix_t* s) { return view_for(s, s->dir, s->dir_cap); }
+
+/* ---- phase accounting (host wall clock; see SMX_STAT_NS_*) ---- */
+enum { PH_PARTITION = 0, PH_UPSERT, PH_GROW_PLAN, PH_SLAB, PH_MIGRATE, PH_DIR, PH_COUNT };
+static inline double now_ns(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec * 1e9 + (double)t.tv_nsec;
 }
 
 static void read_ctl(smatrix_t* s) {
   CK(cudaMemcpyAsync(s->h_ctl, s->d_ctl, sizeof(smx_ctl_t), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
+  unsigned long long used = 0;
+  for (uint32_t k = 0; k < SMX_DIR_SLICES; k++) used += s->h_ctl->slice_used[k];
+  s->h_ctl->dir_used = used;
 }
 
 /* ------------------------------------------------------------------------------ slab */
@@ -231,16 +261,23 @@ static void timed_collect(smatrix_t* s) { /* call after the stream has been sync
 
 static void grow_rows(smatrix_t* s, uint32_t n_grow) {
   smx_view_t v = view_of(s);
+  double t0 = now_ns();
   smx_launch_grow_plan(s->stream, v, s->lists, n_grow);
   s->n_launches++;
   read_ctl(s);
+  double t1 = now_ns();
   const size_t bytes = (size_t)s->h_ctl->plan_bytes;
   const uint32_t n_big = s->h_ctl->n_big;
   char* region = slab_reserve(s, bytes);
+  double t2 = now_ns();
   CK(cudaMemsetAsync(region, 0, bytes, s->stream));
   smx_launch_migrate(s->stream, v, s->lists, n_grow, n_big, region);
+  if (s->timing) CK(cudaStreamSynchronize(s->stream)); /* attribute the device time to this phase */
   s->n_launches += 1 + (n_big ? 2 : 0);
   s->n_row_grows += n_grow;
+  s->phase_ns[PH_GROW_PLAN] += t1 - t0;
+  s->phase_ns[PH_SLAB] += t2 - t1;
+  s->phase_ns[PH_MIGRATE] += now_ns() - t2;
 }
 
 static uint64_t pow2_at_least(uint64_t v) {
@@ -250,14 +287,12 @@ static uint64_t pow2_at_least(uint64_t v) {
 }
 
 static void resize_dir(smatrix_t* s, uint64_t new_cap) {
+  double t0 = now_ns();
   smx_view_t from = view_of(s);
   smx_row_t* nd = (smx_row_t*)dmalloc(s, (size_t)new_cap * sizeof(smx_row_t));
   CK(cudaMemsetAsync(nd, 0, (size_t)new_cap * sizeof(smx_row_t), s->stream));
-  CK(cudaMemsetAsync(&s->d_ctl->dir_used, 0, sizeof(unsigned long long), s->stream));
-  smx_view_t to = from;
-  to.dir = nd;
-  to.dir_cap = new_cap;
-  to.dir_limit = new_cap / 2;
+  CK(cudaMemsetAsync(s->d_ctl->slice_used, 0, sizeof(uint32_t) * SMX_DIR_SLICES, s->stream));
+  smx_view_t to = view_for(s, nd, new_cap);
   smx_launch_dir_rehash(s->stream, from, to);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
@@ -265,6 +300,7 @@ static void resize_dir(smatrix_t* s, uint64_t new_cap) {
   s->dir = nd;
   s->dir_cap = new_cap;
   s->n_dir_grows++;
+  s->phase_ns[PH_DIR] += now_ns() - t0;
 }
 
 /* ------------------------------------------------------------------------------ write path */
@@ -279,6 +315,7 @@ static void run_pass(smatrix_t* s, smx_ops_t ops, int op, int pass, const uint32
   uint32_t prev_defer = 0xFFFFFFFFu;
   for (int round = 0; m > 0; round++) {
     if (round >= SMX_MAX_ROUNDS) smx_die("update pass does not converge (%u ops left)", m);
+    double t0 = now_ns();
     zero_round_counters(s);
     s->lists.defer_out = s->defer[flip];
     timed_begin(s);
@@ -288,13 +325,17 @@ static void run_pass(smatrix_t* s, smx_ops_t ops, int op, int pass, const uint32
     s->n_rounds++;
     read_ctl(s);
     timed_collect(s);
+    s->phase_ns[PH_UPSERT] += now_ns() - t0;
     const smx_ctl_t c = *s->h_ctl;
-    if (c.n_defer == 0) break;
     if (c.n_grow) grow_rows(s, c.n_grow);
-    if (c.n_dirfull || c.dir_used >= s->dir_cap / 2) {
+    if (c.n_defer == 0) break;
+    if (c.n_dirfull) {
+      /* n_dirfull counts refused OPS, an upper bound on the new rows: grow towards it but at most
+       * x8 per round, so duplicate-heavy chunks do not allocate a huge transient directory */
       uint64_t need = 2 * (c.dir_used + (uint64_t)c.n_dirfull);
       uint64_t cap = pow2_at_least(need);
       if (cap < s->dir_cap * 2) cap = s->dir_cap * 2;
+      if (cap > s->dir_cap * 8) cap = s->dir_cap * 8;
       resize_dir(s, cap);
     } else if (!c.n_grow && c.n_defer >= prev_defer) {
       smx_die("update pass made no progress (%u ops deferred)", c.n_defer);
@@ -316,12 +357,64 @@ static void maybe_shrink_dir(smatrix_t* s) {
   if (fit * 4 <= s->dir_cap) resize_dir(s, fit);
 }
 
+/* Reorder a chunk so that ops on rows of the same directory slice are adjacent: the slice of the
+ * directory (a few MB) then stays in L2 while its ops are applied, and a row header costs one
+ * DRAM read + one write-back per chunk instead of one per op.  idx keeps the input order. */
+static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
+  const uint32_t n = ops->n;
+  uint32_t dir_log = 0;
+  while ((1ull << dir_log) < s->dir_cap) dir_log++;
+  uint32_t parts_log = dir_log > s->slice_log ? dir_log - s->slice_log : 0; /* default: slices of 2^17 entries = 8 MiB */
+  if (parts_log > 7) parts_log = 7; /* 128 parts: a 2048-op tile still writes 64-byte runs */
+  if (parts_log == 0) return;
+  const uint32_t parts = 1u << parts_log, shift = dir_log - parts_log;
+  if (n > s->part_cap) {
+    if (s->part_cap) {
+      CK(cudaStreamSynchronize(s->stream));
+      for (int a = 0; a < 4; a++) cudaFree(s->part[a]);
+    }
+    s->part_cap = s->list_cap > n ? s->list_cap : n;
+    for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)dmalloc(s, (size_t)s->part_cap * 4);
+  }
+  ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
+  unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
+  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
+  unsigned long long h[SMX_MAX_PARTS_H], cur[SMX_MAX_PARTS_H];
+  double t0 = now_ns();
+  CK(cudaMemsetAsync(d_counts, 0, parts * 8, s->stream));
+  smx_launch_partition_count(s->stream, ops->xs, n, parts, (uint32_t)(s->dir_cap - 1), shift, d_counts);
+  CK(cudaMemcpyAsync(h, d_counts, parts * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  unsigned long long at = 0;
+  for (uint32_t p = 0; p < parts; p++) { cur[p] = at; at += h[p]; }
+  CK(cudaMemcpyAsync(d_cursors, cur, parts * 8, cudaMemcpyHostToDevice, s->stream));
+  smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, (uint32_t)(s->dir_cap - 1),
+                               shift, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
+                               s->part[3], ops->idx);
+  s->n_launches += 2;
+  if (s->timing) CK(cudaStreamSynchronize(s->stream));
+  s->phase_ns[PH_PARTITION] += now_ns() - t0;
+  ops->xs = s->part[0];
+  ops->ys = s->part[1];
+  if (ops->vs) ops->vs = s->part[2];
+  ops->idx = s->part[3];
+}
+
+static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs, const uint32_t* d_ys,
+                                  const uint32_t* d_vs, const uint32_t* d_ords, uint32_t n);
 static void process_chunk(smatrix_t* s, int api_op, const uint32_t* d_xs, const uint32_t* d_ys,
                           const uint32_t* d_vs, uint32_t n) {
+  process_chunk_ordered(s, api_op, d_xs, d_ys, d_vs, NULL, n);
+}
+
+/* d_ords == NULL: "input order" is the array order; else ords[i] is op i's place in that order */
+static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs, const uint32_t* d_ys,
+                                  const uint32_t* d_vs, const uint32_t* d_ords, uint32_t n) {
   if (n == 0) return;
   ensure_lists(s, n);
   smx_ops_t ops;
-  ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.v_const = 1u; ops.n = n;
+  ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = d_ords; ops.v_const = 1u; ops.n = n;
+  if (n >= s->part_min) partition_chunk(s, &ops);
   const int op = (api_op == 2) ? SMX_OP_SETZERO : api_op;
   CK(cudaMemsetAsync(&s->d_ctl->n_late, 0, 2 * sizeof(uint32_t), s->stream));
   run_pass(s, ops, op, SMX_PASS_COL0, NULL, n);
@@ -336,7 +429,7 @@ static void process_chunk(smatrix_t* s, int api_op, const uint32_t* d_xs, const 
     }
     smx_launch_set_max(s->stream, view_of(s), ops, s->addrs);
     smx_launch_set_commit(s->stream, ops, s->addrs);
-    s->n_launches += 2;
+    s->n_launches += 3;
   }
   const uint32_t n_t0 = s->h_ctl->n_t0;
   if (n_t0) {
@@ -420,6 +513,34 @@ void smatrix_decr_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
 void smatrix_set_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
                        const uint32_t* vals, size_t n) {
   write_batch(self, 2, xs, ys, vals, n);
+}
+
+void smatrix_b200_apply_ordered(smatrix_t* s, int op, const uint32_t* d_xs, const uint32_t* d_ys,
+                                const uint32_t* d_vals, const uint32_t* d_ords, size_t n) {
+  if (n == 0) return;
+  if (op < 0 || op > 2) smx_die("apply_ordered: op must be 0 (incr), 1 (decr) or 2 (set)");
+  enter(s);
+  if (n > (1u << 30)) smx_die("apply_ordered: at most 2^30 ops per call (one chunk)");
+  const int dev = is_device_ptr(d_xs);
+  if (is_device_ptr(d_ys) != dev || (d_vals && is_device_ptr(d_vals) != dev) || is_device_ptr(d_ords) != dev)
+    smx_die("batch arrays must be all host or all device pointers");
+  if (dev) {
+    process_chunk_ordered(s, op, d_xs, d_ys, d_vals, d_ords, (uint32_t)n);
+    CK(cudaStreamSynchronize(s->stream));
+  } else { /* host arrays: one staged copy (this entry point is meant for device-resident batches) */
+    const uint32_t* src[4] = {d_xs, d_ys, d_vals, d_ords};
+    uint32_t* tmp[4] = {NULL, NULL, NULL, NULL};
+    for (int a = 0; a < 4; a++) {
+      if (!src[a]) continue;
+      tmp[a] = (uint32_t*)dmalloc(s, n * 4);
+      CK(cudaMemcpyAsync(tmp[a], src[a], n * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    process_chunk_ordered(s, op, tmp[0], tmp[1], tmp[2], tmp[3], (uint32_t)n);
+    CK(cudaStreamSynchronize(s->stream));
+    for (int a = 0; a < 4; a++)
+      if (tmp[a]) CK(cudaFree(tmp[a]));
+  }
+  leave(s);
 }
 
 /* ------------------------------------------------------------------------------ read path */
@@ -656,6 +777,8 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   if (s->chunk_max < 1) s->chunk_max = 1;
   if (s->chunk_max > (1u << 30)) s->chunk_max = 1u << 30;
   s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
+  s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
+  s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->dir_cap = 1ull << s->dir_log_min;
   s->dir = (smx_row_t*)dmalloc(s, (size_t)s->dir_cap * sizeof(smx_row_t));
   CK(cudaMemsetAsync(s->dir, 0, (size_t)s->dir_cap * sizeof(smx_row_t), s->stream));
@@ -690,6 +813,8 @@ void smatrix_close(smatrix_t* s) {
     cudaFree(s->lists.t0rows); cudaFree(s->lists.plan); cudaFree(s->lists.big);
   }
   if (s->addrs) cudaFree(s->addrs);
+  if (s->part_cap)
+    for (int a = 0; a < 4; a++) cudaFree(s->part[a]);
   if (s->stage_cap)
     for (int b = 0; b < 2; b++)
       for (int a = 0; a < 3; a++) cudaFree(s->stage[b][a]);
@@ -733,6 +858,7 @@ void smatrix_b200_set_kernel_timing(smatrix_t* s, int on) {
   enter(s);
   s->timing = on;
   s->kernel_ns = 0.0;
+  memset(s->phase_ns, 0, sizeof s->phase_ns);
   leave(s);
 }
 
@@ -756,13 +882,19 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
     case SMX_STAT_DEVICE_BYTES:
       r = s->seg_bytes + s->dir_cap * sizeof(smx_row_t) + (uint64_t)s->list_cap * (6 * 4 + sizeof(smx_plan_t)) +
           (uint64_t)s->stage_cap * 24 + s->d_tmp_bytes + s->d_tmp64_bytes + s->d_rowbuf_bytes +
-          (uint64_t)s->addrs_cap * 8;
+          (uint64_t)s->addrs_cap * 8 + (uint64_t)s->part_cap * 16;
       break;
     case SMX_STAT_LAUNCHES: r = s->n_launches; break;
     case SMX_STAT_ROUNDS: r = s->n_rounds; break;
     case SMX_STAT_ROW_GROWS: r = s->n_row_grows; break;
     case SMX_STAT_DIR_GROWS: r = s->n_dir_grows; break;
     case SMX_STAT_KERNEL_NS: r = (uint64_t)s->kernel_ns; break;
+    case SMX_STAT_NS_PARTITION: r = (uint64_t)s->phase_ns[PH_PARTITION]; break;
+    case SMX_STAT_NS_UPSERT: r = (uint64_t)s->phase_ns[PH_UPSERT]; break;
+    case SMX_STAT_NS_GROW_PLAN: r = (uint64_t)s->phase_ns[PH_GROW_PLAN]; break;
+    case SMX_STAT_NS_SLAB: r = (uint64_t)s->phase_ns[PH_SLAB]; break;
+    case SMX_STAT_NS_MIGRATE: r = (uint64_t)s->phase_ns[PH_MIGRATE]; break;
+    case SMX_STAT_NS_DIR: r = (uint64_t)s->phase_ns[PH_DIR]; break;
     default: break;
   }
   leave(s);
@@ -866,7 +998,7 @@ void smatrix_b200_partition(smatrix_t* s, const uint32_t* d_xs, const uint32_t* 
   unsigned long long* d_cursors = d_counts + 64;
   unsigned long long h[64], cur[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
-  smx_launch_partition_count(s->stream, d_xs, (uint32_t)n, world, d_counts);
+  smx_launch_partition_count(s->stream, d_xs, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
   CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   unsigned long long at = 0;
@@ -876,8 +1008,8 @@ void smatrix_b200_partition(smatrix_t* s, const uint32_t* d_xs, const uint32_t* 
     h_counts[r] = h[r];
   }
   CK(cudaMemcpyAsync(d_cursors, cur, world * 8, cudaMemcpyHostToDevice, s->stream));
-  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, d_cursors,
-                               d_out_xs, d_out_ys, d_out_vals, d_out_src);
+  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER,
+                               d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL);
   s->n_launches += 2;
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());

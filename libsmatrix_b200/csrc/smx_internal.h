@@ -51,9 +51,10 @@ typedef struct {
 } smx_row_t;       /* 64 bytes */
 
 /* ---- device control block (counters the host reads back after every round) -------------- */
+#define SMX_DIR_SLICES 256u      /* occupancy is tracked (and limited) per directory slice     */
 typedef struct {
   /* persistent */
-  unsigned long long dir_used;   /* rows in the directory                                    */
+  unsigned long long dir_used;   /* rows in the directory (sum of slice_used, set by the host's readers) */
   /* per chunk */
   uint32_t n_late;               /* ops parked for the LATE pass                             */
   uint32_t n_t0;                 /* rows whose column 0 turned non-zero in this chunk        */
@@ -64,12 +65,17 @@ typedef struct {
   uint32_t n_big;                /* of those, rows whose OLD bucket is >= 2^SMX_BIG_LOG      */
   unsigned long long plan_bytes; /* bytes of new buckets planned by grow_plan                */
   unsigned long long scratch;    /* misc: reductions (nnz, probe checksums)                  */
+  /* persistent: rows per directory slice (slice = position >> dir_slice_shift); new rows are
+   * refused in a slice at its limit, so that no region of the directory exceeds the load limit
+   * even when a chunk is applied slice by slice */
+  uint32_t slice_used[SMX_DIR_SLICES];
 } smx_ctl_t;
 
 typedef struct {
   smx_row_t* dir;
   uint64_t dir_cap;    /* entries, power of two                                             */
-  uint64_t dir_limit;  /* new rows are refused once dir_used >= dir_limit                    */
+  uint32_t slice_shift; /* directory position >> slice_shift = slice index                  */
+  uint32_t slice_limit; /* new rows are refused in a slice holding this many rows            */
   smx_ctl_t* ctl;
 } smx_view_t;
 
@@ -77,6 +83,8 @@ typedef struct {
   const uint32_t* xs;
   const uint32_t* ys;
   const uint32_t* vs;  /* NULL: every value is v_const                                       */
+  const uint32_t* idx; /* NULL: identity; else idx[p] = index of array position p in the caller's
+                          input order (the batch was partitioned by directory slice)          */
   uint32_t v_const;
   uint32_t n;
 } smx_ops_t;
@@ -110,7 +118,7 @@ void smx_launch_migrate(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32
 void smx_launch_dir_rehash(smx_stream_t stream, smx_view_t from, smx_view_t to);
 void smx_launch_finalize_t0(smx_stream_t stream, smx_view_t v, const uint32_t* t0rows, uint32_t n);
 void smx_launch_set_max(smx_stream_t stream, smx_view_t v, smx_ops_t ops, uint64_t* addrs);
-void smx_launch_set_commit(smx_stream_t stream, smx_ops_t ops, const uint64_t* addrs);
+void smx_launch_set_commit(smx_stream_t stream, smx_ops_t ops, uint64_t* addrs); /* mark + commit */
 void smx_launch_get(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
                     uint32_t n, uint32_t* out);
 void smx_launch_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
@@ -130,12 +138,18 @@ void smx_launch_gen_c2_queries(smx_stream_t stream, uint64_t seed_get, uint64_t 
 void smx_launch_probe_read(smx_stream_t stream, const void* buf, uint64_t n_units, uint64_t accesses,
                            int width, smx_ctl_t* ctl);
 void smx_launch_probe_atomic(smx_stream_t stream, uint32_t* buf, uint64_t n_words, uint64_t accesses);
+/* part = owner rank when shift == SMX_PART_OWNER, else directory slice (mix_row(x) & dir_mask) >> shift */
+#define SMX_PART_OWNER 0xFFFFFFFFu
+#define SMX_MAX_PARTS_H 256u
 void smx_launch_partition_count(smx_stream_t stream, const uint32_t* xs, uint32_t n, uint32_t world,
+                                uint32_t dir_mask, uint32_t shift,
                                 unsigned long long* counts /* [world], zeroed */);
 void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const uint32_t* ys,
                                   const uint32_t* vs, uint32_t n, uint32_t world,
+                                  uint32_t dir_mask, uint32_t shift,
                                   unsigned long long* cursors /* [world] start offsets */,
-                                  uint32_t* oxs, uint32_t* oys, uint32_t* ovs, uint32_t* osrc);
+                                  uint32_t* oxs, uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
+                                  const uint32_t* src_in /* NULL: osrc = position; else osrc = src_in[position] */);
 uint32_t smx_scan_scratch_items(uint32_t n); /* number of uint64 block sums smx_launch_scan needs */
 int smx_grid_blocks(void);                   /* resident grid size used by the streaming kernels */
 

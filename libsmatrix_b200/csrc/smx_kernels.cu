@@ -14,7 +14,7 @@
  *   k_get               smatrix_get (:174-185)
  *   k_rowlen            smatrix_rowlen (:212-223)
  *   k_row_counts/scan/getrow_fill   smatrix_getrow (:189-210) for whole batches of rows
- *   k_set_max/commit    last-writer-wins resolution for smatrix_set batches (:225-234 applied
+ *   k_set_max/mark/commit  last-writer-wins resolution for smatrix_set batches (:225-234 applied
  *                       sequentially)
  *
  * Concurrency rules the code relies on (DESIGN.md "Concurrency"):
@@ -144,11 +144,12 @@ __device__ __forceinline__ int dir_find(const smx_view_t& V, uint32_t x, bool cr
       continue;
     }
     if (!create) return DIR_MISS;
-    if (__ldcg(&V.ctl->dir_used) >= V.dir_limit) return DIR_FULL;
+    uint32_t* slice = &V.ctl->slice_used[pos >> V.slice_shift];
+    if (step >= 256 || __ldcg(slice) >= V.slice_limit) return DIR_FULL;
     const ull fresh = (ull)x | ((ull)(SMX_META_USED | SMX_INLINE_LOG) << 32);
     ull old = atomicCAS((ull*)e, 0ull, fresh);
     if (old == 0ull) {
-      agg_inc64(&V.ctl->dir_used);
+      atomicAdd(slice, 1u);
       h.key = x; h.meta = SMX_META_USED | SMX_INLINE_LOG;
       h.slots = 0; h.live = 0; h.c0 = 0; h.t0inv = 0; h.want = 0;
       *out = e; *hdr = h;
@@ -174,9 +175,11 @@ __device__ __forceinline__ void apply_value(uint32_t* vp, uint32_t v) {
   else *(volatile uint32_t*)vp = 0u;
 }
 
-/* returns true when done, false when the bucket is at its load limit (caller defers the op) */
+/* SLOT_FULL: bucket at its load limit (caller defers the op); SLOT_DONE; SLOT_DONE_GROW: done, and
+ * the row crossed 3/4 of its load limit — ask for growth now so that later ops are not deferred */
+enum { SLOT_FULL = 0, SLOT_DONE = 1, SLOT_DONE_GROW = 2 };
 template <int OP>
-__device__ __forceinline__ bool slot_upsert(smx_row_t* e, const Hdr& h, uint32_t y, uint32_t v,
+__device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t y, uint32_t v,
                                             bool counts_col0) {
   const uint32_t caplog = h.meta & SMX_META_CAPLOG;
   ull* base = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
@@ -193,27 +196,28 @@ __device__ __forceinline__ bool slot_upsert(smx_row_t* e, const Hdr& h, uint32_t
     for (int k = 0; k < 4; ++k) {
       if ((uint32_t)c[k] == y) { /* y != 0, so this is a live cell of ours */
         apply_value<OP>((uint32_t*)(sec + k) + 1, v);
-        return true;
+        return SLOT_DONE;
       }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (c[k] != 0ull) continue;
-      if (h.live >= limit) return false;
+      if (h.live >= limit) return SLOT_FULL;
       ull old = atomicCAS(sec + k, 0ull, fresh);
       if (old == 0ull) { /* new column */
         uint32_t n = atomicAdd(&e->live, 1u) + 1u;
         if (counts_col0 && is_resize_count(n)) atomicOr(&e->meta, SMX_META_D);
-        return true;
+        (void)n;
+        return SLOT_DONE;
       }
       if ((uint32_t)old == y) {
         apply_value<OP>((uint32_t*)(sec + k) + 1, v);
-        return true;
+        return SLOT_DONE;
       }
       /* claimed for another column meanwhile: try the next cell in probe order */
     }
   }
-  return false;
+  return SLOT_FULL;
 }
 
 /* read-only probe: value of column y (y != 0) or 0 */
@@ -245,9 +249,10 @@ __device__ __forceinline__ uint32_t slot_find(const smx_row_t* e, const Hdr& h, 
 /* ------------------------------------------------------------------------------------------
  * K1+K2+K3: the update kernel
  * ---------------------------------------------------------------------------------------- */
+/* `ord` is the op's index in the caller's input order (what "sequential application" refers to) */
 template <int OP>
 __device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t& S, int pass,
-                                          uint32_t i, uint32_t x, uint32_t y, uint32_t v) {
+                                          uint32_t ord, uint32_t x, uint32_t y, uint32_t v) {
   smx_row_t* e;
   Hdr h;
   int r = dir_find(V, x, true, &e, &h);
@@ -260,7 +265,7 @@ __device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t
     /* column 0 of this row turns non-zero inside this batch: remember the first such op
      * (rowlen depends on whether column 0 was non-zero at each virtual resize) */
     if (v != 0u && !(h.meta & SMX_META_ZC)) {
-      atomicMax(&e->t0inv, ~i);
+      atomicMax(&e->t0inv, ~ord);
       if (!(h.meta & SMX_META_T0P)) {
         uint32_t old = atomicOr(&e->meta, SMX_META_T0P);
         if (!(old & SMX_META_T0P)) S.t0rows[agg_inc(&V.ctl->n_t0)] = x;
@@ -269,16 +274,17 @@ __device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t
     return ST_OK;
   }
   if (pass == SMX_PASS_EARLY && (h.meta & SMX_META_T0P)) {
-    if (i > ~h.t0inv) return ST_LATE; /* ordered after column 0 became non-zero */
+    if (ord > ~h.t0inv) return ST_LATE; /* ordered after column 0 became non-zero */
   }
   const bool counts_col0 = (pass == SMX_PASS_LATE) || (h.meta & SMX_META_ZC);
-  if (slot_upsert<OP>(e, h, y, v, counts_col0)) return ST_OK;
-  atomicAdd(&e->want, 1u);
-  if (!(h.meta & SMX_META_GROW)) {
+  const int r2 = slot_upsert<OP>(e, h, y, v, counts_col0);
+  if (r2 == SLOT_DONE) return ST_OK;
+  if (r2 == SLOT_FULL) atomicAdd(&e->want, 1u);
+  if (!(h.meta & SMX_META_GROW)) { /* queue the row for growth, once per round */
     uint32_t old = atomicOr(&e->meta, SMX_META_GROW);
     if (!(old & SMX_META_GROW)) S.grow[agg_inc(&V.ctl->n_grow)] = (uint32_t)(e - V.dir);
   }
-  return ST_DEFER;
+  return r2 == SLOT_FULL ? ST_DEFER : ST_OK;
 }
 
 template <int OP>
@@ -290,18 +296,21 @@ k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* lis
   const uint32_t m_up = (m + (SMX_WARP - 1)) / SMX_WARP * SMX_WARP; /* whole warps stay in the loop */
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m_up; j += stride) {
     bool act = j < m;
-    uint32_t i = 0, x = 0, y = 0, v = 0;
+    uint32_t pos = 0, ord = 0, x = 0, y = 0, v = 0;
     if (act) {
-      i = list ? list[j] : j;
-      x = O.xs[i];
-      y = O.ys[i];
-      v = O.vs ? O.vs[i] : O.v_const;
+      pos = list ? list[j] : j;           /* position in the (possibly partitioned) batch arrays */
+      ord = O.idx ? O.idx[pos] : pos;     /* index in the caller's input order */
+      x = O.xs[pos];
+      y = O.ys[pos];
+      v = O.vs ? O.vs[pos] : O.v_const;
       if (!list) act = (pass == SMX_PASS_COL0) ? (y == 0u) : (y != 0u);
     }
-    /* K1: collapse duplicate (x,y) keys inside the warp before they reach the table */
+    /* K1: collapse duplicate (x,y) keys inside the warp before they reach the table; the member
+     * that comes first in input order leads (it decides EARLY vs LATE for the group) */
     bool lead = act;
     uint32_t vsum = v;
     unsigned peers = 1u << lane;
+    int leader = (int)lane;
     if (preagg) {
       const ull k64 = ((ull)x << 32) | (ull)y;
       const unsigned valid = __ballot_sync(SMX_FULL, act);
@@ -309,23 +318,27 @@ k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* lis
       const bool dup = act && (peers != (1u << lane));
       if (__any_sync(SMX_FULL, dup)) {
         vsum = 0u;
-        for (int src = 0; src < SMX_WARP; ++src) { /* segmented sum, lanes are in input order */
-          uint32_t t = __shfl_sync(SMX_FULL, v, src);
-          if ((peers >> src) & 1u) vsum += t;
+        uint32_t best = 0xFFFFFFFFu;
+        for (int src = 0; src < SMX_WARP; ++src) { /* segmented sum + arg-min of ord */
+          const uint32_t tv = __shfl_sync(SMX_FULL, v, src);
+          const uint32_t to = __shfl_sync(SMX_FULL, ord, src);
+          if ((peers >> src) & 1u) {
+            vsum += tv;
+            if (to < best) { best = to; leader = src; }
+          }
         }
-        lead = act && ((uint32_t)(__ffs(peers) - 1) == lane);
+        lead = act && (leader == (int)lane);
       }
     }
     int status = ST_OK;
-    if (lead) status = upsert_one<OP>(V, S, pass, i, x, y, vsum);
+    if (lead) status = upsert_one<OP>(V, S, pass, ord, x, y, vsum);
     if (preagg) { /* members of a group share their leader's fate (retry / late pass) */
       __syncwarp();
-      const int src = act ? (__ffs(peers) - 1) : (int)lane;
-      const int ls = __shfl_sync(SMX_FULL, status, src);
+      const int ls = __shfl_sync(SMX_FULL, status, act ? leader : (int)lane);
       if (act && !lead) status = ls;
     }
-    if (act && status == ST_DEFER) S.defer_out[agg_inc(&V.ctl->n_defer)] = i;
-    else if (act && status == ST_LATE) S.late[agg_inc(&V.ctl->n_late)] = i;
+    if (act && status == ST_DEFER) S.defer_out[agg_inc(&V.ctl->n_defer)] = pos;
+    else if (act && status == ST_LATE) S.late[agg_inc(&V.ctl->n_late)] = pos;
   }
 }
 
@@ -346,7 +359,8 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       Hdr h = ld_hdr(V.dir + entry);
       caplog = h.meta & SMX_META_CAPLOG;
       const ull need = 2ull * ((ull)h.live + (ull)h.want); /* load factor <= 1/2 after growth */
-      newlog = caplog + 1u;
+      /* small buckets grow x4 (fewer growth waves, less vacated memory), big ones x2 */
+      newlog = caplog + (caplog < 8u ? 2u : 1u);
       if (newlog < SMX_MIN_SLAB_LOG) newlog = SMX_MIN_SLAB_LOG;
       while ((1ull << newlog) < need && newlog < SMX_MAX_CAPLOG) ++newlog;
       bytes = 8ull << newlog;
@@ -466,14 +480,14 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_dir_rehash(smx_view_t from, smx_v
       if (atomicCAS(dst, 0ull, a[0]) == 0ull) {
         dst[1] = a[1]; dst[2] = a[2]; dst[3] = a[3];
         dst[4] = b[0]; dst[5] = b[1]; dst[6] = b[2]; dst[7] = b[3];
+        atomicAdd(&to.ctl->slice_used[q >> to.slice_shift], 1u);
         break;
       }
       q = (q + 1) & mask;
     }
     ++moved;
   }
-  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) moved += __shfl_xor_sync(SMX_FULL, moved, d);
-  if (lane_id() == 0 && moved) atomicAdd(&to.ctl->dir_used, moved);
+  (void)moved;
 }
 
 /* end of a chunk: column 0 of these rows is now (and stays) non-zero */
@@ -489,7 +503,8 @@ __global__ void k_finalize_t0(smx_view_t V, const uint32_t* t0rows, uint32_t n) 
 
 /* ------------------------------------------------------------------------------------------
  * set: last writer in input order wins.  After k_upsert<SETZERO> created every cell and stored
- * 0 in it, k_set_max leaves max(i)+1 in the cell and k_set_commit lets that op store its value.
+ * 0 in it, k_set_max leaves max(i)+1 in the cell, k_set_mark finds the op that holds it and
+ * k_set_commit lets that op store its value.
  * ---------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(SMX_BLOCK) k_set_max(smx_view_t V, smx_ops_t O, ull* addrs) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x) {
@@ -501,14 +516,24 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_set_max(smx_view_t V, smx_ops_t O
       if (y == 0u) vp = &e->c0;
       else slot_find(e, h, y, &vp);
     }
-    if (vp) atomicMax(vp, i + 1u);
+    const uint32_t ord = O.idx ? O.idx[i] : i;
+    if (vp) atomicMax(vp, ord + 1u);
     addrs[i] = (ull)vp;
+  }
+}
+/* read-only: keep the cell address only for the op that holds the maximum (no value is stored
+ * in this kernel, so a stored VALUE can never be mistaken for somebody's index + 1) */
+__global__ void __launch_bounds__(SMX_BLOCK) k_set_mark(smx_ops_t O, ull* addrs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x) {
+    const uint32_t* vp = (const uint32_t*)addrs[i];
+    const uint32_t ord = O.idx ? O.idx[i] : i;
+    if (vp && __ldcg(vp) != ord + 1u) addrs[i] = 0ull;
   }
 }
 __global__ void __launch_bounds__(SMX_BLOCK) k_set_commit(smx_ops_t O, const ull* addrs) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x) {
     uint32_t* vp = (uint32_t*)addrs[i];
-    if (vp && __ldcg(vp) == i + 1u) *vp = O.vs ? O.vs[i] : O.v_const;
+    if (vp) *vp = O.vs ? O.vs[i] : O.v_const;
   }
 }
 
@@ -744,47 +769,82 @@ k_probe_atomic(uint32_t* buf, ull n_words, ull accesses) {
 /* ------------------------------------------------------------------------------------------
  * K8: owner-rank bucketing for the multi-GPU router
  * ---------------------------------------------------------------------------------------- */
-#define SMX_MAX_WORLD 64
+#define SMX_MAX_PARTS 256
+/* part = owner rank (shift == 0xFFFFFFFF: mix_owner(x) % world) or directory slice
+ * ((mix_row(x) & dir_mask) >> shift, `world` slices) */
+__device__ __forceinline__ uint32_t part_of(uint32_t x, uint32_t world, uint32_t dir_mask, uint32_t shift) {
+  return shift == 0xFFFFFFFFu ? smx_mix_owner(x) % world : (smx_mix_row(x) & dir_mask) >> shift;
+}
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, ull* counts) {
-  __shared__ uint32_t hist[SMX_MAX_WORLD];
+k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, uint32_t dir_mask, uint32_t shift,
+                  ull* counts) {
+  __shared__ uint32_t hist[SMX_MAX_PARTS];
   for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    atomicAdd(&hist[smx_mix_owner(xs[i]) % world], 1u);
+    atomicAdd(&hist[part_of(xs[i], world, dir_mask, shift)], 1u);
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
     if (hist[k]) atomicAdd(&counts[k], (ull)hist[k]);
 }
-/* each block reserves a contiguous range per owner, then scatters; order inside an owner's
- * segment is not the input order (fine for incr/decr/get, see DESIGN.md "Multi-GPU") */
+/* Tiled partition: a block stages a tile of ops in shared memory sorted by part, reserves one
+ * contiguous range per part with a single global atomic, and writes whole runs — so every
+ * (tile, part) run reaches L2 as full sectors no matter how many parts there are.  Order inside a
+ * part is not the input order (osrc carries the original index). */
+#define PART_ITEMS 8
+#define PART_TILE (SMX_BLOCK * PART_ITEMS)
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
-                    uint32_t world, ull* cursors, uint32_t* oxs, uint32_t* oys, uint32_t* ovs,
-                    uint32_t* osrc) {
-  __shared__ uint32_t hist[SMX_MAX_WORLD];
-  __shared__ ull start[SMX_MAX_WORLD];
-  const uint32_t per_block = (n + gridDim.x - 1) / gridDim.x;
-  const uint32_t lo = blockIdx.x * per_block;
-  const uint32_t hi = (lo + per_block < n) ? lo + per_block : n;
-  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
-  __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-    atomicAdd(&hist[smx_mix_owner(xs[i]) % world], 1u);
-  __syncthreads();
-  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) {
-    start[k] = hist[k] ? atomicAdd(&cursors[k], (ull)hist[k]) : 0ull;
-    hist[k] = 0u;
-  }
-  __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const uint32_t x = xs[i];
-    const uint32_t o = smx_mix_owner(x) % world;
-    const ull at = start[o] + atomicAdd(&hist[o], 1u);
-    oxs[at] = x;
-    if (ys) oys[at] = ys[i];
-    if (vs) ovs[at] = vs[i];
-    if (osrc) osrc[at] = i;
+                    uint32_t world, uint32_t dir_mask, uint32_t shift, ull* cursors, uint32_t* oxs,
+                    uint32_t* oys, uint32_t* ovs, uint32_t* osrc, const uint32_t* src_in) {
+  __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_v[PART_TILE], s_i[PART_TILE];
+  __shared__ uint32_t hist[SMX_MAX_PARTS], off[SMX_MAX_PARTS];
+  __shared__ ull gbase[SMX_MAX_PARTS];
+  const uint32_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t base = tile * PART_TILE;
+    const uint32_t cnt = (n - base < PART_TILE) ? n - base : PART_TILE;
+    for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
+    __syncthreads();
+    uint32_t x[PART_ITEMS], rank[PART_ITEMS];
+#pragma unroll
+    for (int k = 0; k < PART_ITEMS; ++k) {
+      const uint32_t j = k * blockDim.x + threadIdx.x;
+      if (j < cnt) {
+        x[k] = xs[base + j];
+        rank[k] = atomicAdd(&hist[part_of(x[k], world, dir_mask, shift)], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { /* world <= 256: a serial prefix is cheap next to the tile */
+      uint32_t run = 0;
+      for (uint32_t k = 0; k < world; ++k) { off[k] = run; run += hist[k]; }
+    }
+    for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
+      gbase[k] = hist[k] ? atomicAdd(&cursors[k], (ull)hist[k]) : 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PART_ITEMS; ++k) {
+      const uint32_t j = k * blockDim.x + threadIdx.x;
+      if (j < cnt) {
+        const uint32_t at = off[part_of(x[k], world, dir_mask, shift)] + rank[k];
+        s_x[at] = x[k];
+        if (ys) s_y[at] = ys[base + j];
+        if (vs) s_v[at] = vs[base + j];
+        s_i[at] = src_in ? src_in[base + j] : base + j; /* carry the caller's order index */
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+      const uint32_t xx = s_x[j];
+      const uint32_t p = part_of(xx, world, dir_mask, shift);
+      const ull at = gbase[p] + (j - off[p]);
+      oxs[at] = xx;
+      if (ys) oys[at] = s_y[j];
+      if (vs) ovs[at] = s_v[j];
+      if (osrc) osrc[at] = s_i[j];
+    }
+    __syncthreads();
   }
 }
 
@@ -858,8 +918,9 @@ extern "C" void smx_launch_set_max(smx_stream_t st, smx_view_t v, smx_ops_t ops,
   if (!ops.n) return;
   SMX_LAUNCH(k_set_max, grid_for(ops.n), SMX_BLOCK, st, v, ops, (ull*)addrs);
 }
-extern "C" void smx_launch_set_commit(smx_stream_t st, smx_ops_t ops, const uint64_t* addrs) {
+extern "C" void smx_launch_set_commit(smx_stream_t st, smx_ops_t ops, uint64_t* addrs) {
   if (!ops.n) return;
+  SMX_LAUNCH(k_set_mark, grid_for(ops.n), SMX_BLOCK, st, ops, (ull*)addrs);
   SMX_LAUNCH(k_set_commit, grid_for(ops.n), SMX_BLOCK, st, ops, (const ull*)addrs);
 }
 
@@ -925,17 +986,20 @@ extern "C" void smx_launch_probe_atomic(smx_stream_t st, uint32_t* buf, uint64_t
 }
 
 extern "C" void smx_launch_partition_count(smx_stream_t st, const uint32_t* xs, uint32_t n,
-                                           uint32_t world, unsigned long long* counts) {
+                                           uint32_t world, uint32_t dir_mask, uint32_t shift,
+                                           unsigned long long* counts) {
   if (!n) return;
-  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, n, world, counts);
+  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, n, world, dir_mask, shift, counts);
 }
 extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs, const uint32_t* ys,
                                              const uint32_t* vs, uint32_t n, uint32_t world,
+                                             uint32_t dir_mask, uint32_t shift,
                                              unsigned long long* cursors, uint32_t* oxs,
-                                             uint32_t* oys, uint32_t* ovs, uint32_t* osrc) {
+                                             uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
+                                             const uint32_t* src_in) {
   if (!n) return;
-  SMX_LAUNCH(k_partition_scatter, grid_for(n), SMX_BLOCK, st, xs, ys, vs, n, world, cursors, oxs,
-             oys, ovs, osrc);
+  SMX_LAUNCH(k_partition_scatter, grid_for((ull)(n + PART_ITEMS - 1) / PART_ITEMS), SMX_BLOCK, st, xs, ys,
+             vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, osrc, src_in);
 }
 
 extern "C" uint32_t smx_owner_hash(uint32_t x) { return smx_mix_owner(x); }

@@ -7,11 +7,16 @@ complete private table for the rows it owns.  A batch call is collective: each r
 slice of the batch; the slice is bucketed by owner on the device (K8, smatrix_b200_partition),
 the per-owner counts are exchanged, one all-to-all-v moves the (x, y, value) triples, and each
 rank updates only its own shard.  Reads add the reverse all-to-all-v and un-permute the answers
-into input order.  There is no cross-rank state besides the exchange, so incr/decr results are
-bit-exact for any interleaving (addition mod 2^32 commutes); `set` needs one rank to see every
-write to a key in input order, which holds because a key has exactly one owner and a rank's
-slice keeps its order per owner only for world == 1 — so set_batch is routed with the global op
-index and resolved by the owner (see set_batch).
+into input order.
+
+Input order.  The collective batch is the concatenation of the ranks' slices in rank order.
+Routing permutes ops, and two results depend on order: which duplicate `set` wins, and the
+history-dependent rowlen when column 0 turns non-zero in the same batch as new columns (SURVEY.md
+Q1).  With `ordered=True` (default) every op travels with its global index (16 B/op instead of
+12) and the owner applies the batch through smatrix_b200_apply_ordered, which is bit-exact with
+the sequential reference.  `ordered=False` skips the index for incr/decr streams that never
+write column 0 (BASELINE configs 2 and 5): values never depend on order (addition mod 2^32
+commutes), so the result is identical.
 """
 from __future__ import annotations
 
@@ -61,28 +66,48 @@ class ShardedSparseMatrix:
         dist.all_to_all_single(out, t, output_split_sizes=recv, input_split_sizes=send, group=self.group)
         return out
 
-    def _route(self, xs, ys, vals, want_src=False):
-        send, oxs, oys, ovs, osrc = self._partition(xs, ys, vals, want_src)
+    def _route(self, xs, ys, vals, want_src=False, ordered=False):
+        send, oxs, oys, ovs, osrc = self._partition(xs, ys, vals, want_src or ordered)
         recv = self._exchange_counts(send)
         rx = self._a2a(oxs, send, recv)
         ry = self._a2a(oys, send, recv) if oys is not None else None
         rv = self._a2a(ovs, send, recv) if ovs is not None else None
+        rord = None
+        if ordered:   # global index = (ops in the slices of lower ranks) + index inside my slice
+            sizes = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+            sizes[self.rank] = xs.numel()
+            dist.all_reduce(sizes, group=self.group)
+            if int(sizes.sum()) >= 2**32 - 1:
+                raise ValueError("ordered collective batches are limited to 2^32 - 2 ops")
+            base = int(sizes[: self.rank].sum())
+            gidx = (osrc.long() + base).to(torch.int32)   # wraps into uint32 bit pattern
+            rord = self._a2a(gidx, send, recv)
         self._sync_torch()   # the library runs on its own stream
-        return send, recv, rx, ry, rv, osrc
+        return send, recv, rx, ry, rv, osrc, rord
+
+    def _write(self, op: int, xs, ys, vals, ordered: bool):
+        _, _, rx, ry, rv, _, rord = self._route(xs, ys, vals, ordered=ordered)
+        if not rx.numel():
+            return
+        if ordered:
+            p = lambda t: t.data_ptr() if t is not None else None
+            self._lib.smatrix_b200_apply_ordered(self.local._handle(), op, p(rx), p(ry), p(rv), p(rord),
+                                                 rx.numel())
+        else:
+            (self.local.incr_batch, self.local.decr_batch)[op](rx, ry, rv)
 
     # ------------------------------------------------------------------ collective batch API
-    def incr_batch(self, xs, ys, vals=None):
-        _, _, rx, ry, rv, _ = self._route(xs, ys, vals)
-        if rx.numel():
-            self.local.incr_batch(rx, ry, rv)
+    def incr_batch(self, xs, ys, vals=None, ordered: bool = True):
+        self._write(0, xs, ys, vals, ordered)
 
-    def decr_batch(self, xs, ys, vals=None):
-        _, _, rx, ry, rv, _ = self._route(xs, ys, vals)
-        if rx.numel():
-            self.local.decr_batch(rx, ry, rv)
+    def decr_batch(self, xs, ys, vals=None, ordered: bool = True):
+        self._write(1, xs, ys, vals, ordered)
+
+    def set_batch(self, xs, ys, vals=None):
+        self._write(2, xs, ys, vals, True)     # last writer in GLOBAL input order wins
 
     def get_batch(self, xs, ys, out=None):
-        send, recv, rx, ry, _, osrc = self._route(xs, ys, None, want_src=True)
+        send, recv, rx, ry, _, osrc, _ = self._route(xs, ys, None, want_src=True)
         ans = self.local.get_batch(rx, ry) if rx.numel() else self._buf(0)
         self._sync_torch()
         back = self._a2a(ans, recv, send)           # answers travel the reverse way
@@ -92,7 +117,7 @@ class ShardedSparseMatrix:
         return out
 
     def rowlen_batch(self, xs):
-        send, recv, rx, _, _, osrc = self._route(xs, None, None, want_src=True)
+        send, recv, rx, _, _, osrc, _ = self._route(xs, None, None, want_src=True)
         ans = self.local.rowlen_batch(rx) if rx.numel() else self._buf(0)
         self._sync_torch()
         back = self._a2a(ans, recv, send)

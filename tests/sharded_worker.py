@@ -35,6 +35,14 @@ def main():
     k = len(sx)
     part = slice(rank * k // world, (rank + 1) * k // world)
     m.decr_batch(t(sx[part]), t(sy[part]), t(sv[part]))
+    # set with duplicate keys across ranks: the last writer in GLOBAL input order must win
+    gx = rng.integers(0, 50, 6000).astype(np.uint32) * np.uint32(2654435761)
+    gy = rng.integers(1, 20, 6000).astype(np.uint32)
+    gv = rng.integers(1, 2**32, 6000, dtype=np.uint64).astype(np.uint32)
+    ref.apply("set", gx, gy, gv)
+    gs = slice(rank * 6000 // world, (rank + 1) * 6000 // world)
+    m.set_batch(t(gx[gs]), t(gy[gs]), t(gv[gs]))
+    xs = np.concatenate([xs, gx]); ys = np.concatenate([ys, gy])
     # every rank asks for a different slice of queries and must get input-ordered answers
     qx = np.concatenate([xs[rank::5], rng.integers(0, 2**32, 300, dtype=np.uint64).astype(np.uint32)])
     qy = np.concatenate([ys[rank::5], rng.integers(0, 70, 300).astype(np.uint32)])

@@ -14,11 +14,15 @@ U32 = np.uint32
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(params=["default", "chunk65536"])
+@pytest.fixture(params=["default", "chunk65536", "partitioned"])
 def make(request, monkeypatch):
-    if request.param != "default":
+    if request.param == "chunk65536":
         monkeypatch.setenv("SMATRIX_CHUNK", "65536")       # multi-chunk batches
         monkeypatch.setenv("SMATRIX_DIR_LOG2", "12")       # directory growth from 4096 entries
+    if request.param == "partitioned":                     # every chunk re-ordered by directory slice
+        monkeypatch.setenv("SMATRIX_PARTITION_MIN", "64")
+        monkeypatch.setenv("SMATRIX_SLICE_LOG2", "6")
+        monkeypatch.setenv("SMATRIX_DIR_LOG2", "10")
     return lambda: SparseMatrix()
 
 

@@ -16,11 +16,15 @@ def sim():
     return hb.build()
 
 
-@pytest.fixture(params=[(6, 1 << 26), (10, 3000), (4, 777)], ids=["dir64", "chunk3000", "dir16-chunk777"])
+@pytest.fixture(params=[(6, 1 << 26, 0), (10, 3000, 0), (4, 777, 0), (8, 5000, 1)],
+                ids=["dir64", "chunk3000", "dir16-chunk777", "partitioned"])
 def make(request, sim, monkeypatch):
-    dir_log2, chunk = request.param
+    dir_log2, chunk, partitioned = request.param
     monkeypatch.setenv("SMATRIX_DIR_LOG2", str(dir_log2))   # tiny directory: growth on every test
     monkeypatch.setenv("SMATRIX_CHUNK", str(chunk))         # small chunks: multi-chunk batches
+    if partitioned:                                         # chunks re-ordered by directory slice
+        monkeypatch.setenv("SMATRIX_PARTITION_MIN", "16")
+        monkeypatch.setenv("SMATRIX_SLICE_LOG2", "3")
     return lambda: SparseMatrix(_lib_path=sim)
 
 
