@@ -53,6 +53,8 @@ def parse():
     p.add_argument("--ycols", type=int, default=YCOLS)
     p.add_argument("--total-ops", type=int, default=TOTAL_OPS, help="build ops per GPU")
     p.add_argument("--gets", type=int, default=TOTAL_GETS, help="point gets per GPU")
+    p.add_argument("--arena-gib", type=int, default=48,
+                   help="slab memory each matrix reserves at smatrix_open (SMATRIX_ARENA_GIB); 0 = on demand")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-probes", action="store_true")
@@ -182,6 +184,8 @@ def main_ours(a):
             raise SystemExit("launch N>1 with torchrun (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if a.arena_gib:
+        os.environ["SMATRIX_ARENA_GIB"] = str(a.arena_gib)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -255,8 +259,14 @@ def main_ours(a):
     barrier()
     wall0 = time.time()
     m.timer_start()
+    step_ms, kern_ms, prev_k = [], [], 0
     for j in range(K):
-        m.incr_batch(xs[j], ys[j], None)
+        t_s = time.perf_counter()
+        m.incr_batch(xs[j], ys[j], None)        # synchronous: returns when the device is done
+        step_ms.append(round((time.perf_counter() - t_s) * 1e3, 2))
+        k_now = m.stat("kernel_ns")
+        kern_ms.append(round((k_now - prev_k) / 1e6, 2))
+        prev_k = k_now
     ms_build = m.timer_stop_ms()
     barrier()
     wall1 = time.time()
@@ -336,8 +346,14 @@ def main_ours(a):
     upsert_launches = max(rounds, 1)
     ops_per_launch = K * B / upsert_launches
     ach = INCR_BYTES * K * B / (upsert_ns * 1e-9) / 1e9 if upsert_ns else None
+    traffic = None
+    try:   # dram bytes per op of k_upsert from the committed ncu capture (profiles/), scaled to one launch
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
+            traffic = json.load(f)["upsert_dram_bytes_per_op"] * ops_per_launch
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_upsert<INCR>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_op": INCR_BYTES, "ops_per_launch": ops_per_launch,
                 "launches": upsert_launches, "avg_launch_ms": upsert_ns / upsert_launches / 1e6 if upsert_ns else None,
                 "kernel_share_of_step": upsert_ns / 1e6 / ms_build if upsert_ns else None}
@@ -361,11 +377,14 @@ def main_ours(a):
                    "rows": rows_total, "ycols": a.ycols, "ops_per_step": B * world, "timed_ops": K * B * world,
                    "prefill_ops": prefill * B * world, "gets": G * world,
                    "l2": "inputs larger than L2 (512 MiB of keys per step, table >> 126 MB)",
+                   "arena_gib": a.arena_gib, "arena_note": "slab arena reserved by smatrix_open (outside the timed region); "
+                   "on-demand cudaMalloc is the fallback and costs 0.3-8 ms/step on this pool",
+                   "chunk_ops": int(os.environ.get("SMATRIX_CHUNK", 1 << 25)),
                    "parallelism": f"row-hash shard x{world}" if world > 1 else "single GPU"},
         "get_mops": get_mops, "get_ms": ms_get, "get_hit_fraction": hits / G,
         "nnz": nnz_total, "rows_present": rows_seen, "prefill_s": t_prefill,
         "table": stats, "clocks": clocks, "gpu_launches": launches, "upsert_rounds": rounds,
-        "host_phase_ms_per_step": phases,
+        "host_phase_ms_per_step": phases, "step_ms": step_ms, "step_upsert_kernel_ms": kern_ms,
         "roofline": roofline,
     }
     if e2e:

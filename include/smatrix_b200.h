@@ -12,7 +12,10 @@
 extern "C" {
 #endif
 
-/* smatrix_open on an explicit CUDA device ordinal (smatrix_open uses $SMATRIX_DEVICE, default 0). */
+/* smatrix_open on an explicit CUDA device ordinal (smatrix_open uses $SMATRIX_DEVICE, default 0).
+ * Environment read at open: SMATRIX_ARENA_GIB (reserve that much slab memory up front instead of
+ * cudaMalloc'ing segments on demand), SMATRIX_CHUNK (ops per internal chunk, default 2^25),
+ * SMATRIX_DIR_LOG2 (initial directory size), SMATRIX_PREAGG (warp pre-aggregation on/off). */
 smatrix_t* smatrix_b200_open(const char* fname, int device);
 
 int   smatrix_b200_device(smatrix_t* self);   /* CUDA device ordinal                            */

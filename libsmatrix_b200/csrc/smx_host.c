@@ -31,10 +31,10 @@
 #include "smx_internal.h"
 
 #define SMX_DIR_LOG_DEFAULT 20u
-#define SMX_CHUNK_DEFAULT (1u << 26)
+#define SMX_CHUNK_DEFAULT (1u << 25) /* measured sweet spot on B200 */
 #define SMX_STAGE_MAX (1u << 24)
 #define SMX_SEG_MIN ((size_t)64 << 20)
-#define SMX_SEG_MAX ((size_t)8 << 30)
+#define SMX_SEG_MAX ((size_t)16 << 30)
 #define SMX_MAX_ROUNDS 128
 
 typedef struct {
@@ -59,6 +59,7 @@ struct smatrix_s {
   int nsegs, segs_cap;
   size_t slab_bytes; /* handed out */
   size_t seg_bytes;  /* held */
+  size_t arena_bytes; /* slab memory reserved at open (SMATRIX_ARENA_GIB) */
 
   uint32_t chunk_max;
   uint32_t list_cap;
@@ -75,6 +76,8 @@ struct smatrix_s {
   uint32_t part_cap;
   uint32_t part_min; /* chunks smaller than this are applied in input order */
   uint32_t slice_log; /* log2(directory entries per slice) */
+  uint32_t parts_log_max; /* at most 2^this parts (<= 8) */
+
 
   uint32_t* d_small; /* 64 words */
   uint32_t* h_small; /* pinned, 64 words */
@@ -166,34 +169,44 @@ static void read_ctl(smatrix_t* s) {
 }
 
 /* ------------------------------------------------------------------------------ slab */
-/* A contiguous, 128-byte aligned device region of `bytes` (not zeroed). */
-static char* slab_reserve(smatrix_t* s, size_t bytes) {
-  bytes = (bytes + 127) & ~(size_t)127;
-  if (s->nsegs) {
-    smx_seg_t* g = &s->segs[s->nsegs - 1];
-    if (g->size - g->used >= bytes) {
-      char* p = g->base + g->used;
-      g->used += bytes;
-      s->slab_bytes += bytes;
-      return p;
-    }
-  }
-  size_t want = s->seg_bytes; /* geometric: each new segment doubles what is held */
+static size_t next_segment_size(smatrix_t* s) { /* geometric x4: 64 MiB, 256 MiB, 1 GiB, 4, 16, 16, ... */
+  size_t want = s->nsegs ? s->segs[s->nsegs - 1].size * 4 : SMX_SEG_MIN;
   if (want < SMX_SEG_MIN) want = SMX_SEG_MIN;
   if (want > SMX_SEG_MAX) want = SMX_SEG_MAX;
-  if (want < bytes) want = bytes;
+  return want;
+}
+
+static void push_segment(smatrix_t* s, char* base, size_t size) {
   if (s->nsegs == s->segs_cap) {
     s->segs_cap = s->segs_cap ? s->segs_cap * 2 : 16;
     s->segs = (smx_seg_t*)realloc(s->segs, sizeof(smx_seg_t) * (size_t)s->segs_cap);
     if (!s->segs) smx_die("out of host memory");
   }
   smx_seg_t* g = &s->segs[s->nsegs++];
-  g->base = (char*)dmalloc(s, want);
-  g->size = want;
-  g->used = bytes;
-  s->seg_bytes += want;
+  g->base = base;
+  g->size = size;
+  g->used = 0;
+  s->seg_bytes += size;
+}
+
+/* A contiguous, 128-byte aligned device region of `bytes` (not zeroed).  Carved from the arena
+ * reserved at open when there is one; otherwise (or once it is exhausted) from segments that are
+ * cudaMalloc'ed on demand, x4 geometric.  On-demand cudaMalloc costs 2-10 ms per call on B200
+ * hosts and far more when the driver has to scrub recently freed memory, which is why a
+ * long-lived table should reserve its arena up front (SMATRIX_ARENA_GIB). */
+static char* slab_reserve(smatrix_t* s, size_t bytes) {
+  bytes = (bytes + 127) & ~(size_t)127;
+  smx_seg_t* g = s->nsegs ? &s->segs[s->nsegs - 1] : NULL;
+  if (!g || g->size - g->used < bytes) {
+    size_t size = next_segment_size(s);
+    if (size < bytes) size = bytes;
+    push_segment(s, (char*)dmalloc(s, size), size);
+    g = &s->segs[s->nsegs - 1];
+  }
+  char* p = g->base + g->used;
+  g->used += bytes;
   s->slab_bytes += bytes;
-  return g->base;
+  return p;
 }
 
 /* ------------------------------------------------------------------------------ scratch */
@@ -331,7 +344,8 @@ static void run_pass(smatrix_t* s, smx_ops_t ops, int op, int pass, const uint32
     if (c.n_defer == 0) break;
     if (c.n_dirfull) {
       /* n_dirfull counts refused OPS, an upper bound on the new rows: grow towards it but at most
-       * x8 per round, so duplicate-heavy chunks do not allocate a huge transient directory */
+       * x8 per round, so duplicate-heavy chunks do not allocate a huge transient directory;
+       * maybe_shrink_dir() trims an over-shoot after the chunk */
       uint64_t need = 2 * (c.dir_used + (uint64_t)c.n_dirfull);
       uint64_t cap = pow2_at_least(need);
       if (cap < s->dir_cap * 2) cap = s->dir_cap * 2;
@@ -365,7 +379,7 @@ static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
   uint32_t dir_log = 0;
   while ((1ull << dir_log) < s->dir_cap) dir_log++;
   uint32_t parts_log = dir_log > s->slice_log ? dir_log - s->slice_log : 0; /* default: slices of 2^17 entries = 8 MiB */
-  if (parts_log > 7) parts_log = 7; /* 128 parts: a 2048-op tile still writes 64-byte runs */
+  if (parts_log > s->parts_log_max) parts_log = s->parts_log_max;
   if (parts_log == 0) return;
   const uint32_t parts = 1u << parts_log, shift = dir_log - parts_log;
   if (n > s->part_cap) {
@@ -414,6 +428,7 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   ensure_lists(s, n);
   smx_ops_t ops;
   ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = d_ords; ops.v_const = 1u; ops.n = n;
+
   if (n >= s->part_min) partition_chunk(s, &ops);
   const int op = (api_op == 2) ? SMX_OP_SETZERO : api_op;
   CK(cudaMemsetAsync(&s->d_ctl->n_late, 0, 2 * sizeof(uint32_t), s->stream));
@@ -779,6 +794,8 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
+  s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
+  if (s->parts_log_max > 8) s->parts_log_max = 8;
   s->dir_cap = 1ull << s->dir_log_min;
   s->dir = (smx_row_t*)dmalloc(s, (size_t)s->dir_cap * sizeof(smx_row_t));
   CK(cudaMemsetAsync(s->dir, 0, (size_t)s->dir_cap * sizeof(smx_row_t), s->stream));
@@ -786,6 +803,8 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(smx_ctl_t), s->stream));
   CK(cudaHostAlloc((void**)&s->h_ctl, sizeof(smx_ctl_t), cudaHostAllocDefault));
   memset(s->h_ctl, 0, sizeof(smx_ctl_t));
+  s->arena_bytes = (size_t)env_u32("SMATRIX_ARENA_GIB", 0) << 30;
+  if (s->arena_bytes) push_segment(s, (char*)dmalloc(s, s->arena_bytes), s->arena_bytes);
   s->d_small = (uint32_t*)dmalloc(s, 64 * 4);
   CK(cudaHostAlloc((void**)&s->h_small, 64 * 4, cudaHostAllocDefault));
   CK(cudaStreamSynchronize(s->stream));

@@ -175,8 +175,10 @@ __device__ __forceinline__ void apply_value(uint32_t* vp, uint32_t v) {
   else *(volatile uint32_t*)vp = 0u;
 }
 
-/* SLOT_FULL: bucket at its load limit (caller defers the op); SLOT_DONE; SLOT_DONE_GROW: done, and
- * the row crossed 3/4 of its load limit — ask for growth now so that later ops are not deferred */
+/* Two thresholds per bucket: above `soft` (1/2 load, the reference's own limit, src/smatrix.c:346)
+ * the row asks for growth (SLOT_DONE_GROW) but keeps accepting new columns up to `hard` (7/8
+ * load); only then is an op turned away (SLOT_FULL, re-run after the growth).  Final bucket sizes
+ * are the same as with a single 1/2 limit, but ops are almost never deferred. */
 enum { SLOT_FULL = 0, SLOT_DONE = 1, SLOT_DONE_GROW = 2 };
 template <int OP>
 __device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t y, uint32_t v,
@@ -184,7 +186,8 @@ __device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t 
   const uint32_t caplog = h.meta & SMX_META_CAPLOG;
   ull* base = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
   const uint32_t nsec = 1u << (caplog - 2u);
-  const uint32_t limit = (caplog == SMX_INLINE_LOG) ? 4u : (1u << (caplog - 1u));
+  const uint32_t soft = (caplog == SMX_INLINE_LOG) ? 4u : (1u << (caplog - 1u));
+  const uint32_t hard = (caplog == SMX_INLINE_LOG) ? 4u : (1u << caplog) - (1u << (caplog - 3u));
   const uint32_t init = (OP == SMX_OP_INCR) ? v : (OP == SMX_OP_DECR) ? (0u - v) : 0u;
   const ull fresh = (ull)y | ((ull)init << 32);
   uint32_t s = smx_mix_col(y) & (nsec - 1u);
@@ -202,13 +205,12 @@ __device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (c[k] != 0ull) continue;
-      if (h.live >= limit) return SLOT_FULL;
+      if (h.live >= hard) return SLOT_FULL;
       ull old = atomicCAS(sec + k, 0ull, fresh);
       if (old == 0ull) { /* new column */
         uint32_t n = atomicAdd(&e->live, 1u) + 1u;
         if (counts_col0 && is_resize_count(n)) atomicOr(&e->meta, SMX_META_D);
-        (void)n;
-        return SLOT_DONE;
+        return (n > soft && caplog < SMX_MAX_CAPLOG) ? SLOT_DONE_GROW : SLOT_DONE;
       }
       if ((uint32_t)old == y) {
         apply_value<OP>((uint32_t*)(sec + k) + 1, v);
