@@ -329,3 +329,48 @@ def scenario_threads_single_ops(make, per_thread: int = 300):
     assert total == 4 * per_thread
     assert all(m.get(100 + t, 1) == 2 * per_thread for t in range(4))
     m.close()
+
+
+def scenario_benchmark_pattern(make, threads: int = 8, rounds: int = 16):
+    """BASELINE config 1: the reference benchmark's fixed pattern (src/smatrix_benchmark.c:29-65),
+    thread t uses offset o = 42 + t and does incr(n+o, i+o, 1); incr(i+o, n+o, 1) over n < 23,
+    i < 22 — a few thousand distinct keys hit over and over (pure pre-aggregation / contention)."""
+    m, ref = make(), checker()
+    n, i = np.meshgrid(np.arange(23, dtype=U32), np.arange(22, dtype=U32), indexing="ij")
+    xs, ys = [], []
+    for t in range(threads):
+        o = U32(42 + t)
+        a = np.stack([n.ravel() + o, i.ravel() + o], axis=1)      # incr(n+o, i+o)
+        b = np.stack([i.ravel() + o, n.ravel() + o], axis=1)      # incr(i+o, n+o)
+        pat = np.stack([a, b], axis=1).reshape(-1, 2)             # interleaved like the C loop
+        xs.append(np.tile(pat[:, 0], rounds)); ys.append(np.tile(pat[:, 1], rounds))
+    # threads interleave arbitrarily in the reference; addition commutes, any order gives the same matrix
+    xs, ys = np.concatenate(xs), np.concatenate(ys)
+    apply_both(m, ref, "incr", xs, ys, np.ones(len(xs), U32))
+    qx, qy = np.meshgrid(np.arange(40, 80, dtype=U32), np.arange(40, 80, dtype=U32))
+    compare(m, ref, np.arange(40, 80), qx.ravel(), qy.ravel())     # benchmark_get_mixed's key space
+    assert int(np.asarray(m.get_batch(qx.ravel(), qy.ravel())).astype(np.uint64).sum()) == len(xs)
+    m.close(); ref.close()
+
+
+def scenario_read_path_zipf(make, n_rows: int = 3000, max_len: int = 20000, seed: int = 31):
+    """BASELINE config 4 shape: rows with Zipf lengths P(k) ~ k^-1.7 on [1, max_len], distinct random
+    uint32 columns >= 1, random non-zero values; rowlen over all rows, then getrow over all rows,
+    compared sorted by column."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(1, max_len + 1, dtype=np.float64)
+    pk = k ** -1.7
+    lens = rng.choice(np.arange(1, max_len + 1), size=n_rows, p=pk / pk.sum())
+    lens[0] = max_len                                        # make sure the longest row exists
+    ids = (np.arange(n_rows, dtype=U32) * U32(2654435761))
+    xs = np.repeat(ids, lens)
+    ys = np.concatenate([rng.choice(2**32 - 2, size=int(L), replace=False).astype(np.uint64) + 1
+                         for L in lens]).astype(U32)
+    vs = rng.integers(1, 2**32, len(xs), dtype=np.uint64).astype(U32)
+    perm = rng.permutation(len(xs))
+    m, ref = make(), checker()
+    apply_both(m, ref, "set", xs[perm], ys[perm], vs[perm])
+    assert (np.asarray(m.rowlen_batch(ids)) == lens).all()    # no column 0 anywhere: rowlen == length
+    sample = rng.integers(0, len(xs), 5000)
+    compare(m, ref, np.concatenate([ids, np.array([1, 2, 3], U32)]), xs[sample], ys[sample])
+    m.close(); ref.close()

@@ -1,0 +1,64 @@
+"""Worker for tests/test_gpu_sharded.py: one rank (= one GPU) of an NCCL group driving the
+row-shard router on the real CUDA library."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from libsmatrix_b200.sharded import ShardedSparseMatrix  # noqa: E402
+from oracle import cpu  # noqa: E402
+
+U32 = np.uint32
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    m = ShardedSparseMatrix(rank, world, rank)
+    ref = cpu.CpuMatrix("reference" if cpu.have_reference() else "port")
+    rng = np.random.default_rng(321)                  # the same global stream on every rank
+    n = 400_000
+    xs = rng.integers(0, 20000, n).astype(U32) * U32(2654435761)
+    ys = rng.integers(0, 120, n).astype(U32)          # includes column 0: order matters for rowlen
+    vs = rng.integers(0, 1000, n).astype(U32)
+    t = lambda a: torch.from_numpy(a.view(np.int32).copy()).to(dev)
+    sl = lambda k: slice(rank * k // world, (rank + 1) * k // world)
+    ref.apply("incr", xs, ys, vs)
+    m.incr_batch(t(xs[sl(n)]), t(ys[sl(n)]), t(vs[sl(n)]))                 # ordered (default)
+    gx = rng.integers(0, 300, 50000).astype(U32) * U32(2654435761)
+    gy = rng.integers(1, 40, 50000).astype(U32)
+    gv = rng.integers(1, 2**32, 50000, dtype=np.uint64).astype(U32)
+    ref.apply("set", gx, gy, gv)
+    m.set_batch(t(gx[sl(50000)]), t(gy[sl(50000)]), t(gv[sl(50000)]))      # last writer in GLOBAL order
+    nz = ys != 0
+    ref.apply("incr", xs[nz], ys[nz], np.ones(int(nz.sum()), U32))
+    k = int(nz.sum())
+    m.incr_batch(t(xs[nz][sl(k)]), t(ys[nz][sl(k)]), None, ordered=False)  # order-free stream
+    allx = np.concatenate([xs, gx]); ally = np.concatenate([ys, gy])
+    qx = np.concatenate([allx[rank::7], rng.integers(0, 2**32, 1000, dtype=np.uint64).astype(U32)])
+    qy = np.concatenate([ally[rank::7], rng.integers(0, 130, 1000).astype(U32)])
+    got = m.get_batch(t(qx), t(qy)).cpu().numpy().view(U32)
+    assert (got == ref.get_many(qx, qy)).all(), f"rank {rank}: sharded get mismatch"
+    rows = np.unique(allx)[rank::world]
+    got = m.rowlen_batch(t(rows)).cpu().numpy().view(U32)
+    assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
+    tot = torch.tensor([m.stat("rows"), m.stat("nnz")], device=dev)
+    dist.all_reduce(tot)
+    o, p = ref.getrow_many(np.unique(allx))
+    assert int(tot[0]) == len(np.unique(allx)) and int(tot[1]) == len(p)
+    m.close(); ref.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank} ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,14 @@ def test_threads_single_ops(make_default):
     ps.scenario_threads_single_ops(make_default, per_thread=200)
 
 
+def test_benchmark_pattern(make):
+    ps.scenario_benchmark_pattern(make, threads=32, rounds=32)      # 1 036 288 ops per cell at T=32 x 32
+
+
+def test_read_path_zipf(make):
+    ps.scenario_read_path_zipf(make, n_rows=20000, max_len=200000)
+
+
 def test_preaggregation_off_is_identical(monkeypatch):
     monkeypatch.setenv("SMATRIX_PREAGG", "0")
     ps.scenario_hot_keys(lambda: SparseMatrix())

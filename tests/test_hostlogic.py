@@ -85,6 +85,14 @@ def test_threads_single_ops(make):
     ps.scenario_threads_single_ops(make, per_thread=100)
 
 
+def test_benchmark_pattern(make):
+    ps.scenario_benchmark_pattern(make, threads=4, rounds=3)
+
+
+def test_read_path_zipf(make):
+    ps.scenario_read_path_zipf(make, n_rows=300, max_len=3000)
+
+
 def test_golden_fixtures(make):
     import numpy as np
     from oracle import cpu
