@@ -440,8 +440,23 @@ def run_e2e(a, torch, dev, local, SparseMatrix, B, K, prefill, n_batches):
             "note": "pinned host arrays through smatrix_incr_batch / smatrix_get_batch; wall clock around the call"}
 
 
+def _json_only_stdout():
+    """Everything that C libraries print to fd 1 (NCCL's version banner, ...) goes to stderr; the
+    returned file object is the real stdout for the ONE JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
     args = parse()
+    _REAL_STDOUT = _json_only_stdout()
+    _print = print
+
+    def print(*a, **k):     # noqa: A001 - only the JSON line is printed with flush=True below
+        k.setdefault("file", _REAL_STDOUT)
+        _print(*a, **k)
     if args.impl == "reference":
         main_reference(args)
     else:

@@ -79,6 +79,16 @@ void smatrix_b200_partition(smatrix_t* self, const uint32_t* d_xs, const uint32_
                             uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
                             uint32_t* d_out_src /* nullable: original index of each routed op */);
 
+/* Same, and additionally d_out_pos[i] = position of op i in the routed arrays (the inverse
+ * permutation; nullable).  smatrix_b200_gather(out, vals, pos, n): out[i] = vals[pos[i]] puts
+ * answers that came back in routed order into input order. */
+void smatrix_b200_partition2(smatrix_t* self, const uint32_t* d_xs, const uint32_t* d_ys,
+                             const uint32_t* d_vals, size_t n, uint32_t world, uint64_t* h_counts,
+                             uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
+                             uint32_t* d_out_src, uint32_t* d_out_pos);
+void smatrix_b200_gather(smatrix_t* self, uint32_t* d_out, const uint32_t* d_vals,
+                         const uint32_t* d_pos, size_t n);
+
 /* smatrix_{incr,decr,set}_batch (op = 0, 1, 2) on DEVICE arrays whose "input order" is given
  * explicitly: d_ords[i] (unique, < 2^32 - 1) is op i's place in the sequential order the result
  * must be equal to.  Used by the multi-GPU router, where ops arrive permuted: the order decides

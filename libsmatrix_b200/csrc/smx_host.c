@@ -404,7 +404,7 @@ static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
   CK(cudaMemcpyAsync(d_cursors, cur, parts * 8, cudaMemcpyHostToDevice, s->stream));
   smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, (uint32_t)(s->dir_cap - 1),
                                shift, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
-                               s->part[3], ops->idx);
+                               s->part[3], ops->idx, NULL);
   s->n_launches += 2;
   if (s->timing) CK(cudaStreamSynchronize(s->stream));
   s->phase_ns[PH_PARTITION] += now_ns() - t0;
@@ -1005,10 +1005,30 @@ double smatrix_b200_probe_random_atomic(smatrix_t* s, size_t footprint, size_t a
 /* ------------------------------------------------------------------------------ router (K8) */
 uint32_t smatrix_b200_owner(uint32_t x, uint32_t world) { return smx_owner_hash(x) % world; }
 
+void smatrix_b200_gather(smatrix_t* s, uint32_t* d_out, const uint32_t* d_vals, const uint32_t* d_pos,
+                         size_t n) {
+  if (n == 0) return;
+  if (n > 0xFFFFFFFFull) smx_die("gather: batch too large");
+  enter(s);
+  smx_launch_gather(s->stream, d_out, d_vals, d_pos, (uint32_t)n);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
 void smatrix_b200_partition(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
                             const uint32_t* d_vals, size_t n, uint32_t world, uint64_t* h_counts,
                             uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
                             uint32_t* d_out_src) {
+  smatrix_b200_partition2(s, d_xs, d_ys, d_vals, n, world, h_counts, d_out_xs, d_out_ys, d_out_vals,
+                          d_out_src, NULL);
+}
+
+void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
+                             const uint32_t* d_vals, size_t n, uint32_t world, uint64_t* h_counts,
+                             uint32_t* d_out_xs, uint32_t* d_out_ys, uint32_t* d_out_vals,
+                             uint32_t* d_out_src, uint32_t* d_out_pos) {
   if (world == 0 || world > 64) smx_die("partition: world size must be 1..64");
   if (n > 0xFFFFFFFFull) smx_die("partition: batch too large");
   enter(s);
@@ -1028,7 +1048,7 @@ void smatrix_b200_partition(smatrix_t* s, const uint32_t* d_xs, const uint32_t* 
   }
   CK(cudaMemcpyAsync(d_cursors, cur, world * 8, cudaMemcpyHostToDevice, s->stream));
   smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER,
-                               d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL);
+                               d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL, d_out_pos);
   s->n_launches += 2;
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());

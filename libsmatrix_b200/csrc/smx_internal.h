@@ -149,7 +149,10 @@ void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const
                                   uint32_t dir_mask, uint32_t shift,
                                   unsigned long long* cursors /* [world] start offsets */,
                                   uint32_t* oxs, uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
-                                  const uint32_t* src_in /* NULL: osrc = position; else osrc = src_in[position] */);
+                                  const uint32_t* src_in /* NULL: osrc = position; else osrc = src_in[position] */,
+                                  uint32_t* opos /* nullable: opos[input position] = routed position */);
+void smx_launch_gather(smx_stream_t stream, uint32_t* out, const uint32_t* vals, const uint32_t* pos,
+                       uint32_t n);
 uint32_t smx_scan_scratch_items(uint32_t n); /* number of uint64 block sums smx_launch_scan needs */
 int smx_grid_blocks(void);                   /* resident grid size used by the streaming kernels */
 

@@ -798,7 +798,8 @@ k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, uint32_t dir_m
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
                     uint32_t world, uint32_t dir_mask, uint32_t shift, ull* cursors, uint32_t* oxs,
-                    uint32_t* oys, uint32_t* ovs, uint32_t* osrc, const uint32_t* src_in) {
+                    uint32_t* oys, uint32_t* ovs, uint32_t* osrc, const uint32_t* src_in,
+                    uint32_t* opos) {
   __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_v[PART_TILE], s_i[PART_TILE];
   __shared__ uint32_t hist[SMX_MAX_PARTS], off[SMX_MAX_PARTS];
   __shared__ ull gbase[SMX_MAX_PARTS];
@@ -845,9 +846,19 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
       if (ys) oys[at] = s_y[j];
       if (vs) ovs[at] = s_v[j];
       if (osrc) osrc[at] = s_i[j];
+      /* inverse permutation, for reads: input position -> routed position.  A tile's ops land
+       * in one run per part, so a later gather through opos reads long contiguous runs. */
+      if (opos && !src_in) opos[s_i[j]] = (uint32_t)at; /* s_i is the input position when src_in == NULL */
     }
     __syncthreads();
   }
+}
+
+/* out[i] = vals[pos[i]]: un-permute routed answers into input order */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gather(uint32_t* out, const uint32_t* vals, const uint32_t* pos, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = vals[pos[i]];
 }
 
 /* ==========================================================================================
@@ -998,10 +1009,15 @@ extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs
                                              uint32_t dir_mask, uint32_t shift,
                                              unsigned long long* cursors, uint32_t* oxs,
                                              uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
-                                             const uint32_t* src_in) {
+                                             const uint32_t* src_in, uint32_t* opos) {
   if (!n) return;
   SMX_LAUNCH(k_partition_scatter, grid_for((ull)(n + PART_ITEMS - 1) / PART_ITEMS), SMX_BLOCK, st, xs, ys,
-             vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, osrc, src_in);
+             vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, osrc, src_in, opos);
+}
+extern "C" void smx_launch_gather(smx_stream_t st, uint32_t* out, const uint32_t* vals,
+                                  const uint32_t* pos, uint32_t n) {
+  if (!n) return;
+  SMX_LAUNCH(k_gather, grid_for(n), SMX_BLOCK, st, out, vals, pos, n);
 }
 
 extern "C" uint32_t smx_owner_hash(uint32_t x) { return smx_mix_owner(x); }

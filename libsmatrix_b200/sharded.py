@@ -31,7 +31,9 @@ class ShardedSparseMatrix:
     def __init__(self, rank: int, world: int, device: int = 0, group=None, _lib_path: str | None = None):
         self.rank, self.world, self.group = rank, world, group
         self.local = SparseMatrix(device=device, _lib_path=_lib_path)
+        self.router = SparseMatrix(device=device, _lib_path=_lib_path)   # K8 only: never holds data
         self._lib = self.local._lib
+        self._pool = None
         self._cuda = _lib_path is None
         self.dev = torch.device("cuda", device) if self._cuda else torch.device("cpu")
 
@@ -43,17 +45,20 @@ class ShardedSparseMatrix:
         if self._cuda:
             torch.cuda.current_stream(self.dev).synchronize()
 
-    def _partition(self, xs, ys, vals, want_src: bool):
+    def _partition(self, xs, ys, vals, want_src: bool, want_pos: bool = False):
         n = xs.numel()
         oxs, oys = self._buf(n), self._buf(n) if ys is not None else None
         ovs = self._buf(n) if vals is not None else None
         osrc = self._buf(n) if want_src else None
+        opos = self._buf(n) if want_pos else None
         counts = np.zeros(self.world, dtype=np.uint64)
         p = lambda t: t.data_ptr() if t is not None else None
         self._sync_torch()   # inputs may have been produced on torch's stream
-        self._lib.smatrix_b200_partition(self.local._handle(), p(xs), p(ys), p(vals), n, self.world,
-                                         counts.ctypes.data, p(oxs), p(oys), p(ovs), p(osrc))
-        return [int(c) for c in counts], oxs, oys, ovs, osrc
+        # the router has its own handle (own stream + mutex) so that routing the next sub-batch can
+        # overlap the update of the current one
+        self._lib.smatrix_b200_partition2(self.router._handle(), p(xs), p(ys), p(vals), n, self.world,
+                                          counts.ctypes.data, p(oxs), p(oys), p(ovs), p(osrc), p(opos))
+        return [int(c) for c in counts], oxs, oys, ovs, osrc, opos
 
     def _exchange_counts(self, send):
         t = torch.tensor(send, dtype=torch.int64, device=self.dev)
@@ -66,8 +71,8 @@ class ShardedSparseMatrix:
         dist.all_to_all_single(out, t, output_split_sizes=recv, input_split_sizes=send, group=self.group)
         return out
 
-    def _route(self, xs, ys, vals, want_src=False, ordered=False):
-        send, oxs, oys, ovs, osrc = self._partition(xs, ys, vals, want_src or ordered)
+    def _route(self, xs, ys, vals, want_src=False, ordered=False, want_pos=False):
+        send, oxs, oys, ovs, osrc, opos = self._partition(xs, ys, vals, want_src or ordered, want_pos)
         recv = self._exchange_counts(send)
         rx = self._a2a(oxs, send, recv)
         ry = self._a2a(oys, send, recv) if oys is not None else None
@@ -83,18 +88,47 @@ class ShardedSparseMatrix:
             gidx = (osrc.long() + base).to(torch.int32)   # wraps into uint32 bit pattern
             rord = self._a2a(gidx, send, recv)
         self._sync_torch()   # the library runs on its own stream
-        return send, recv, rx, ry, rv, osrc, rord
+        return send, recv, rx, ry, rv, (opos if want_pos else osrc), rord
+
+    PIPELINE_MIN = 1 << 23      # order-free batches at least this big are routed in overlapped pieces
+    PIPELINE_PIECE = 1 << 24
 
     def _write(self, op: int, xs, ys, vals, ordered: bool):
-        _, _, rx, ry, rv, _, rord = self._route(xs, ys, vals, ordered=ordered)
-        if not rx.numel():
-            return
         if ordered:
-            p = lambda t: t.data_ptr() if t is not None else None
-            self._lib.smatrix_b200_apply_ordered(self.local._handle(), op, p(rx), p(ry), p(rv), p(rord),
-                                                 rx.numel())
-        else:
-            (self.local.incr_batch, self.local.decr_batch)[op](rx, ry, rv)
+            _, _, rx, ry, rv, _, rord = self._route(xs, ys, vals, ordered=True)
+            if rx.numel():
+                p = lambda t: t.data_ptr() if t is not None else None
+                self._lib.smatrix_b200_apply_ordered(self.local._handle(), op, p(rx), p(ry), p(rv), p(rord),
+                                                     rx.numel())
+            return
+        apply = (self.local.incr_batch, self.local.decr_batch)[op]
+        n = xs.numel()
+        # every rank must cut the same number of pieces (the exchanges are collective)
+        nmax = torch.tensor([n], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=self.group)
+        pieces = max(1, -(-int(nmax) // self.PIPELINE_PIECE)) if int(nmax) >= self.PIPELINE_MIN else 1
+        if pieces == 1:
+            _, _, rx, ry, rv, _, _ = self._route(xs, ys, vals)
+            if rx.numel():
+                apply(rx, ry, rv)
+            return
+        # route piece j+1 (router handle + NCCL, helper thread) while piece j updates the shard
+        import concurrent.futures as cf
+        if self._pool is None:
+            self._pool = cf.ThreadPoolExecutor(max_workers=1)
+        cut = lambda t, j: None if t is None else t[j * n // pieces:(j + 1) * n // pieces]
+
+        def route(j):
+            if self._cuda:
+                torch.cuda.set_device(self.dev)
+            return self._route(cut(xs, j), cut(ys, j), cut(vals, j))
+        fut = self._pool.submit(route, 0)
+        for j in range(pieces):
+            _, _, rx, ry, rv, _, _ = fut.result()
+            if j + 1 < pieces:
+                fut = self._pool.submit(route, j + 1)
+            if rx.numel():
+                apply(rx, ry, rv)
 
     # ------------------------------------------------------------------ collective batch API
     def incr_batch(self, xs, ys, vals=None, ordered: bool = True):
@@ -107,23 +141,27 @@ class ShardedSparseMatrix:
         self._write(2, xs, ys, vals, True)     # last writer in GLOBAL input order wins
 
     def get_batch(self, xs, ys, out=None):
-        send, recv, rx, ry, _, osrc, _ = self._route(xs, ys, None, want_src=True)
+        send, recv, rx, ry, _, opos, _ = self._route(xs, ys, None, want_pos=True)
         ans = self.local.get_batch(rx, ry) if rx.numel() else self._buf(0)
         self._sync_torch()
         back = self._a2a(ans, recv, send)           # answers travel the reverse way
+        return self._unpermute(back, opos, out)
+
+    def _unpermute(self, back, opos, out=None):
+        """out[i] = back[opos[i]] — answers arrive in routed order."""
         if out is None:
-            out = self._buf(xs.numel())
-        out[osrc.long()] = back                      # un-permute into input order
+            out = self._buf(opos.numel())
+        self._sync_torch()
+        self._lib.smatrix_b200_gather(self.router._handle(), out.data_ptr(), back.data_ptr(),
+                                      opos.data_ptr(), opos.numel())
         return out
 
     def rowlen_batch(self, xs):
-        send, recv, rx, _, _, osrc, _ = self._route(xs, None, None, want_src=True)
+        send, recv, rx, _, _, opos, _ = self._route(xs, None, None, want_pos=True)
         ans = self.local.rowlen_batch(rx) if rx.numel() else self._buf(0)
         self._sync_torch()
         back = self._a2a(ans, recv, send)
-        out = self._buf(xs.numel())
-        out[osrc.long()] = back
-        return out
+        return self._unpermute(back, opos)
 
     # ------------------------------------------------------------------ local controls
     def stat(self, name):
@@ -134,4 +172,8 @@ class ShardedSparseMatrix:
         return getattr(self.local, name)
 
     def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        self.router.close()
         self.local.close()

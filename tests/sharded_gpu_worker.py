@@ -41,6 +41,7 @@ def main():
     nz = ys != 0
     ref.apply("incr", xs[nz], ys[nz], np.ones(int(nz.sum()), U32))
     k = int(nz.sum())
+    m.PIPELINE_MIN, m.PIPELINE_PIECE = 50_000, 40_000                      # force the overlapped pieces
     m.incr_batch(t(xs[nz][sl(k)]), t(ys[nz][sl(k)]), None, ordered=False)  # order-free stream
     allx = np.concatenate([xs, gx]); ally = np.concatenate([ys, gy])
     qx = np.concatenate([allx[rank::7], rng.integers(0, 2**32, 1000, dtype=np.uint64).astype(U32)])

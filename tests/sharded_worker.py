@@ -35,6 +35,13 @@ def main():
     k = len(sx)
     part = slice(rank * k // world, (rank + 1) * k // world)
     m.decr_batch(t(sx[part]), t(sy[part]), t(sv[part]))
+    # order-free stream (no column 0), routed in overlapped pieces by the helper thread
+    m.PIPELINE_MIN, m.PIPELINE_PIECE = 1000, 1500
+    fx = rng.integers(0, 3000, 9000).astype(np.uint32) * np.uint32(2654435761)
+    fy = rng.integers(1, 60, 9000).astype(np.uint32)
+    ref.apply("incr", fx, fy, np.ones(9000, np.uint32))
+    fs = slice(rank * 9000 // world, (rank + 1) * 9000 // world)
+    m.incr_batch(t(fx[fs]), t(fy[fs]), None, ordered=False)
     # set with duplicate keys across ranks: the last writer in GLOBAL input order must win
     gx = rng.integers(0, 50, 6000).astype(np.uint32) * np.uint32(2654435761)
     gy = rng.integers(1, 20, 6000).astype(np.uint32)
