@@ -184,8 +184,18 @@ def main_ours(a):
             raise SystemExit("launch N>1 with torchrun (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if a.arena_gib:
-        os.environ["SMATRIX_ARENA_GIB"] = str(a.arena_gib)
+    os.environ.pop("SMATRIX_ARENA_GIB", None)
+
+    def with_arena(make):
+        """Only matrices that hold the table reserve the slab arena (helper handles do not)."""
+        def wrapped():
+            if a.arena_gib:
+                os.environ["SMATRIX_ARENA_GIB"] = str(a.arena_gib)
+            try:
+                return make()
+            finally:
+                os.environ.pop("SMATRIX_ARENA_GIB", None)
+        return wrapped
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -213,9 +223,9 @@ def main_ours(a):
         class _Unordered(ShardedSparseMatrix):   # the C2 stream never writes column 0: order-free
             def incr_batch(self, xs, ys, vals=None):
                 super().incr_batch(xs, ys, vals, ordered=False)
-        mk = lambda: _Unordered(rank, world, local)
+        mk = with_arena(lambda: _Unordered(rank, world, local))
     else:
-        mk = lambda: SparseMatrix(device=local)
+        mk = with_arena(lambda: SparseMatrix(device=local))
 
     sampler = ClockSampler(local)
     ibuf = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
@@ -321,7 +331,7 @@ def main_ours(a):
     # ---- e2e: the same build through host (pinned) buffers
     e2e = None
     if not a.no_e2e and world == 1:
-        e2e = run_e2e(a, torch, dev, local, SparseMatrix, B, K, prefill, n_batches)
+        e2e = run_e2e(a, torch, dev, local, with_arena(lambda: SparseMatrix(device=local)), B, K, prefill, n_batches)
 
     if world > 1:
         t = torch.tensor([nnz_local, rows_local], dtype=torch.int64, device=dev)
@@ -396,10 +406,10 @@ def main_ours(a):
         dist.destroy_process_group()
 
 
-def run_e2e(a, torch, dev, local, SparseMatrix, B, K, prefill, n_batches):
+def run_e2e(a, torch, dev, local, make_matrix, B, K, prefill, n_batches):
     """Same stream, HOST buffers: each timed step is one smatrix_incr_batch(host pointers) call —
     H2D of the batch, the update, and the D2H reads of the control block."""
-    m = SparseMatrix(device=local)
+    m = make_matrix()
     dx = torch.empty(B, dtype=torch.int32, device=dev)
     dy = torch.empty(B, dtype=torch.int32, device=dev)
     hx = torch.empty(B, dtype=torch.int32, pin_memory=True)

@@ -434,6 +434,10 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   CK(cudaMemsetAsync(&s->d_ctl->n_late, 0, 2 * sizeof(uint32_t), s->stream));
   run_pass(s, ops, op, SMX_PASS_COL0, NULL, n);
   run_pass(s, ops, op, SMX_PASS_EARLY, NULL, n);
+  if (s->h_ctl->n_t0) { /* column 0 of these rows turns non-zero now: sync their rowlen state (z = 0 so far) */
+    smx_launch_sync_rowlen(s->stream, view_of(s), s->lists.t0rows, s->h_ctl->n_t0);
+    s->n_launches++;
+  }
   const uint32_t n_late = s->h_ctl->n_late;
   if (n_late) run_pass(s, ops, op, SMX_PASS_LATE, s->lists.late, n_late);
   if (api_op == 2) { /* set: last writer in input order wins */

@@ -32,6 +32,8 @@ extern "C" {
 #define SMX_META_USED   0x100u  /* entry holds a row                                         */
 #define SMX_META_ZC     0x200u  /* column 0 was already non-zero when the current batch began */
 #define SMX_META_D      0x400u  /* rowlen = live + 1: a virtual resize counted column 0 (Q1)  */
+#define SMX_META_SLOG_SHIFT 16  /* bits 16..20: log2(reference row size) - 4, as of the last sync */
+#define SMX_META_SLOG   (0x1Fu << SMX_META_SLOG_SHIFT)
 #define SMX_META_T0P    0x800u  /* column 0 turns non-zero inside the current batch at t0     */
 #define SMX_META_GROW   0x1000u /* row is queued for growth in the current round              */
 #define SMX_INLINE_LOG  2u
@@ -117,6 +119,7 @@ void smx_launch_migrate(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32
                         uint32_t n_big, void* region_base);
 void smx_launch_dir_rehash(smx_stream_t stream, smx_view_t from, smx_view_t to);
 void smx_launch_finalize_t0(smx_stream_t stream, smx_view_t v, const uint32_t* t0rows, uint32_t n);
+void smx_launch_sync_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* rows, uint32_t n);
 void smx_launch_set_max(smx_stream_t stream, smx_view_t v, smx_ops_t ops, uint64_t* addrs);
 void smx_launch_set_commit(smx_stream_t stream, smx_ops_t ops, uint64_t* addrs); /* mark + commit */
 void smx_launch_get(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* ys,

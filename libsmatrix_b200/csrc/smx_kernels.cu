@@ -123,10 +123,25 @@ __device__ __forceinline__ void agg_inc64(ull* ctr) {
   if ((int)lane_id() == __ffs(m) - 1) atomicAdd(ctr, (ull)__popc(m));
 }
 
-/* the n-th distinct non-zero column of a row triggers one of the reference's row resizes
- * (src/smatrix.c:346, 16 cells doubling) while column 0 is still uncounted: n = 2^j + 2, j >= 3 */
-__device__ __forceinline__ bool is_resize_count(uint32_t n) {
-  return n >= 10u && (((n - 2u) & (n - 3u)) == 0u);
+/* rowlen: the reference returns its running `used` counter (src/smatrix.c:212-223).  With L =
+ * number of columns != 0 in the row, used = L + d where the pair (S, d) follows the reference's
+ * automaton: inserting a new column when L_before + d > S/2 doubles S (src/smatrix.c:346-348) and
+ * recounts, which makes d = (column 0 is non-zero at that moment) (:397-402).  Because that rule is
+ * monotone in L, the state can be caught up lazily from (S, d) as of any earlier moment as long
+ * as z = (c0 != 0) did not change in between: the loop below gives the same (S, d) as stepping
+ * through every insertion.  The table therefore only has to materialise the state right before z
+ * flips (k_sync_rowlen); the hot update kernel never touches it. */
+__host__ __device__ __forceinline__ uint32_t rowlen_catch_up(uint32_t meta, uint32_t live, bool z) {
+  uint32_t slog = 4u + ((meta & SMX_META_SLOG) >> SMX_META_SLOG_SHIFT);
+  uint32_t d = (meta & SMX_META_D) ? 1u : 0u;
+  if (live) {
+    const ull last = (ull)live - 1u; /* L_before of the latest insertion */
+    while (slog < 36u && last + d > (1ull << (slog - 1u))) {
+      ++slog;
+      d = z ? 1u : d;
+    }
+  }
+  return (meta & ~(SMX_META_SLOG | SMX_META_D)) | ((slog - 4u) << SMX_META_SLOG_SHIFT) | (d ? SMX_META_D : 0u);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -181,8 +196,7 @@ __device__ __forceinline__ void apply_value(uint32_t* vp, uint32_t v) {
  * are the same as with a single 1/2 limit, but ops are almost never deferred. */
 enum { SLOT_FULL = 0, SLOT_DONE = 1, SLOT_DONE_GROW = 2 };
 template <int OP>
-__device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t y, uint32_t v,
-                                            bool counts_col0) {
+__device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t y, uint32_t v) {
   const uint32_t caplog = h.meta & SMX_META_CAPLOG;
   ull* base = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
   const uint32_t nsec = 1u << (caplog - 2u);
@@ -208,8 +222,7 @@ __device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t 
       if (h.live >= hard) return SLOT_FULL;
       ull old = atomicCAS(sec + k, 0ull, fresh);
       if (old == 0ull) { /* new column */
-        uint32_t n = atomicAdd(&e->live, 1u) + 1u;
-        if (counts_col0 && is_resize_count(n)) atomicOr(&e->meta, SMX_META_D);
+        const uint32_t n = atomicAdd(&e->live, 1u) + 1u;
         return (n > soft && caplog < SMX_MAX_CAPLOG) ? SLOT_DONE_GROW : SLOT_DONE;
       }
       if ((uint32_t)old == y) {
@@ -278,8 +291,7 @@ __device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t
   if (pass == SMX_PASS_EARLY && (h.meta & SMX_META_T0P)) {
     if (ord > ~h.t0inv) return ST_LATE; /* ordered after column 0 became non-zero */
   }
-  const bool counts_col0 = (pass == SMX_PASS_LATE) || (h.meta & SMX_META_ZC);
-  const int r2 = slot_upsert<OP>(e, h, y, v, counts_col0);
+  const int r2 = slot_upsert<OP>(e, h, y, v);
   if (r2 == SLOT_DONE) return ST_OK;
   if (r2 == SLOT_FULL) atomicAdd(&e->want, 1u);
   if (!(h.meta & SMX_META_GROW)) { /* queue the row for growth, once per round */
@@ -492,6 +504,17 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_dir_rehash(smx_view_t from, smx_v
   (void)moved;
 }
 
+/* between the EARLY and LATE passes: column 0 of these rows turns non-zero HERE in input order, so
+ * bring their (S, d) up to date with z = 0 for the columns inserted so far */
+__global__ void k_sync_rowlen(smx_view_t V, const uint32_t* rows, uint32_t n) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    if (dir_find(V, rows[j], false, &e, &h) != DIR_FOUND) continue;
+    e->meta = rowlen_catch_up(h.meta, h.live, (h.meta & SMX_META_ZC) != 0u);
+  }
+}
+
 /* end of a chunk: column 0 of these rows is now (and stays) non-zero */
 __global__ void k_finalize_t0(smx_view_t V, const uint32_t* t0rows, uint32_t n) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -562,8 +585,10 @@ k_rowlen(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* out) {
     smx_row_t* e;
     Hdr h;
     uint32_t len = 0u;
-    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND)
-      len = h.live + ((h.meta & SMX_META_D) ? 1u : 0u); /* the reference's `used` (Q1) */
+    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) { /* the reference's `used` (Q1) */
+      const uint32_t m2 = rowlen_catch_up(h.meta, h.live, (h.meta & (SMX_META_ZC | SMX_META_T0P)) != 0u);
+      len = h.live + ((m2 & SMX_META_D) ? 1u : 0u);
+    }
     out[i] = len;
   }
 }
@@ -886,7 +911,12 @@ extern "C" void smx_launch_upsert(smx_stream_t st, smx_view_t v, smx_ops_t ops, 
                                   int op, int pass, const uint32_t* list, uint32_t m,
                                   int preaggregate) {
   if (m == 0) return;
-  const uint32_t grid = grid_for(m);
+  /* NOT a persistent grid: one block per 4 x 256 ops, so blocks retire continuously and kernels of
+   * other streams (the multi-GPU router's partition + NCCL copies) interleave with an update in
+   * flight instead of waiting for 1184 resident blocks to drain */
+  ull want_blocks = ((ull)m + 4ull * SMX_BLOCK - 1) / (4ull * SMX_BLOCK);
+  if (want_blocks < 1) want_blocks = 1;
+  const uint32_t grid = (uint32_t)want_blocks;
   const int pre = (preaggregate && !list && pass == SMX_PASS_EARLY && SMX_WARP > 1) ? 1 : 0;
   if (op == SMX_OP_INCR) {
     auto k = k_upsert<SMX_OP_INCR>;
@@ -925,6 +955,11 @@ extern "C" void smx_launch_finalize_t0(smx_stream_t st, smx_view_t v, const uint
                                        uint32_t n) {
   if (!n) return;
   SMX_LAUNCH(k_finalize_t0, grid_for(n), SMX_BLOCK, st, v, t0rows, n);
+}
+
+extern "C" void smx_launch_sync_rowlen(smx_stream_t st, smx_view_t v, const uint32_t* rows, uint32_t n) {
+  if (!n) return;
+  SMX_LAUNCH(k_sync_rowlen, grid_for(n), SMX_BLOCK, st, v, rows, n);
 }
 
 extern "C" void smx_launch_set_max(smx_stream_t st, smx_view_t v, smx_ops_t ops, uint64_t* addrs) {

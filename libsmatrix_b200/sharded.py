@@ -20,6 +20,8 @@ commutes), so the result is identical.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -31,9 +33,16 @@ class ShardedSparseMatrix:
     def __init__(self, rank: int, world: int, device: int = 0, group=None, _lib_path: str | None = None):
         self.rank, self.world, self.group = rank, world, group
         self.local = SparseMatrix(device=device, _lib_path=_lib_path)
-        self.router = SparseMatrix(device=device, _lib_path=_lib_path)   # K8 only: never holds data
+        arena = os.environ.pop("SMATRIX_ARENA_GIB", None)               # the router holds no data:
+        try:                                                             # it must not reserve an arena
+            self.router = SparseMatrix(device=device, _lib_path=_lib_path)   # K8 only
+        finally:
+            if arena is not None:
+                os.environ["SMATRIX_ARENA_GIB"] = arena
         self._lib = self.local._lib
         self._pool = None
+        self._bufs: dict[str, torch.Tensor] = {}
+        self._gen = 0
         self._cuda = _lib_path is None
         self.dev = torch.device("cuda", device) if self._cuda else torch.device("cpu")
 
@@ -41,16 +50,26 @@ class ShardedSparseMatrix:
     def _buf(self, n, like=None):
         return torch.empty(n, dtype=torch.int32, device=self.dev)
 
+    def _slot(self, name: str, n: int):
+        """Grow-only reusable device buffer (no allocator traffic in steady state)."""
+        b = self._bufs.get(name)
+        if b is None or b.numel() < n:
+            b = torch.empty(max(n + n // 8, 1024), dtype=torch.int32, device=self.dev)
+            self._bufs[name] = b
+        return b[:n]
+
     def _sync_torch(self):
         if self._cuda:
             torch.cuda.current_stream(self.dev).synchronize()
 
     def _partition(self, xs, ys, vals, want_src: bool, want_pos: bool = False):
         n = xs.numel()
-        oxs, oys = self._buf(n), self._buf(n) if ys is not None else None
-        ovs = self._buf(n) if vals is not None else None
-        osrc = self._buf(n) if want_src else None
-        opos = self._buf(n) if want_pos else None
+        g = self._gen = (self._gen + 1) % 3      # three generations: routed / in flight / being applied
+        oxs = self._slot(f"ox{g}", n)
+        oys = self._slot(f"oy{g}", n) if ys is not None else None
+        ovs = self._slot(f"ov{g}", n) if vals is not None else None
+        osrc = self._slot(f"os{g}", n) if want_src else None
+        opos = self._slot(f"op{g}", n) if want_pos else None
         counts = np.zeros(self.world, dtype=np.uint64)
         p = lambda t: t.data_ptr() if t is not None else None
         self._sync_torch()   # inputs may have been produced on torch's stream
@@ -66,17 +85,18 @@ class ShardedSparseMatrix:
         dist.all_to_all_single(r, t, group=self.group)
         return [int(v) for v in r.tolist()]
 
-    def _a2a(self, t, send, recv):
-        out = self._buf(sum(recv))
+    def _a2a(self, t, send, recv, name=None):
+        out = self._slot(name, sum(recv)) if name else self._buf(sum(recv))
         dist.all_to_all_single(out, t, output_split_sizes=recv, input_split_sizes=send, group=self.group)
         return out
 
     def _route(self, xs, ys, vals, want_src=False, ordered=False, want_pos=False):
         send, oxs, oys, ovs, osrc, opos = self._partition(xs, ys, vals, want_src or ordered, want_pos)
         recv = self._exchange_counts(send)
-        rx = self._a2a(oxs, send, recv)
-        ry = self._a2a(oys, send, recv) if oys is not None else None
-        rv = self._a2a(ovs, send, recv) if ovs is not None else None
+        g = self._gen
+        rx = self._a2a(oxs, send, recv, f"rx{g}")
+        ry = self._a2a(oys, send, recv, f"ry{g}") if oys is not None else None
+        rv = self._a2a(ovs, send, recv, f"rv{g}") if ovs is not None else None
         rord = None
         if ordered:   # global index = (ops in the slices of lower ranks) + index inside my slice
             sizes = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
@@ -175,5 +195,7 @@ class ShardedSparseMatrix:
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None
+        self._bufs: dict[str, torch.Tensor] = {}
+        self._gen = 0
         self.router.close()
         self.local.close()

@@ -114,3 +114,15 @@ class ModelMatrix:
 
 class UnsafeDomain(Exception):
     """The op stream left the domain on which the reference's result is layout independent."""
+
+
+def catch_up(slog: int, d: int, live: int, z: bool) -> tuple[int, int]:
+    """The lazy form of the (S, d) automaton the CUDA table uses (smx_kernels.cu rowlen_catch_up):
+    given the state as of some earlier moment and the current number of columns, with z = (c0 != 0)
+    constant in between, return the state the step-by-step reference automaton would be in."""
+    if live:
+        last = live - 1
+        while last + d > (1 << (slog - 1)):
+            slog += 1
+            d = 1 if z else d
+    return slog, d

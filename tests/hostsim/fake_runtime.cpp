@@ -4,8 +4,8 @@
 #include <map>
 #include <mutex>
 
-uint3_sim blockIdx, threadIdx;
-dim3 gridDim, blockDim;
+thread_local uint3_sim blockIdx, threadIdx;
+thread_local dim3 gridDim, blockDim;
 
 static std::map<uintptr_t, size_t> g_dev;   // "device" allocations
 static std::mutex g_mu;

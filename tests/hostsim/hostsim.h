@@ -16,7 +16,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __shared__ static
+#define __shared__ static thread_local /* two host threads may run 'kernels' at once */
 #define __restrict__
 #define __launch_bounds__(...)
 
@@ -25,8 +25,8 @@ struct dim3 {
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 struct uint3_sim { unsigned x, y, z; };
-extern uint3_sim blockIdx, threadIdx;
-extern dim3 gridDim, blockDim;
+extern thread_local uint3_sim blockIdx, threadIdx;
+extern thread_local dim3 gridDim, blockDim;
 
 template <class F>
 static inline void smx_sim_launch(dim3 g, dim3 b, F f) {

@@ -215,3 +215,36 @@ def _replay_golden(make_matrix):
 def test_golden_fixtures(kind):
     """tests/golden/*.npz were recorded from the unmodified reference (make_golden.py)."""
     _replay_golden(lambda: cpu.CpuMatrix(kind))
+
+
+def test_lazy_rowlen_automaton_equals_stepwise():
+    """catching the (S, d) state up lazily gives the reference's `used` as long as the
+    state is synced right before column 0 turns non-zero."""
+    from oracle.model import catch_up
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n_total = int(rng.integers(1, 700))
+        flip = int(rng.integers(0, n_total + 1))          # column 0 becomes non-zero after `flip` inserts
+        checkpoints = sorted(set(int(c) for c in rng.integers(0, n_total + 1, 4)) | {flip, n_total})
+        # step-by-step reference automaton
+        S, U, L, z = 16, 0, 0, False
+        want = {}
+        for n in range(n_total + 1):
+            if n == flip:
+                z = True
+            if n in checkpoints:
+                want[n] = U
+            if n < n_total:
+                if U > S // 2:
+                    S *= 2
+                    U = L + (1 if z else 0)
+                U += 1
+                L += 1
+        # lazy: sync only at the flip, evaluate at arbitrary checkpoints
+        slog, d, z = 4, 0, False
+        for c in checkpoints:
+            if c == flip:
+                slog, d = catch_up(slog, d, c, False)     # the k_sync_rowlen moment
+                z = True
+            s2, d2 = catch_up(slog, d, c, z)
+            assert c + d2 == want[c], (n_total, flip, c)
