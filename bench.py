@@ -198,7 +198,8 @@ def main_ours(a):
         return wrapped
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # all-to-all under the update
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     def barrier():
         torch.cuda.synchronize()

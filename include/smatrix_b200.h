@@ -89,6 +89,23 @@ void smatrix_b200_partition2(smatrix_t* self, const uint32_t* d_xs, const uint32
 void smatrix_b200_gather(smatrix_t* self, uint32_t* d_out, const uint32_t* d_vals,
                          const uint32_t* d_pos, size_t n);
 
+/* K8 fused with the exchange (peer memory over NVLink instead of an NCCL all-to-all).
+ * smatrix_b200_partition_count: ops per owner for a device batch.
+ * smatrix_b200_route_p2p: bucket by owner and write every owner's run straight to the addresses in
+ *   h_dst[5][world] = { x, y, v, src (0 = not wanted) output bases, routed-position bases } — local
+ *   memory or peer mappings obtained with smatrix_b200_ipc_open (cudaIpc handles of buffers that a
+ *   peer allocated with smatrix_b200_dev_alloc and exported with smatrix_b200_ipc_export).  src
+ *   values are (index in this batch + src_bias); d_out_pos (nullable) receives, per op, its
+ *   position in routed order (pos_base[owner] + index inside the owner's run). */
+void smatrix_b200_partition_count(smatrix_t* self, const uint32_t* d_xs, size_t n, uint32_t world,
+                                  uint64_t* h_counts);
+void smatrix_b200_route_p2p(smatrix_t* self, const uint32_t* d_xs, const uint32_t* d_ys,
+                            const uint32_t* d_vals, size_t n, uint32_t world, const uint64_t* h_dst,
+                            uint32_t src_bias, uint32_t* d_out_pos);
+int   smatrix_b200_ipc_export(smatrix_t* self, void* dptr, unsigned char* handle64);
+void* smatrix_b200_ipc_open(smatrix_t* self, const unsigned char* handle64);
+void  smatrix_b200_ipc_close(smatrix_t* self, void* p);
+
 /* smatrix_{incr,decr,set}_batch (op = 0, 1, 2) on DEVICE arrays whose "input order" is given
  * explicitly: d_ords[i] (unique, < 2^32 - 1) is op i's place in the sequential order the result
  * must be equal to.  Used by the multi-GPU router, where ops arrive permuted: the order decides

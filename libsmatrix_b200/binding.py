@@ -57,6 +57,12 @@ PROTOTYPES = {
     "smatrix_b200_partition2": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "smatrix_b200_partition_count": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "smatrix_b200_route_p2p": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                      C.c_void_p, C.c_uint32, C.c_void_p]),
+    "smatrix_b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smatrix_b200_ipc_open": (C.c_void_p, [C.c_void_p, C.c_void_p]),
+    "smatrix_b200_ipc_close": (None, [C.c_void_p, C.c_void_p]),
     "smatrix_b200_gather": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "smatrix_b200_apply_ordered": (None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_size_t]),

@@ -404,7 +404,7 @@ static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
   CK(cudaMemcpyAsync(d_cursors, cur, parts * 8, cudaMemcpyHostToDevice, s->stream));
   smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, (uint32_t)(s->dir_cap - 1),
                                shift, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
-                               s->part[3], ops->idx, NULL);
+                               s->part[3], ops->idx, NULL, NULL, 0);
   s->n_launches += 2;
   if (s->timing) CK(cudaStreamSynchronize(s->stream));
   s->phase_ns[PH_PARTITION] += now_ns() - t0;
@@ -781,7 +781,14 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   if (!s) return NULL;
   s->device = device;
   pthread_mutex_init(&s->mu, NULL);
-  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (env_u32("SMATRIX_STREAM_HIGH_PRIORITY", 0)) { /* router handles: their kernels must interleave
+                                                       with an update in flight on another handle */
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi));
+  } else {
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  }
   CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&s->stage_ready[0], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s->stage_ready[1], cudaEventDisableTiming));
@@ -1006,7 +1013,73 @@ double smatrix_b200_probe_random_atomic(smatrix_t* s, size_t footprint, size_t a
   return (double)accesses / ((double)ms * 1e-3);
 }
 
+/* ------------------------------------------------------------------------------ peer memory */
+int smatrix_b200_ipc_export(smatrix_t* s, void* dptr, unsigned char* handle64) {
+  cudaIpcMemHandle_t h;
+  enter(s);
+  cudaError_t e = cudaIpcGetMemHandle(&h, dptr);
+  leave(s);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  memcpy(handle64, &h, sizeof h);
+  return 0;
+}
+void* smatrix_b200_ipc_open(smatrix_t* s, const unsigned char* handle64) {
+  cudaIpcMemHandle_t h;
+  void* p = NULL;
+  memcpy(&h, handle64, sizeof h);
+  enter(s);
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  leave(s);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
+  return p;
+}
+void smatrix_b200_ipc_close(smatrix_t* s, void* p) {
+  enter(s);
+  if (p) (void)cudaIpcCloseMemHandle(p);
+  leave(s);
+}
+
 /* ------------------------------------------------------------------------------ router (K8) */
+void smatrix_b200_partition_count(smatrix_t* s, const uint32_t* d_xs, size_t n, uint32_t world,
+                                  uint64_t* h_counts) {
+  if (world == 0 || world > 64) smx_die("partition: world size must be 1..64");
+  if (n > 0xFFFFFFFFull) smx_die("partition: batch too large");
+  enter(s);
+  ensure_tmp(s, 0, (2 * 64 + 5 * 64) * 8);
+  unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
+  unsigned long long h[64];
+  CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
+  smx_launch_partition_count(s->stream, d_xs, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
+  CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  for (uint32_t r = 0; r < world; r++) h_counts[r] = h[r];
+  s->n_launches++;
+  leave(s);
+}
+
+/* K8 fused with the exchange: bucket by owner and write every owner's run straight to
+ * h_dst[0..4][world] = {x, y, v, src (0 = none) output base addresses, routed-position bases}
+ * (peer mappings or local memory), see k_partition_scatter. */
+void smatrix_b200_route_p2p(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
+                            const uint32_t* d_vals, size_t n, uint32_t world, const uint64_t* h_dst,
+                            uint32_t src_bias, uint32_t* d_out_pos) {
+  if (world == 0 || world > 64) smx_die("route: world size must be 1..64");
+  if (n == 0) return;
+  if (n > 0xFFFFFFFFull) smx_die("route: batch too large");
+  enter(s);
+  ensure_tmp(s, 0, (2 * 64 + 5 * 64) * 8);
+  unsigned long long* d_cursors = (unsigned long long*)s->d_tmp64 + 64;
+  unsigned long long* d_tab = (unsigned long long*)s->d_tmp64 + 128;
+  CK(cudaMemsetAsync(d_cursors, 0, 64 * 8, s->stream));
+  CK(cudaMemcpyAsync(d_tab, h_dst, 5 * (size_t)world * 8, cudaMemcpyHostToDevice, s->stream));
+  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER,
+                               d_cursors, NULL, NULL, NULL, NULL, NULL, d_out_pos, d_tab, src_bias);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
 uint32_t smatrix_b200_owner(uint32_t x, uint32_t world) { return smx_owner_hash(x) % world; }
 
 void smatrix_b200_gather(smatrix_t* s, uint32_t* d_out, const uint32_t* d_vals, const uint32_t* d_pos,
@@ -1052,7 +1125,7 @@ void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t*
   }
   CK(cudaMemcpyAsync(d_cursors, cur, world * 8, cudaMemcpyHostToDevice, s->stream));
   smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER,
-                               d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL, d_out_pos);
+                               d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL, d_out_pos, NULL, 0);
   s->n_launches += 2;
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());

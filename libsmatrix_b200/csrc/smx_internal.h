@@ -153,7 +153,10 @@ void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const
                                   unsigned long long* cursors /* [world] start offsets */,
                                   uint32_t* oxs, uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
                                   const uint32_t* src_in /* NULL: osrc = position; else osrc = src_in[position] */,
-                                  uint32_t* opos /* nullable: opos[input position] = routed position */);
+                                  uint32_t* opos /* nullable: opos[input position] = routed position */,
+                                  const unsigned long long* dst_tab /* nullable, device: [5][world] =
+                                     per-part x / y / v / src output bases + routed-position bases */,
+                                  uint32_t src_bias /* added to every osrc value */);
 void smx_launch_gather(smx_stream_t stream, uint32_t* out, const uint32_t* vals, const uint32_t* pos,
                        uint32_t n);
 uint32_t smx_scan_scratch_items(uint32_t n); /* number of uint64 block sums smx_launch_scan needs */

@@ -824,8 +824,8 @@ __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
                     uint32_t world, uint32_t dir_mask, uint32_t shift, ull* cursors, uint32_t* oxs,
                     uint32_t* oys, uint32_t* ovs, uint32_t* osrc, const uint32_t* src_in,
-                    uint32_t* opos) {
-  __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_v[PART_TILE], s_i[PART_TILE];
+                    uint32_t* opos, const ull* dst_tab, uint32_t src_bias) {
+  __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_v[PART_TILE], s_i[PART_TILE], s_p[PART_TILE];
   __shared__ uint32_t hist[SMX_MAX_PARTS], off[SMX_MAX_PARTS];
   __shared__ ull gbase[SMX_MAX_PARTS];
   const uint32_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
@@ -866,15 +866,30 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
     for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
       const uint32_t xx = s_x[j];
       const uint32_t p = part_of(xx, world, dir_mask, shift);
-      const ull at = gbase[p] + (j - off[p]);
-      oxs[at] = xx;
-      if (ys) oys[at] = s_y[j];
-      if (vs) ovs[at] = s_v[j];
-      if (osrc) osrc[at] = s_i[j];
-      /* inverse permutation, for reads: input position -> routed position.  A tile's ops land
-       * in one run per part, so a later gather through opos reads long contiguous runs. */
-      if (opos && !src_in) opos[s_i[j]] = (uint32_t)at; /* s_i is the input position when src_in == NULL */
+      ull at = gbase[p] + (j - off[p]);
+      if (dst_tab) {
+        /* fused with the exchange: part p's run goes straight into owner p's inbox — a peer
+         * mapping over NVLink (or local memory for p == this rank).  dst_tab = [x | y | v | src |
+         * pos_base][world]; the cursors started at 0, so `at` is the index inside my segment. */
+        ((uint32_t*)dst_tab[p])[at] = xx;
+        if (ys) ((uint32_t*)dst_tab[world + p])[at] = s_y[j];
+        if (vs) ((uint32_t*)dst_tab[2 * world + p])[at] = s_v[j];
+        if (dst_tab[3 * world + p]) ((uint32_t*)dst_tab[3 * world + p])[at] = s_i[j] + src_bias;
+        at += dst_tab[4 * world + p]; /* position in the requester's routed order, for opos */
+      } else {
+        oxs[at] = xx;
+        if (ys) oys[at] = s_y[j];
+        if (vs) ovs[at] = s_v[j];
+        if (osrc) osrc[at] = s_i[j] + src_bias;
+      }
+      /* inverse permutation, for reads: input position -> routed position (staged in shared
+       * memory so that it is written coalesced).  A tile's ops land in one run per part, so a
+       * later gather through opos reads long contiguous runs. */
+      if (opos && !src_in) s_p[s_i[j] - base] = (uint32_t)at; /* s_i = input position when src_in == NULL */
     }
+    __syncthreads();
+    if (opos && !src_in)
+      for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) opos[base + j] = s_p[j];
     __syncthreads();
   }
 }
@@ -1044,10 +1059,12 @@ extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs
                                              uint32_t dir_mask, uint32_t shift,
                                              unsigned long long* cursors, uint32_t* oxs,
                                              uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
-                                             const uint32_t* src_in, uint32_t* opos) {
+                                             const uint32_t* src_in, uint32_t* opos,
+                                             const unsigned long long* dst_tab, uint32_t src_bias) {
   if (!n) return;
   SMX_LAUNCH(k_partition_scatter, grid_for((ull)(n + PART_ITEMS - 1) / PART_ITEMS), SMX_BLOCK, st, xs, ys,
-             vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, osrc, src_in, opos);
+             vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, osrc, src_in, opos,
+             (const ull*)dst_tab, src_bias);
 }
 extern "C" void smx_launch_gather(smx_stream_t st, uint32_t* out, const uint32_t* vals,
                                   const uint32_t* pos, uint32_t n) {

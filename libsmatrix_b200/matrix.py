@@ -22,6 +22,17 @@ def _is_torch(a) -> bool:
     return type(a).__module__.startswith("torch")
 
 
+class DevPtr:
+    """A raw device array of `n` uint32 (library- or peer-allocated memory that is not a tensor)."""
+    __slots__ = ("ptr", "n")
+
+    def __init__(self, ptr: int, n: int):
+        self.ptr, self.n = int(ptr), int(n)
+
+    def __len__(self):
+        return self.n
+
+
 class SparseMatrix:
     def __init__(self, file_path: str | None = None, device: int | None = None,
                  _lib_path: str | None = None):
@@ -100,6 +111,9 @@ class SparseMatrix:
         """-> raw pointer (int) of a uint32 numpy array (host) or CUDA/CPU torch tensor."""
         if a is None:
             return None
+        if isinstance(a, DevPtr):
+            keep.append(a)
+            return a.ptr
         if _is_torch(a):
             import torch
             if a.dtype not in (torch.int32, torch.uint32):
@@ -114,7 +128,7 @@ class SparseMatrix:
     def _write(self, fn, xs, ys, vals):
         keep: list = []
         px, py, pv = self._arg(xs, keep), self._arg(ys, keep), self._arg(vals, keep)
-        n = len(keep[0]) if not _is_torch(keep[0]) else keep[0].numel()
+        n = keep[0].numel() if _is_torch(keep[0]) else len(keep[0])
         fn(self._handle(), px, py, pv, n)
 
     def incr_batch(self, xs, ys, vals=None):
@@ -129,6 +143,10 @@ class SparseMatrix:
     def get_batch(self, xs, ys, out=None):
         keep: list = []
         px, py = self._arg(xs, keep), self._arg(ys, keep)
+        if isinstance(keep[0], DevPtr):
+            assert isinstance(out, DevPtr)
+            self._lib.smatrix_get_batch(self._handle(), px, py, keep[0].n, out.ptr)
+            return out
         if _is_torch(keep[0]):
             import torch
             n = keep[0].numel()
@@ -143,9 +161,13 @@ class SparseMatrix:
         self._lib.smatrix_get_batch(self._handle(), px, py, n, po)
         return out
 
-    def rowlen_batch(self, xs):
+    def rowlen_batch(self, xs, out=None):
         keep: list = []
         px = self._arg(xs, keep)
+        if isinstance(keep[0], DevPtr):
+            assert isinstance(out, DevPtr)
+            self._lib.smatrix_rowlen_batch(self._handle(), px, keep[0].n, out.ptr)
+            return out
         if _is_torch(keep[0]):
             import torch
             out = torch.empty(keep[0].numel(), dtype=torch.int32, device=keep[0].device)

@@ -26,17 +26,72 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .matrix import SparseMatrix
+import ctypes as C
+
+from .matrix import DevPtr, SparseMatrix
+
+
+class _PeerBuffers:
+    """Symmetric buffers for the fused route: per generation an inbox (x, y, v, order index) that
+    the other ranks' scatter kernels write into, and an answer buffer that owners' read kernels
+    write into — all peer-mapped through CUDA IPC, i.e. plain stores over NVLink / NVSwitch."""
+    GENS = 3            # routed / in flight / being applied (see ShardedSparseMatrix._write)
+    ARRAYS = ("x", "y", "v", "o", "b")
+
+    def __init__(self, sm: "ShardedSparseMatrix", cap_ops: int):
+        self.sm, self.cap, self.gen = sm, int(cap_ops), 0
+        lib, h = sm._lib, sm.router._handle()
+        self.local = {(g, a): int(lib.smatrix_b200_dev_alloc(h, self.cap * 4))
+                      for g in range(self.GENS) for a in self.ARRAYS}
+        mine = {}
+        for k, ptr in self.local.items():
+            buf = (C.c_ubyte * 64)()
+            if lib.smatrix_b200_ipc_export(h, ptr, buf) != 0:
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+            mine[k] = bytes(buf)
+        everyone = [None] * sm.world
+        dist.all_gather_object(everyone, mine, group=sm.group)
+        self.peer = []
+        for r in range(sm.world):
+            if r == sm.rank:
+                self.peer.append(dict(self.local))
+                continue
+            opened = {}
+            for k, hb in everyone[r].items():
+                p = lib.smatrix_b200_ipc_open(h, (C.c_ubyte * 64).from_buffer_copy(hb))
+                if not p:
+                    raise RuntimeError("cudaIpcOpenMemHandle failed")
+                opened[k] = int(p)
+            self.peer.append(opened)
+
+    def next_gen(self) -> int:
+        self.gen = (self.gen + 1) % self.GENS
+        return self.gen
+
+    def close(self):
+        lib, h = self.sm._lib, self.sm.router._handle()
+        for r, d in enumerate(self.peer):
+            if r != self.sm.rank:
+                for p in d.values():
+                    lib.smatrix_b200_ipc_close(h, p)
+        dist.barrier(group=self.sm.group)     # nobody frees memory a peer still maps
+        for p in self.local.values():
+            lib.smatrix_b200_dev_free(h, p)
 
 
 class ShardedSparseMatrix:
-    def __init__(self, rank: int, world: int, device: int = 0, group=None, _lib_path: str | None = None):
+    def __init__(self, rank: int, world: int, device: int = 0, group=None, _lib_path: str | None = None,
+                 p2p: bool | None = None):
         self.rank, self.world, self.group = rank, world, group
+        self._use_p2p = (_lib_path is None) if p2p is None else p2p   # CUDA build: peer memory; else NCCL/gloo
+        self._peers: _PeerBuffers | None = None
         self.local = SparseMatrix(device=device, _lib_path=_lib_path)
         arena = os.environ.pop("SMATRIX_ARENA_GIB", None)               # the router holds no data:
-        try:                                                             # it must not reserve an arena
-            self.router = SparseMatrix(device=device, _lib_path=_lib_path)   # K8 only
+        os.environ["SMATRIX_STREAM_HIGH_PRIORITY"] = "1"                 # no arena, and a high-priority
+        try:                                                             # stream so K8 interleaves with
+            self.router = SparseMatrix(device=device, _lib_path=_lib_path)   # an update in flight
         finally:
+            os.environ.pop("SMATRIX_STREAM_HIGH_PRIORITY", None)
             if arena is not None:
                 os.environ["SMATRIX_ARENA_GIB"] = arena
         self._lib = self.local._lib
@@ -110,26 +165,97 @@ class ShardedSparseMatrix:
         self._sync_torch()   # the library runs on its own stream
         return send, recv, rx, ry, rv, (opos if want_pos else osrc), rord
 
+    # ------------------------------------------------------------------ fused route over peer memory
+    def _ensure_peers(self, nmax: int) -> bool:
+        """(Re)create the symmetric buffers for batches of up to nmax ops per rank.  Collective:
+        every rank calls it with the same nmax."""
+        if not self._use_p2p or self.world == 1:
+            return False
+        need = int(nmax * 1.25) + 65536
+        if self._peers is None or self._peers.cap < need:
+            try:
+                if self._peers is not None:
+                    self._peers.close()
+                self._peers = _PeerBuffers(self, need)
+            except Exception as e:            # no peer access on this box: stay on the NCCL path
+                ok = torch.tensor([0], device=self.dev)
+                self._peers, self._use_p2p = None, False
+                print(f"[smatrix sharded] peer-memory route unavailable ({e}); using NCCL all-to-all",
+                      flush=True)
+                return False
+        return True
+
+    def _route_p2p(self, xs, ys, vals, ordered=False, want_pos=False):
+        """K8 fused with the exchange: count per owner, all-gather the world x world count matrix
+        (tiny), then ONE scatter kernel writes every owner's run straight into that owner's inbox
+        over NVLink.  Returns None (on every rank alike) if some inbox would overflow."""
+        pb, W, me, n = self._peers, self.world, self.rank, xs.numel()
+        lib, rh = self._lib, self.router._handle()
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        self._sync_torch()
+        counts = np.zeros(W, dtype=np.uint64)
+        if n:
+            lib.smatrix_b200_partition_count(rh, ptr(xs), n, W, counts.ctypes.data)
+        mine = torch.from_numpy(counts.astype(np.int64)).to(self.dev)
+        allc = torch.empty(W * W, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        cnt = allc.view(W, W).cpu().numpy()              # cnt[s][o]: ops sender s has for owner o
+        if int(cnt.sum(axis=0).max()) > pb.cap or int(cnt.sum(axis=1).max()) > pb.cap:
+            return None
+        g = pb.next_gen()
+        in_base = cnt[:me].sum(axis=0)                   # where my run starts inside owner o's inbox
+        send_base = np.concatenate([[0], np.cumsum(cnt[me])[:-1]])   # my routed order: runs by owner
+        tab = np.zeros(5 * W, dtype=np.uint64)
+        for o in range(W):
+            off = 4 * int(in_base[o])
+            tab[o] = pb.peer[o][(g, "x")] + off
+            tab[W + o] = pb.peer[o][(g, "y")] + off if ys is not None else 0
+            tab[2 * W + o] = pb.peer[o][(g, "v")] + off if vals is not None else 0
+            tab[3 * W + o] = pb.peer[o][(g, "o")] + off if ordered else 0
+            tab[4 * W + o] = int(send_base[o])
+        opos = self._slot(f"pp{g}", n) if want_pos else None
+        bias = int(cnt[:me].sum())                       # global index of my first op (rank-major order)
+        if n:
+            lib.smatrix_b200_route_p2p(rh, ptr(xs), ptr(ys), ptr(vals), n, W, tab.ctypes.data,
+                                       bias & 0xFFFFFFFF, ptr(opos))
+        dist.barrier(group=self.group)                   # every rank's runs have landed
+        n_recv = int(cnt[:, me].sum())
+        dp = lambda a, used: DevPtr(pb.local[(g, a)], n_recv) if used else None
+        return cnt, g, dp("x", True), dp("y", ys is not None), dp("v", vals is not None), dp("o", ordered), opos
+
     PIPELINE_MIN = 1 << 23      # order-free batches at least this big are routed in overlapped pieces
     PIPELINE_PIECE = 1 << 24
 
+    def _nmax(self, n: int) -> int:
+        t = torch.tensor([n], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t)
+
+    def _routed(self, xs, ys, vals, ordered=False, nmax=None):
+        """-> (rx, ry, rv, rord, n_recv) through peer memory when possible, else NCCL all-to-all."""
+        if self._ensure_peers(nmax if nmax is not None else self._nmax(xs.numel())):
+            r = self._route_p2p(xs, ys, vals, ordered=ordered)
+            if r is not None:
+                _, _, rx, ry, rv, rord, _ = r
+                return rx, ry, rv, rord, rx.n
+        _, _, rx, ry, rv, _, rord = self._route(xs, ys, vals, ordered=ordered)
+        return rx, ry, rv, rord, rx.numel()
+
     def _write(self, op: int, xs, ys, vals, ordered: bool):
+        n = xs.numel()
+        nmax = self._nmax(n)    # every rank must take the same decisions (the exchanges are collective)
         if ordered:
-            _, _, rx, ry, rv, _, rord = self._route(xs, ys, vals, ordered=True)
-            if rx.numel():
-                p = lambda t: t.data_ptr() if t is not None else None
+            rx, ry, rv, rord, n_recv = self._routed(xs, ys, vals, ordered=True, nmax=nmax)
+            if n_recv:
+                p = lambda t: None if t is None else (t.ptr if isinstance(t, DevPtr) else t.data_ptr())
                 self._lib.smatrix_b200_apply_ordered(self.local._handle(), op, p(rx), p(ry), p(rv), p(rord),
-                                                     rx.numel())
+                                                     n_recv)
             return
         apply = (self.local.incr_batch, self.local.decr_batch)[op]
-        n = xs.numel()
-        # every rank must cut the same number of pieces (the exchanges are collective)
-        nmax = torch.tensor([n], dtype=torch.int64, device=self.dev)
-        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=self.group)
-        pieces = max(1, -(-int(nmax) // self.PIPELINE_PIECE)) if int(nmax) >= self.PIPELINE_MIN else 1
+        pieces = max(1, -(-nmax // self.PIPELINE_PIECE)) if nmax >= self.PIPELINE_MIN else 1
         if pieces == 1:
-            _, _, rx, ry, rv, _, _ = self._route(xs, ys, vals)
-            if rx.numel():
+            rx, ry, rv, _, n_recv = self._routed(xs, ys, vals, nmax=nmax)
+            if n_recv:
                 apply(rx, ry, rv)
             return
         # route piece j+1 (router handle + NCCL, helper thread) while piece j updates the shard
@@ -138,16 +264,19 @@ class ShardedSparseMatrix:
             self._pool = cf.ThreadPoolExecutor(max_workers=1)
         cut = lambda t, j: None if t is None else t[j * n // pieces:(j + 1) * n // pieces]
 
+        piece_max = -(-nmax // pieces) + 1
+        self._ensure_peers(piece_max)      # size the inboxes once, before the helper thread starts
+
         def route(j):
             if self._cuda:
                 torch.cuda.set_device(self.dev)
-            return self._route(cut(xs, j), cut(ys, j), cut(vals, j))
+            return self._routed(cut(xs, j), cut(ys, j), cut(vals, j), nmax=piece_max)
         fut = self._pool.submit(route, 0)
         for j in range(pieces):
-            _, _, rx, ry, rv, _, _ = fut.result()
+            rx, ry, rv, _, n_recv = fut.result()
             if j + 1 < pieces:
                 fut = self._pool.submit(route, j + 1)
-            if rx.numel():
+            if n_recv:
                 apply(rx, ry, rv)
 
     # ------------------------------------------------------------------ collective batch API
@@ -160,7 +289,39 @@ class ShardedSparseMatrix:
     def set_batch(self, xs, ys, vals=None):
         self._write(2, xs, ys, vals, True)     # last writer in GLOBAL input order wins
 
+    def _read_p2p(self, fn, xs, ys, out):
+        """Queries travel through the inboxes; every owner's read kernel writes its answers straight
+        into the requester's answer buffer (peer memory), which the requester then gathers into
+        input order."""
+        r = self._route_p2p(xs, ys, None, want_pos=True)
+        if r is None:
+            return None
+        cnt, g, rx, ry, _, _, opos = r
+        pb, me, off = self._peers, self.rank, 0
+        for s_ in range(self.world):              # one launch per sender's run
+            c = int(cnt[s_][me])
+            if c:
+                dst = DevPtr(pb.peer[s_][(g, "b")] + 4 * int(cnt[s_][:me].sum()), c)
+                qx = DevPtr(rx.ptr + 4 * off, c)
+                if ry is not None:
+                    fn(qx, DevPtr(ry.ptr + 4 * off, c), out=dst)
+                else:
+                    fn(qx, out=dst)
+                off += c
+        dist.barrier(group=self.group)             # all answers have landed
+        n = xs.numel()
+        if out is None:
+            out = self._buf(n)
+        if n:
+            self._lib.smatrix_b200_gather(self.router._handle(), out.data_ptr(), pb.local[(g, "b")],
+                                          opos.data_ptr(), n)
+        return out
+
     def get_batch(self, xs, ys, out=None):
+        if self._ensure_peers(self._nmax(xs.numel())):
+            r = self._read_p2p(self.local.get_batch, xs, ys, out)
+            if r is not None:
+                return r
         send, recv, rx, ry, _, opos, _ = self._route(xs, ys, None, want_pos=True)
         ans = self.local.get_batch(rx, ry) if rx.numel() else self._buf(0)
         self._sync_torch()
@@ -177,6 +338,10 @@ class ShardedSparseMatrix:
         return out
 
     def rowlen_batch(self, xs):
+        if self._ensure_peers(self._nmax(xs.numel())):
+            r = self._read_p2p(self.local.rowlen_batch, xs, None, None)
+            if r is not None:
+                return r
         send, recv, rx, _, _, opos, _ = self._route(xs, None, None, want_pos=True)
         ans = self.local.rowlen_batch(rx) if rx.numel() else self._buf(0)
         self._sync_torch()
@@ -197,5 +362,8 @@ class ShardedSparseMatrix:
             self._pool = None
         self._bufs: dict[str, torch.Tensor] = {}
         self._gen = 0
+        if self._peers is not None:
+            self._peers.close()
+            self._peers = None
         self.router.close()
         self.local.close()

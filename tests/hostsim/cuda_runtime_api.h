@@ -33,6 +33,8 @@ cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int kind);
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int kind, cudaStream_t st);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
+cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned flags, int prio);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags);
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
@@ -41,6 +43,11 @@ cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+typedef struct { char reserved[64]; } cudaIpcMemHandle_t;
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void* p);
 cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void* p);
 cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b);
 cudaError_t cudaGetLastError(void);

@@ -22,7 +22,8 @@ def main():
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    m = ShardedSparseMatrix(rank, world, rank)
+    p2p = os.environ.get("SMX_P2P", "1") == "1"       # fused peer-memory route vs NCCL all-to-all
+    m = ShardedSparseMatrix(rank, world, rank, p2p=p2p)
     ref = cpu.CpuMatrix("reference" if cpu.have_reference() else "port")
     rng = np.random.default_rng(321)                  # the same global stream on every rank
     n = 400_000
@@ -55,10 +56,11 @@ def main():
     dist.all_reduce(tot)
     o, p = ref.getrow_many(np.unique(allx))
     assert int(tot[0]) == len(np.unique(allx)) and int(tot[1]) == len(p)
+    assert (m._peers is not None) == p2p, "peer-memory route was expected to be active"
     m.close(); ref.close()
     dist.barrier()
     dist.destroy_process_group()
-    print(f"rank {rank} ok")
+    print(f"rank {rank} ok (p2p={p2p}, peers={'yes' if p2p else 'n/a'})")
 
 
 if __name__ == "__main__":

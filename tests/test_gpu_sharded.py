@@ -19,11 +19,13 @@ def _ngpu():
         return 0
 
 
+@pytest.mark.parametrize("p2p", [1, 0], ids=["peer-memory", "nccl-a2a"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_row_sharding_nccl(world):
+def test_row_sharding_nccl(world, p2p):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + world), WORLD_SIZE=str(world))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + world + 10 * p2p),
+               WORLD_SIZE=str(world), SMX_P2P=str(p2p))
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "sharded_gpu_worker.py")],
                               env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True) for r in range(world)]
