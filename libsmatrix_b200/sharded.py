@@ -223,7 +223,9 @@ class ShardedSparseMatrix:
         dp = lambda a, used: DevPtr(pb.local[(g, a)], n_recv) if used else None
         return cnt, g, dp("x", True), dp("y", ys is not None), dp("v", vals is not None), dp("o", ordered), opos
 
-    PIPELINE_MIN = 1 << 23      # order-free batches at least this big are routed in overlapped pieces
+    # overlapped pieces (helper thread routes piece j+1 while piece j updates): measured slower than one
+    # fused route per batch on B200 (7.4 vs 6.7 ms per 2^26 ops at N=2), so off unless asked for
+    PIPELINE_MIN = 1 << 62
     PIPELINE_PIECE = 1 << 24
 
     def _nmax(self, n: int) -> int:
