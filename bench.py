@@ -244,6 +244,8 @@ def main_ours(a):
     scratch.close()
 
     m = mk()
+    if world > 1:
+        m.reserve_route(B)      # symmetric inboxes + IPC exchange: communicator-style set-up, untimed
     g = gen or m
     # global op index of (rank, batch k, offset i): ranks interleave batch-wise
     first_of = lambda k: (k * world + rank) * B

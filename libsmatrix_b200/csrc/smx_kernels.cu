@@ -820,12 +820,16 @@ k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, uint32_t dir_m
  * part is not the input order (osrc carries the original index). */
 #define PART_ITEMS 8
 #define PART_TILE (SMX_BLOCK * PART_ITEMS)
+template <bool HAS_V, bool HAS_POS> /* shared memory only for what is used: 24 - 40 KB per block */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
                     uint32_t world, uint32_t dir_mask, uint32_t shift, ull* cursors, uint32_t* oxs,
                     uint32_t* oys, uint32_t* ovs, uint32_t* osrc, const uint32_t* src_in,
                     uint32_t* opos, const ull* dst_tab, uint32_t src_bias) {
-  __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_v[PART_TILE], s_i[PART_TILE], s_p[PART_TILE];
+  __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_i[PART_TILE];
+  __shared__ uint32_t s_v[HAS_V ? PART_TILE : 1], s_p[HAS_POS ? PART_TILE : 1];
+  if (!HAS_V) vs = nullptr;
+  if (!HAS_POS) opos = nullptr;
   __shared__ uint32_t hist[SMX_MAX_PARTS], off[SMX_MAX_PARTS];
   __shared__ ull gbase[SMX_MAX_PARTS];
   const uint32_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
@@ -1062,9 +1066,19 @@ extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs
                                              const uint32_t* src_in, uint32_t* opos,
                                              const unsigned long long* dst_tab, uint32_t src_bias) {
   if (!n) return;
-  SMX_LAUNCH(k_partition_scatter, grid_for((ull)(n + PART_ITEMS - 1) / PART_ITEMS), SMX_BLOCK, st, xs, ys,
-             vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, osrc, src_in, opos,
-             (const ull*)dst_tab, src_bias);
+  const uint32_t grid = grid_for((ull)(n + PART_ITEMS - 1) / PART_ITEMS);
+  const bool pos = opos && !src_in;
+#define SMX_SCATTER(V, P)                                                                            \
+  {                                                                                                  \
+    auto k = k_partition_scatter<V, P>;                                                              \
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, xs, ys, vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, \
+               osrc, src_in, opos, (const ull*)dst_tab, src_bias);                                   \
+  }
+  if (vs && pos) SMX_SCATTER(true, true)
+  else if (vs) SMX_SCATTER(true, false)
+  else if (pos) SMX_SCATTER(false, true)
+  else SMX_SCATTER(false, false)
+#undef SMX_SCATTER
 }
 extern "C" void smx_launch_gather(smx_stream_t st, uint32_t* out, const uint32_t* vals,
                                   const uint32_t* pos, uint32_t n) {

@@ -185,6 +185,12 @@ class ShardedSparseMatrix:
                 return False
         return True
 
+    def reserve_route(self, max_ops_per_rank: int) -> bool:
+        """Collective set-up of the peer-memory route for batches of up to max_ops_per_rank ops
+        (symmetric inboxes + CUDA IPC exchange, ~15 x 5 B/op of HBM per rank).  Optional: the first
+        batch does it lazily; call it to keep that cost out of a timed region."""
+        return self._ensure_peers(self._nmax(max_ops_per_rank))
+
     def _route_p2p(self, xs, ys, vals, ordered=False, want_pos=False):
         """K8 fused with the exchange: count per owner, all-gather the world x world count matrix
         (tiny), then ONE scatter kernel writes every owner's run straight into that owner's inbox
