@@ -24,6 +24,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "../../include/smatrix.h"
 #include "../../include/smatrix_b200.h"
@@ -761,6 +766,252 @@ uint32_t smatrix_getrow(smatrix_t* s, uint32_t x, uint32_t* ret, size_t ret_len)
   return (uint32_t)n;
 }
 
+
+/* ------------------------------------------------------------------------------ snapshot (.smx)
+ * File-backed mode = snapshot on open/close (BASELINE.json north_star), in the reference's exact
+ * byte format (src/smatrix.c:30-72) so that files interchange with the CPU library:
+ *   512-byte header: 8 x 0x17, u64 offset of the first directory block
+ *   directory blocks: u64 entries (4 194 304), u64 next-block offset, entries {u32 row, u64 row offset}
+ *   row blocks: 8 x 0x23, u64 size (cells, power of two), size x {u32 column, u32 value}
+ * Row blocks are written in the REFERENCE's hash layout (position = column % size, linear probing,
+ * src/smatrix.c:363-380) because the reference loads them positionally (:533-540).  Like the
+ * reference's loader, ours drops cells whose value is 0 (so zero-valued cells vanish across a
+ * reopen); zero-valued cells are written last so that dropping them never breaks
+ * another cell's probe chain. */
+#define SMX_F_META 512ull
+#define SMX_F_DIR_ENTRIES 4194304ull
+#define SMX_F_DIR_HEAD 16ull
+#define SMX_F_DIR_SLOT 12ull
+#define SMX_F_ROW_HEAD 16ull
+#define SMX_SNAPSHOT_ROWS (1u << 20)
+
+static void ref_place(uint32_t* cells, uint64_t size, uint32_t key, uint32_t val) {
+  uint64_t at = key % size;
+  for (;;) {
+    if (key == 0 ? cells[2 * at] == 0 : (cells[2 * at] == 0 && cells[2 * at + 1] == 0)) break;
+    at = (at + 1) % size;
+  }
+  cells[2 * at] = key;
+  cells[2 * at + 1] = val;
+}
+
+static int write_all(int fd, const void* buf, size_t bytes, uint64_t at) {
+  const char* p = (const char*)buf;
+  while (bytes) {
+    ssize_t w = pwrite(fd, p, bytes, (off_t)at);
+    if (w <= 0) return -1;
+    p += w; bytes -= (size_t)w; at += (uint64_t)w;
+  }
+  return 0;
+}
+
+/* caller holds the handle lock */
+static int snapshot_save(smatrix_t* s) {
+  size_t fl = strlen(s->fname);
+  char* tmp = (char*)malloc(fl + 8);
+  if (!tmp) return -1;
+  memcpy(tmp, s->fname, fl);
+  memcpy(tmp + fl, ".tmp", 5);
+  int fd = open(tmp, O_RDWR | O_CREAT | O_TRUNC, 00600);
+  if (fd == -1) { perror("cannot open file"); free(tmp); return -1; }
+  read_ctl(s);
+  const uint64_t n_rows = s->h_ctl->dir_used;
+  const uint64_t n_blocks = n_rows ? (n_rows + SMX_F_DIR_ENTRIES - 1) / SMX_F_DIR_ENTRIES : 1;
+  const uint64_t block_bytes = SMX_F_DIR_HEAD + SMX_F_DIR_ENTRIES * SMX_F_DIR_SLOT;
+  uint64_t fpos = SMX_F_META + n_blocks * block_bytes; /* row blocks start after the directory */
+  int rc = 0;
+  unsigned char head[SMX_F_META];
+  memset(head, 0, sizeof head);
+  memset(head, 0x17, 8);
+  { uint64_t first = SMX_F_META; memcpy(head + 8, &first, 8); }
+  if (write_all(fd, head, sizeof head, 0)) rc = -1;
+
+  uint32_t* d_keys = NULL;
+  unsigned char* dir_entries = (unsigned char*)calloc(n_rows ? n_rows : 1, SMX_F_DIR_SLOT);
+  uint32_t* h_keys = (uint32_t*)malloc(SMX_SNAPSHOT_ROWS * 4);
+  uint32_t* h_slog = (uint32_t*)malloc(SMX_SNAPSHOT_ROWS * 4);
+  uint64_t* h_off = (uint64_t*)malloc(((size_t)SMX_SNAPSHOT_ROWS + 1) * 8);
+  uint32_t* h_pairs = NULL;
+  size_t h_pairs_cap = 0;
+  unsigned char* out = NULL;
+  size_t out_cap = 0;
+  if (!dir_entries || !h_keys || !h_slog || !h_off) smx_die("out of host memory");
+  if (n_rows) {
+    d_keys = (uint32_t*)dmalloc(s, n_rows * 4);
+    CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
+    smx_launch_list_rows(s->stream, view_of(s), d_keys, (uint32_t*)&s->d_ctl->scratch);
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  for (uint64_t first = 0; first < n_rows && rc == 0; first += SMX_SNAPSHOT_ROWS) {
+    const uint32_t len = (uint32_t)((n_rows - first < SMX_SNAPSHOT_ROWS) ? n_rows - first : SMX_SNAPSHOT_ROWS);
+    const uint32_t* d_xs = d_keys + first;
+    const uint32_t tiles = smx_scan_scratch_items(len);
+    ensure_tmp(s, (size_t)len * 8, ((size_t)len + 1 + tiles) * 8);
+    uint32_t* d_counts = s->d_tmp;
+    uint32_t* d_slog = s->d_tmp + len;
+    const uint64_t total = plan_rows(s, d_xs, len, d_counts);
+    smx_launch_row_slog(s->stream, view_of(s), d_xs, len, d_slog);
+    if (total * 8 > s->d_rowbuf_bytes) {
+      if (s->d_rowbuf) cudaFree(s->d_rowbuf);
+      s->d_rowbuf_bytes = (size_t)total * 8 + 4096;
+      s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
+    }
+    if (total) smx_launch_getrow_fill(s->stream, view_of(s), d_xs, len, s->d_tmp64, 0, s->d_rowbuf);
+    if (total * 2 > h_pairs_cap) {
+      free(h_pairs);
+      h_pairs_cap = (size_t)total * 2 + 1024;
+      h_pairs = (uint32_t*)malloc(h_pairs_cap * 4);
+      if (!h_pairs) smx_die("out of host memory");
+    }
+    CK(cudaMemcpyAsync(h_keys, d_xs, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(h_slog, d_slog, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(h_off, s->d_tmp64, ((size_t)len + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (total) CK(cudaMemcpyAsync(h_pairs, s->d_rowbuf, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    /* lay the chunk's row blocks out in one buffer, then one write */
+    size_t need = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      const uint64_t c = h_off[i + 1] - h_off[i];
+      uint64_t size = 1ull << (h_slog[i] < 4 ? 4 : h_slog[i]);
+      while (c > size / 2) size *= 2;
+      need += SMX_F_ROW_HEAD + size * 8;
+    }
+    if (need > out_cap) {
+      free(out);
+      out_cap = need + 4096;
+      out = (unsigned char*)malloc(out_cap);
+      if (!out) smx_die("out of host memory");
+    }
+    memset(out, 0, need);
+    size_t at = 0;
+    for (uint32_t i = 0; i < len; i++) {
+      const uint32_t* pr = h_pairs + 2 * h_off[i];
+      const uint64_t c = h_off[i + 1] - h_off[i];
+      uint64_t size = 1ull << (h_slog[i] < 4 ? 4 : h_slog[i]);
+      while (c > size / 2) size *= 2;
+      unsigned char* blk = out + at;
+      memset(blk, 0x23, 8);
+      memcpy(blk + 8, &size, 8);
+      uint32_t* cells = (uint32_t*)(blk + SMX_F_ROW_HEAD);
+      for (uint64_t k = 0; k < c; k++) /* non-zero values of real columns first */
+        if (pr[2 * k] != 0 && pr[2 * k + 1] != 0) ref_place(cells, size, pr[2 * k], pr[2 * k + 1]);
+      for (uint64_t k = 0; k < c; k++) /* column 0 goes to the first cell whose column is 0 */
+        if (pr[2 * k] == 0) ref_place(cells, size, 0, pr[2 * k + 1]);
+      for (uint64_t k = 0; k < c; k++) /* zero-valued cells last (both loaders drop them) */
+        if (pr[2 * k] != 0 && pr[2 * k + 1] == 0) ref_place(cells, size, pr[2 * k], 0);
+      unsigned char* de = dir_entries + (first + i) * SMX_F_DIR_SLOT;
+      const uint64_t row_fpos = fpos + at;
+      memcpy(de, &h_keys[i], 4);
+      memcpy(de + 4, &row_fpos, 8);
+      at += SMX_F_ROW_HEAD + size * 8;
+    }
+    if (write_all(fd, out, need, fpos)) rc = -1;
+    fpos += need;
+  }
+  for (uint64_t b = 0; b < n_blocks && rc == 0; b++) {
+    const uint64_t bpos = SMX_F_META + b * block_bytes;
+    unsigned char bh[SMX_F_DIR_HEAD];
+    const uint64_t entries = SMX_F_DIR_ENTRIES, next = (b + 1 < n_blocks) ? bpos + block_bytes : 0;
+    memcpy(bh, &entries, 8);
+    memcpy(bh + 8, &next, 8);
+    if (write_all(fd, bh, sizeof bh, bpos)) rc = -1;
+    const uint64_t lo = b * SMX_F_DIR_ENTRIES;
+    const uint64_t cnt = (n_rows > lo) ? ((n_rows - lo < SMX_F_DIR_ENTRIES) ? n_rows - lo : SMX_F_DIR_ENTRIES) : 0;
+    if (cnt && write_all(fd, dir_entries + lo * SMX_F_DIR_SLOT, cnt * SMX_F_DIR_SLOT, bpos + SMX_F_DIR_HEAD)) rc = -1;
+  }
+  if (rc == 0 && ftruncate(fd, (off_t)fpos) == -1) rc = -1; /* unused directory entries read back as zeros */
+  if (close(fd) == -1) rc = -1;
+  if (rc == 0 && rename(tmp, s->fname) == -1) rc = -1;
+  if (rc) perror("libsmatrix: writing the snapshot failed");
+  if (d_keys) cudaFree(d_keys);
+  free(dir_entries); free(h_keys); free(h_slog); free(h_off); free(h_pairs); free(out); free(tmp);
+  return rc;
+}
+
+static int read_all(int fd, void* buf, size_t bytes, uint64_t at) {
+  char* p = (char*)buf;
+  while (bytes) {
+    ssize_t r = pread(fd, p, bytes, (off_t)at);
+    if (r <= 0) return -1;
+    p += r; bytes -= (size_t)r; at += (uint64_t)r;
+  }
+  return 0;
+}
+
+/* handle is complete and not yet published: public entry points may be used */
+static int snapshot_load(smatrix_t* s, int fd) {
+  unsigned char head[SMX_F_META];
+  if (read_all(fd, head, sizeof head, 0) || head[0] != 0x17 || head[1] != 0x17) {
+    fprintf(stderr, "libsmatrix: invalid file header\n");
+    return -1;
+  }
+  uint64_t bpos;
+  memcpy(&bpos, head + 8, 8);
+  size_t cap = 1u << 22; /* triples per flush (grows for rows larger than that) */
+  uint32_t* xs = (uint32_t*)malloc(cap * 4), * ys = (uint32_t*)malloc(cap * 4), * vs = (uint32_t*)malloc(cap * 4);
+  uint32_t* rk = (uint32_t*)malloc(cap * 4), * rs = (uint32_t*)malloc(cap * 4);
+  unsigned char* block = (unsigned char*)malloc(SMX_F_DIR_ENTRIES * SMX_F_DIR_SLOT);
+  uint32_t* cells = NULL;
+  size_t cells_cap = 0, n = 0, nr = 0;
+  int rc = 0;
+  if (!xs || !ys || !vs || !rk || !rs || !block) smx_die("out of host memory");
+#define FLUSH_OPS()  do { if (n) { smatrix_set_batch(s, xs, ys, vs, n); n = 0; } } while (0)
+#define FLUSH_ROWS() do { FLUSH_OPS(); if (nr) {                                                     \
+      enter(s); ensure_tmp(s, nr * 8, 0);                                                             \
+      CK(cudaMemcpyAsync(s->d_tmp, rk, nr * 4, cudaMemcpyHostToDevice, s->stream));                   \
+      CK(cudaMemcpyAsync(s->d_tmp + nr, rs, nr * 4, cudaMemcpyHostToDevice, s->stream));              \
+      smx_launch_load_fixup(s->stream, view_of(s), s->d_tmp, s->d_tmp + nr, (uint32_t)nr);            \
+      CK(cudaStreamSynchronize(s->stream)); leave(s); nr = 0; } } while (0)
+  while (bpos && rc == 0) {
+    unsigned char bh[SMX_F_DIR_HEAD];
+    if (read_all(fd, bh, sizeof bh, bpos)) { rc = -1; break; }
+    uint64_t entries, next;
+    memcpy(&entries, bh, 8);
+    memcpy(&next, bh + 8, 8);
+    if (entries > SMX_F_DIR_ENTRIES) { rc = -1; break; }
+    if (read_all(fd, block, entries * SMX_F_DIR_SLOT, bpos + SMX_F_DIR_HEAD)) { rc = -1; break; }
+    for (uint64_t i = 0; i < entries; i++) {
+      uint32_t key;
+      uint64_t rpos;
+      memcpy(&key, block + i * SMX_F_DIR_SLOT, 4);
+      memcpy(&rpos, block + i * SMX_F_DIR_SLOT + 4, 8);
+      if (!rpos) break; /* src/smatrix.c:814-815 */
+      unsigned char rh[SMX_F_ROW_HEAD];
+      uint64_t size;
+      if (read_all(fd, rh, sizeof rh, rpos) || rh[0] != 0x23 || rh[7] != 0x23) { rc = -1; break; }
+      memcpy(&size, rh + 8, 8);
+      if (size == 0 || (size & (size - 1)) || size > (1ull << 32)) { rc = -1; break; }
+      if (size * 2 > cells_cap) {
+        free(cells);
+        cells_cap = size * 2;
+        cells = (uint32_t*)malloc(cells_cap * 4);
+        if (!cells) smx_die("out of host memory");
+      }
+      if (read_all(fd, cells, size * 8, rpos + SMX_F_ROW_HEAD)) { rc = -1; break; }
+      if (n + size + 1 > cap) FLUSH_OPS();
+      if (size + 1 > cap) { /* a single row larger than the staging buffers: grow them */
+        cap = size + 1;
+        xs = (uint32_t*)realloc(xs, cap * 4); ys = (uint32_t*)realloc(ys, cap * 4); vs = (uint32_t*)realloc(vs, cap * 4);
+        if (!xs || !ys || !vs) smx_die("out of host memory");
+      }
+      xs[n] = key; ys[n] = 0; vs[n] = 0; n++; /* the row exists even when it is empty */
+      for (uint64_t c = 0; c < size; c++)
+        if (cells[2 * c + 1] != 0) { xs[n] = key; ys[n] = cells[2 * c]; vs[n] = cells[2 * c + 1]; n++; }
+      uint32_t lg = 0;
+      while ((1ull << lg) < size) lg++;
+      rk[nr] = key; rs[nr] = lg; nr++;
+      if (nr == (1u << 22)) FLUSH_ROWS();
+    }
+    bpos = next;
+  }
+  if (rc == 0) FLUSH_ROWS();
+#undef FLUSH_OPS
+#undef FLUSH_ROWS
+  if (rc) fprintf(stderr, "libsmatrix: file is corrupt\n");
+  free(xs); free(ys); free(vs); free(rk); free(rs); free(block); free(cells);
+  return rc;
+}
+
 /* ------------------------------------------------------------------------------ open / close */
 smatrix_t* smatrix_b200_open(const char* fname, int device) {
   int ndev = 0;
@@ -772,11 +1023,15 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
     fprintf(stderr, "libsmatrix: CUDA device %d out of range (0..%d)\n", device, ndev - 1);
     return NULL;
   }
-  if (fname) {
-    fprintf(stderr, "libsmatrix: file-backed mode (%s) is not available in this build yet\n", fname);
-    return NULL;
+  int fd = -1;
+  if (fname) { /* like src/smatrix.c:90-96: the file must be creatable / readable */
+    fd = open(fname, O_RDWR | O_CREAT, 00600);
+    if (fd == -1) {
+      perror("cannot open file");
+      return NULL;
+    }
   }
-  if (cudaSetDevice(device) != cudaSuccess) return NULL;
+  if (cudaSetDevice(device) != cudaSuccess) { if (fd != -1) close(fd); return NULL; }
   smatrix_t* s = (smatrix_t*)calloc(1, sizeof(smatrix_t));
   if (!s) return NULL;
   s->device = device;
@@ -819,6 +1074,19 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   s->d_small = (uint32_t*)dmalloc(s, 64 * 4);
   CK(cudaHostAlloc((void**)&s->h_small, 64 * 4, cudaHostAllocDefault));
   CK(cudaStreamSynchronize(s->stream));
+  if (fname) {
+    s->fname = strdup(fname);
+    struct stat st;
+    int bad = 0;
+    if (fstat(fd, &st) == 0 && st.st_size > 0) bad = snapshot_load(s, fd);
+    close(fd);
+    if (bad) {
+      free(s->fname);
+      s->fname = NULL; /* do not overwrite a file we could not read */
+      smatrix_close(s);
+      return NULL;
+    }
+  }
   return s;
 }
 
@@ -831,6 +1099,7 @@ void smatrix_close(smatrix_t* s) {
   enter(s);
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaStreamSynchronize(s->copy_stream));
+  if (s->fname) snapshot_save(s);
   for (int i = 0; i < s->nsegs; i++) cudaFree(s->segs[i].base);
   free(s->segs);
   cudaFree(s->dir);

@@ -133,6 +133,10 @@ void smx_launch_scan(smx_stream_t stream, const uint32_t* counts, uint32_t n, ui
 void smx_launch_getrow_fill(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
                             const uint64_t* offsets, uint64_t offset_bias, uint32_t* pairs);
 void smx_launch_count_nnz(smx_stream_t stream, smx_view_t v);
+void smx_launch_list_rows(smx_stream_t stream, smx_view_t v, uint32_t* keys, uint32_t* counter /* zeroed */);
+void smx_launch_row_slog(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n, uint32_t* out);
+void smx_launch_load_fixup(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* slogs,
+                           uint32_t n);
 void smx_launch_gen_c2_ops(smx_stream_t stream, uint64_t seed, uint64_t first, uint64_t count,
                            uint32_t rows, uint32_t ycols, uint32_t* xs, uint32_t* ys);
 void smx_launch_gen_c2_queries(smx_stream_t stream, uint64_t seed_get, uint64_t seed_build,

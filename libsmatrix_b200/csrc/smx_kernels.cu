@@ -721,6 +721,45 @@ k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, 
   }
 }
 
+/* ---- snapshot support (file mode, reference src/smatrix.c:30-72) --------------------------- */
+/* all row ids of the directory, in no particular order */
+__global__ void __launch_bounds__(SMX_BLOCK) k_list_rows(smx_view_t V, uint32_t* keys, uint32_t* counter) {
+  for (ull pos = blockIdx.x * blockDim.x + threadIdx.x; pos < V.dir_cap;
+       pos += (ull)gridDim.x * blockDim.x) {
+    Hdr h = ld_hdr(V.dir + pos);
+    if (h.meta & SMX_META_USED) keys[agg_inc(counter)] = h.key;
+  }
+}
+/* log2 of the reference's row size as of now (the caught-up automaton state), per row */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_row_slog(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t slog = 4u;
+    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) {
+      const uint32_t m2 = rowlen_catch_up(h.meta, h.live, (h.meta & (SMX_META_ZC | SMX_META_T0P)) != 0u);
+      slog = 4u + ((m2 & SMX_META_SLOG) >> SMX_META_SLOG_SHIFT);
+    }
+    out[i] = slog;
+  }
+}
+/* after a load: the reference recounts `used` from the file (src/smatrix.c:533-540), i.e. the row
+ * size is the file's and column 0 is counted iff it is non-zero */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_load_fixup(smx_view_t V, const uint32_t* xs, const uint32_t* slogs, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    if (dir_find(V, xs[i], false, &e, &h) != DIR_FOUND) continue;
+    uint32_t slog = slogs[i] < 4u ? 4u : (slogs[i] > 35u ? 35u : slogs[i]);
+    uint32_t m2 = h.meta & ~(SMX_META_SLOG | SMX_META_D | SMX_META_ZC | SMX_META_T0P);
+    m2 |= (slog - 4u) << SMX_META_SLOG_SHIFT;
+    if (h.c0 != 0u) m2 |= SMX_META_D | SMX_META_ZC;
+    e->meta = m2;
+  }
+}
+
 /* nnz = sum over rows of live + (c0 != 0) -> ctl->scratch */
 __global__ void __launch_bounds__(SMX_BLOCK) k_count_nnz(smx_view_t V) {
   ull acc = 0;
@@ -1024,6 +1063,19 @@ extern "C" void smx_launch_getrow_fill(smx_stream_t st, smx_view_t v, const uint
              (const ull*)offsets, (ull)bias, pairs);
 }
 
+extern "C" void smx_launch_list_rows(smx_stream_t st, smx_view_t v, uint32_t* keys, uint32_t* counter) {
+  SMX_LAUNCH(k_list_rows, grid_for(v.dir_cap), SMX_BLOCK, st, v, keys, counter);
+}
+extern "C" void smx_launch_row_slog(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
+                                    uint32_t* out) {
+  if (!n) return;
+  SMX_LAUNCH(k_row_slog, grid_for(n), SMX_BLOCK, st, v, xs, n, out);
+}
+extern "C" void smx_launch_load_fixup(smx_stream_t st, smx_view_t v, const uint32_t* xs,
+                                      const uint32_t* slogs, uint32_t n) {
+  if (!n) return;
+  SMX_LAUNCH(k_load_fixup, grid_for(n), SMX_BLOCK, st, v, xs, slogs, n);
+}
 extern "C" void smx_launch_count_nnz(smx_stream_t st, smx_view_t v) {
   SMX_LAUNCH(k_count_nnz, grid_for(v.dir_cap), SMX_BLOCK, st, v);
 }

@@ -71,7 +71,7 @@ class CpuMatrix:
     """One matrix on the CPU, through either back-end; mirrors src/smatrix.h:87-94 plus bulk
     helpers that loop in C (oracle/smx_driver.c)."""
 
-    def __init__(self, kind: str = "reference"):
+    def __init__(self, kind: str = "reference", fname: str | None = None):
         if kind == "reference":
             if not have_reference():
                 raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where "
@@ -102,7 +102,7 @@ class CpuMatrix:
         self._f["rowlen"].argtypes = [C.c_void_p, C.c_uint32]
         self._f["getrow"].restype = C.c_uint32
         self._f["getrow"].argtypes = [C.c_void_p, C.c_uint32, _u32p, C.c_size_t]
-        self.h = C.c_void_p(self._f["open"](None))
+        self.h = C.c_void_p(self._f["open"](fname.encode() if fname else None))
         if not self.h:
             raise MemoryError("open failed")
 

@@ -96,6 +96,16 @@ def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=20000, max_len=200000)
 
 
+def test_snapshot_interchange(tmp_path):
+    import snapshot_suite as ss
+    ss.scenario_snapshot_interchange(lambda f: SparseMatrix(f), tmp_path)
+
+
+def test_snapshot_roundtrip(tmp_path):
+    import snapshot_suite as ss
+    ss.scenario_snapshot_roundtrip_big(lambda f: SparseMatrix(f), tmp_path, n_rows=200000)
+
+
 def test_preaggregation_off_is_identical(monkeypatch):
     monkeypatch.setenv("SMATRIX_PREAGG", "0")
     ps.scenario_hot_keys(lambda: SparseMatrix())

@@ -93,6 +93,24 @@ def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=300, max_len=3000)
 
 
+def test_snapshot_interchange(sim, tmp_path, monkeypatch):
+    import snapshot_suite as ss
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", "6")
+    ss.scenario_snapshot_interchange(lambda f: SparseMatrix(f, _lib_path=sim), tmp_path)
+
+
+def test_snapshot_roundtrip(sim, tmp_path, monkeypatch):
+    import snapshot_suite as ss
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", "8")
+    ss.scenario_snapshot_roundtrip_big(lambda f: SparseMatrix(f, _lib_path=sim), tmp_path, n_rows=3000)
+
+
+def test_open_unwritable_path_fails(sim):
+    import pytest
+    with pytest.raises(ValueError):                 # smatrix_open -> NULL (src/smatrix.c:92-96)
+        SparseMatrix("/nonexistent-dir/x.smx", _lib_path=sim)
+
+
 def test_golden_fixtures(make):
     import numpy as np
     from oracle import cpu
