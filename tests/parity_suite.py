@@ -347,8 +347,9 @@ def scenario_benchmark_pattern(make, threads: int = 8, rounds: int = 16):
     # threads interleave arbitrarily in the reference; addition commutes, any order gives the same matrix
     xs, ys = np.concatenate(xs), np.concatenate(ys)
     apply_both(m, ref, "incr", xs, ys, np.ones(len(xs), U32))
-    qx, qy = np.meshgrid(np.arange(40, 80, dtype=U32), np.arange(40, 80, dtype=U32))
-    compare(m, ref, np.arange(40, 80), qx.ravel(), qy.ravel())     # benchmark_get_mixed's key space
+    hi = 42 + threads + 23
+    qx, qy = np.meshgrid(np.arange(40, hi, dtype=U32), np.arange(40, hi, dtype=U32))
+    compare(m, ref, np.arange(40, hi), qx.ravel(), qy.ravel())     # benchmark_get_mixed's key space
     assert int(np.asarray(m.get_batch(qx.ravel(), qy.ravel())).astype(np.uint64).sum()) == len(xs)
     m.close(); ref.close()
 
