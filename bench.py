@@ -319,6 +319,29 @@ def main_ours(a):
     hits = int((out != 0).sum().item())
     del qx, qy, out
 
+    # ---- read path on the same table (BASELINE config 4 shape): rowlen over all rows, getrow of 2 M rows
+    reads = None
+    if world == 1:
+        ids = ((torch.arange(a.rows, device=dev, dtype=torch.int64) * 2654435761) & 0xFFFFFFFF)
+        ids = torch.where(ids >= 2**31, ids - 2**32, ids).to(torch.int32)
+        m.rowlen_batch(ids[:1 << 20])                                   # warm
+        m.timer_start(); rl = m.rowlen_batch(ids); ms_rl = m.timer_stop_ms()
+        sample = ids[: min(a.rows, 1 << 21)].contiguous()
+        import ctypes as _C
+        offs = torch.empty(sample.numel() + 1, dtype=torch.int64, device=dev)
+        lib, h = m._lib, m._handle()
+        total = int(lib.smatrix_getrow_batch(h, sample.data_ptr(), sample.numel(), offs.data_ptr(), None, 0))
+        pairs = torch.empty(2 * total, dtype=torch.int32, device=dev)
+        m.timer_start()
+        got = int(lib.smatrix_getrow_batch(h, sample.data_ptr(), sample.numel(), offs.data_ptr(), pairs.data_ptr(), total))
+        ms_gr = m.timer_stop_ms()
+        reads = {"rowlen_mops": a.rows / (ms_rl * 1e-3) / 1e6, "rowlen_sum": int(rl.to(torch.int64).sum().item()),
+                 "getrow_rows": sample.numel(), "getrow_pairs": got, "getrow_ms": ms_gr,
+                 "getrow_gpairs_per_s": got / (ms_gr * 1e-3) / 1e9,
+                 "getrow_algorithmic_gbs": (32 * sample.numel() + 16 * got) / (ms_gr * 1e-3) / 1e9,
+                 "getrow_value_sum": int(pairs[1::2].to(torch.int64).sum().item())}
+        del pairs, offs, ids, sample
+
     # ---- roofline probes in the same process (random 32 B sector reads / 4 B atomics, 32 GiB)
     probes = None
     if not a.no_probes and rank == 0:
@@ -400,6 +423,8 @@ def main_ours(a):
         "host_phase_ms_per_step": phases, "step_ms": step_ms, "step_upsert_kernel_ms": kern_ms,
         "roofline": roofline,
     }
+    if reads:
+        line["reads"] = reads
     if e2e:
         line["e2e"] = e2e
     if cpu:

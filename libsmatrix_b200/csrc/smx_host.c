@@ -93,6 +93,10 @@ struct smatrix_s {
   size_t d_tmp64_bytes;
   uint32_t* d_rowbuf;
   size_t d_rowbuf_bytes;
+  uint32_t* d_big;      /* getrow: indices of big rows in the current query + per-row output cursors */
+  uint32_t* d_cursors;
+  size_t d_big_bytes;
+  uint32_t n_big_rows;
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows;
   double phase_ns[8];
@@ -629,17 +633,28 @@ void smatrix_rowlen_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint32_t* 
   leave(s);
 }
 
-/* counts + scan for rows xs[0..n) (device array); leaves offsets in d_tmp64[0..n], returns total */
+/* counts + scan for rows xs[0..n) (device array); leaves offsets in d_tmp64[0..n], the list of
+ * big rows in s->d_big[0..s->n_big) and zeroed per-row cursors in s->d_cursors; returns total */
 static uint64_t plan_rows(smatrix_t* s, const uint32_t* d_xs, uint32_t n, uint32_t* d_counts) {
   const uint32_t tiles = smx_scan_scratch_items(n);
-  smx_launch_row_counts(s->stream, view_of(s), d_xs, n, d_counts);
+  if ((size_t)n * 8 + 64 > s->d_big_bytes) {
+    if (s->d_big) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_big); }
+    s->d_big_bytes = (size_t)n * 8 + 4096;
+    s->d_big = (uint32_t*)dmalloc(s, s->d_big_bytes);
+  }
+  s->d_cursors = s->d_big + n;
+  CK(cudaMemsetAsync(s->d_cursors, 0, (size_t)n * 4 + 8, s->stream));
+  uint32_t* d_nbig = s->d_cursors + n; /* one counter word after the cursors */
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, n, d_counts, s->d_big, d_nbig);
   smx_launch_scan(s->stream, d_counts, n, 0, s->d_tmp64, s->d_tmp64 + (size_t)n + 1);
   (void)tiles;
   s->n_launches += 4;
   uint64_t total = 0;
   CK(cudaMemcpyAsync(&s->h_small[32], s->d_tmp64 + n, 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(&s->h_small[34], d_nbig, 4, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   memcpy(&total, &s->h_small[32], 8);
+  s->n_big_rows = s->h_small[34];
   return total;
 }
 
@@ -671,7 +686,7 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
     CK(cudaMemcpyAsync(offsets, s->d_tmp64, ((size_t)nn + 1) * 8, cudaMemcpyDefault, s->stream));
   if (pairs && total <= pairs_cap && total > 0) {
     if (is_device_ptr(pairs)) {
-      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, pairs);
+      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, pairs, s->d_big, s->n_big_rows, s->d_cursors);
       s->n_launches++;
     } else {
       if (total * 8 > s->d_rowbuf_bytes) {
@@ -679,7 +694,7 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
         s->d_rowbuf_bytes = (size_t)total * 8;
         s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
       }
-      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, s->d_rowbuf);
+      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
       s->n_launches++;
       CK(cudaMemcpyAsync(pairs, s->d_rowbuf, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
     }
@@ -757,7 +772,7 @@ uint32_t smatrix_getrow(smatrix_t* s, uint32_t x, uint32_t* ret, size_t ret_len)
       s->d_rowbuf_bytes = (size_t)total * 8;
       s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
     }
-    smx_launch_getrow_fill(s->stream, view_of(s), s->d_small, 1, s->d_tmp64, 0, s->d_rowbuf);
+    smx_launch_getrow_fill(s->stream, view_of(s), s->d_small, 1, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
     s->n_launches++;
     CK(cudaMemcpyAsync(ret, s->d_rowbuf, (size_t)n * 8, cudaMemcpyDefault, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -856,7 +871,7 @@ static int snapshot_save(smatrix_t* s) {
       s->d_rowbuf_bytes = (size_t)total * 8 + 4096;
       s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
     }
-    if (total) smx_launch_getrow_fill(s->stream, view_of(s), d_xs, len, s->d_tmp64, 0, s->d_rowbuf);
+    if (total) smx_launch_getrow_fill(s->stream, view_of(s), d_xs, len, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
     if (total * 2 > h_pairs_cap) {
       free(h_pairs);
       h_pairs_cap = (size_t)total * 2 + 1024;
@@ -1120,6 +1135,7 @@ void smatrix_close(smatrix_t* s) {
   if (s->d_tmp) cudaFree(s->d_tmp);
   if (s->d_tmp64) cudaFree(s->d_tmp64);
   if (s->d_rowbuf) cudaFree(s->d_rowbuf);
+  if (s->d_big) cudaFree(s->d_big);
   cudaEventDestroy(s->stage_ready[0]); cudaEventDestroy(s->stage_ready[1]);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   cudaEventDestroy(s->t_start); cudaEventDestroy(s->t_stop);

@@ -597,12 +597,17 @@ k_rowlen(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* out) {
  * K6: getrow for a batch of rows -> CSR
  * ---------------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_row_counts(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* counts) {
+k_row_counts(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* counts, uint32_t* big_list,
+             uint32_t* big_counter) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     smx_row_t* e;
     Hdr h;
     uint32_t c = 0u;
-    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) c = h.live + (h.c0 != 0u ? 1u : 0u);
+    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) {
+      c = h.live + (h.c0 != 0u ? 1u : 0u);
+      /* rows with a big bucket are compacted by the whole grid (k_getrow_big), not by one warp */
+      if (big_list && (h.meta & SMX_META_CAPLOG) >= SMX_BIG_LOG) big_list[agg_inc(big_counter)] = i;
+    }
     counts[i] = c;
   }
 }
@@ -682,7 +687,7 @@ k_scan_apply(const uint32_t* counts, uint32_t n, const ull* tile_sums, ull* offs
 /* one warp per row: 16-byte loads, ballot-free warp prefix over per-lane live counts */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, ull bias,
-              uint32_t* pairs) {
+              uint32_t* pairs, int skip_big) {
   const uint32_t lane = lane_id();
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
   const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
@@ -690,6 +695,7 @@ k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, 
     smx_row_t* e;
     Hdr h;
     if (dir_find(V, xs[i], false, &e, &h) != DIR_FOUND) continue;
+    if (skip_big && (h.meta & SMX_META_CAPLOG) >= SMX_BIG_LOG) continue;
     ull* out = (ull*)pairs + (offsets[i] - bias);
     ull pos = 0;
     if (h.c0 != 0u) {
@@ -718,6 +724,41 @@ k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, 
       if (b != 0ull) out[w] = b;
       pos += total;
     }
+  }
+}
+
+/* big rows: every warp of the grid (x) takes 64-cell pieces of one row's bucket (y) and reserves
+ * its output range with one atomic on the row's cursor; pair order inside the row is arbitrary */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_getrow_big(smx_view_t V, const uint32_t* xs, const uint32_t* big_list, uint32_t big_first,
+             const ull* offsets, ull bias, uint32_t* pairs, uint32_t* cursors) {
+  const uint32_t lane = lane_id();
+  const uint32_t i = big_list[big_first + blockIdx.y];
+  smx_row_t* e;
+  Hdr h;
+  if (dir_find(V, xs[i], false, &e, &h) != DIR_FOUND) return;
+  ull* out = (ull*)pairs + (offsets[i] - bias);
+  const ull* base = (const ull*)h.slots;
+  const ull cap = 1ull << (h.meta & SMX_META_CAPLOG);
+  const ull warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
+  const ull nwarps = (ull)gridDim.x * blockDim.x / SMX_WARP;
+  if (warp == 0 && lane == 0 && h.c0 != 0u) out[atomicAdd(&cursors[i], 1u)] = (ull)h.c0 << 32;
+  for (ull s0 = warp * 2ull * SMX_WARP; s0 < cap; s0 += nwarps * 2ull * SMX_WARP) {
+    const ull s = s0 + 2ull * lane;
+    const ull a = base[s], b = base[s + 1]; /* cap is a multiple of 2 * SMX_WARP here */
+    const uint32_t mine = (a != 0ull) + (b != 0ull);
+    uint32_t incl = mine;
+    for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+      uint32_t t = __shfl_up_sync(SMX_FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(SMX_FULL, incl, SMX_WARP - 1);
+    uint32_t start = 0;
+    if (lane == 0 && total) start = atomicAdd(&cursors[i], total);
+    start = __shfl_sync(SMX_FULL, start, 0);
+    ull w = (ull)start + incl - mine;
+    if (a != 0ull) out[w++] = a;
+    if (b != 0ull) out[w] = b;
   }
 }
 
@@ -1041,9 +1082,9 @@ extern "C" void smx_launch_rowlen(smx_stream_t st, smx_view_t v, const uint32_t*
   SMX_LAUNCH(k_rowlen, grid_for(n), SMX_BLOCK, st, v, xs, n, out);
 }
 extern "C" void smx_launch_row_counts(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
-                                      uint32_t* counts) {
+                                      uint32_t* counts, uint32_t* big_list, uint32_t* big_counter) {
   if (!n) return;
-  SMX_LAUNCH(k_row_counts, grid_for(n), SMX_BLOCK, st, v, xs, n, counts);
+  SMX_LAUNCH(k_row_counts, grid_for(n), SMX_BLOCK, st, v, xs, n, counts, big_list, big_counter);
 }
 
 extern "C" uint32_t smx_scan_scratch_items(uint32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
@@ -1057,10 +1098,17 @@ extern "C" void smx_launch_scan(smx_stream_t st, const uint32_t* counts, uint32_
 }
 
 extern "C" void smx_launch_getrow_fill(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
-                                       const uint64_t* offsets, uint64_t bias, uint32_t* pairs) {
+                                       const uint64_t* offsets, uint64_t bias, uint32_t* pairs,
+                                       const uint32_t* big_list, uint32_t n_big, uint32_t* cursors) {
   if (!n) return;
   SMX_LAUNCH(k_getrow_fill, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, xs, n,
-             (const ull*)offsets, (ull)bias, pairs);
+             (const ull*)offsets, (ull)bias, pairs, n_big ? 1 : 0);
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? 128u : 2u, cnt, 1u);
+    SMX_LAUNCH(k_getrow_big, grid, SMX_BLOCK, st, v, xs, big_list, first, (const ull*)offsets, (ull)bias,
+               pairs, cursors);
+  }
 }
 
 extern "C" void smx_launch_list_rows(smx_stream_t st, smx_view_t v, uint32_t* keys, uint32_t* counter) {
