@@ -437,11 +437,18 @@ def main_ours(a):
 def run_e2e(a, torch, dev, local, make_matrix, B, K, prefill, n_batches):
     """Same stream, HOST buffers: each timed step is one smatrix_incr_batch(host pointers) call —
     H2D of the batch, the update, and the D2H reads of the control block."""
-    m = make_matrix()
     dx = torch.empty(B, dtype=torch.int32, device=dev)
     dy = torch.empty(B, dtype=torch.int32, device=dev)
     hx = torch.empty(B, dtype=torch.int32, pin_memory=True)
     hy = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    scratch = make_matrix()                      # warm-up of the host-pointer path (W steps, other seed)
+    for w in range(a.warmup):
+        scratch.gen_c2_ops(98, w * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
+        hx.copy_(dx); hy.copy_(dy)
+        torch.cuda.synchronize()
+        scratch.incr_batch(hx, hy, None)
+    scratch.close()
+    m = make_matrix()
     for k in range(prefill):
         m.gen_c2_ops(SEED_BUILD, k * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
         m.incr_batch(dx, dy, None)

@@ -37,7 +37,7 @@
 
 #define SMX_DIR_LOG_DEFAULT 20u
 #define SMX_CHUNK_DEFAULT (1u << 25) /* measured sweet spot on B200 */
-#define SMX_STAGE_MAX (1u << 24)
+#define SMX_STAGE_MAX (1u << 23) /* host-pointer batches: piece size with the best copy/update overlap (measured) */
 #define SMX_SEG_MIN ((size_t)64 << 20)
 #define SMX_SEG_MAX ((size_t)16 << 30)
 #define SMX_MAX_ROUNDS 128
@@ -74,6 +74,7 @@ struct smatrix_s {
   uint32_t addrs_cap;
 
   uint32_t stage_cap;
+  uint32_t stage_max; /* ops per staged piece of a host-pointer batch (SMATRIX_STAGE) */
   uint32_t* stage[2][3];
   cudaEvent_t stage_ready[2];
 
@@ -500,7 +501,7 @@ static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint
     CK(cudaStreamSynchronize(s->stream));
   } else {
     /* host arrays: double-buffered upload on the copy stream overlaps the previous chunk's update */
-    uint32_t step = s->chunk_max < SMX_STAGE_MAX ? s->chunk_max : SMX_STAGE_MAX;
+    uint32_t step = s->chunk_max < s->stage_max ? s->chunk_max : s->stage_max;
     if (n < step) step = (uint32_t)n;
     ensure_stage(s, step);
     size_t off = 0;
@@ -592,20 +593,24 @@ void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, siz
       timed_collect(s);
     }
   } else {
-    uint32_t step = n < SMX_STAGE_MAX ? (uint32_t)n : SMX_STAGE_MAX;
+    uint32_t step = n < s->stage_max ? (uint32_t)n : s->stage_max;
+    if (step > (1u << 23) && n > step) step = 1u << 23; /* enough pieces to overlap */
     ensure_stage(s, step);
     int b = 0;
     for (size_t off = 0; off < n; off += step, b ^= 1) {
       const uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
-      /* everything in stream order: upload, look up, download (buffer b is free again: the
-       * download of two chunks ago was enqueued on the same stream) */
-      CK(cudaMemcpyAsync(s->stage[b][0], xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
-      CK(cudaMemcpyAsync(s->stage[b][1], ys + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
-      smx_launch_get(s->stream, view_of(s), s->stage[b][0], s->stage[b][1], len, s->stage[b][2]);
+      /* piece k runs entirely on stream (k & 1) with staging buffer (k & 1): upload, look up,
+       * download in stream order, so the upload of one piece overlaps the look-up and the
+       * download of the previous one (PCIe is full duplex) */
+      cudaStream_t st = b ? s->copy_stream : s->stream;
+      CK(cudaMemcpyAsync(s->stage[b][0], xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(s->stage[b][1], ys + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
+      smx_launch_get(st, view_of(s), s->stage[b][0], s->stage[b][1], len, s->stage[b][2]);
       s->n_launches++;
-      CK(cudaMemcpyAsync(out + off, s->stage[b][2], (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaMemcpyAsync(out + off, s->stage[b][2], (size_t)len * 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(s->stream));
+    CK(cudaStreamSynchronize(s->copy_stream));
   }
   CK(cudaGetLastError());
   leave(s);
@@ -1073,6 +1078,8 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   if (s->chunk_max < 1) s->chunk_max = 1;
   if (s->chunk_max > (1u << 30)) s->chunk_max = 1u << 30;
   s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
+  s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
+  if (s->stage_max < 1024) s->stage_max = 1024;
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
