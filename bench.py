@@ -53,7 +53,7 @@ def parse():
     p.add_argument("--ycols", type=int, default=YCOLS)
     p.add_argument("--total-ops", type=int, default=TOTAL_OPS, help="build ops per GPU")
     p.add_argument("--gets", type=int, default=TOTAL_GETS, help="point gets per GPU")
-    p.add_argument("--arena-gib", type=int, default=48,
+    p.add_argument("--arena-gib", type=int, default=52,
                    help="slab memory each matrix reserves at smatrix_open (SMATRIX_ARENA_GIB); 0 = on demand")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")

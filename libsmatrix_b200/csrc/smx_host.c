@@ -55,6 +55,7 @@ struct smatrix_s {
   pthread_mutex_t mu;
 
   smx_row_t* dir;
+  int dir_in_arena; /* the directory was carved from the slab arena: never cudaFree'd on its own */
   uint64_t dir_cap;
   uint32_t dir_log_min;
   smx_ctl_t* d_ctl;
@@ -312,15 +313,20 @@ static uint64_t pow2_at_least(uint64_t v) {
 static void resize_dir(smatrix_t* s, uint64_t new_cap) {
   double t0 = now_ns();
   smx_view_t from = view_of(s);
-  smx_row_t* nd = (smx_row_t*)dmalloc(s, (size_t)new_cap * sizeof(smx_row_t));
+  /* with an arena the directory lives in it too (cudaMalloc / cudaFree of multi-GiB blocks stall for
+   * tens of ms on these hosts); a replaced directory's arena space is not reused */
+  const int in_arena = s->arena_bytes != 0;
+  smx_row_t* nd = in_arena ? (smx_row_t*)slab_reserve(s, (size_t)new_cap * sizeof(smx_row_t))
+                           : (smx_row_t*)dmalloc(s, (size_t)new_cap * sizeof(smx_row_t));
   CK(cudaMemsetAsync(nd, 0, (size_t)new_cap * sizeof(smx_row_t), s->stream));
   CK(cudaMemsetAsync(s->d_ctl->slice_used, 0, sizeof(uint32_t) * SMX_DIR_SLICES, s->stream));
   smx_view_t to = view_for(s, nd, new_cap);
   smx_launch_dir_rehash(s->stream, from, to);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
-  CK(cudaFree(s->dir));
+  if (!s->dir_in_arena) CK(cudaFree(s->dir));
   s->dir = nd;
+  s->dir_in_arena = in_arena;
   s->dir_cap = new_cap;
   s->n_dir_grows++;
   s->phase_ns[PH_DIR] += now_ns() - t0;
@@ -1124,7 +1130,7 @@ void smatrix_close(smatrix_t* s) {
   if (s->fname) snapshot_save(s);
   for (int i = 0; i < s->nsegs; i++) cudaFree(s->segs[i].base);
   free(s->segs);
-  cudaFree(s->dir);
+  if (!s->dir_in_arena) cudaFree(s->dir);
   cudaFree(s->d_ctl);
   cudaFreeHost(s->h_ctl);
   cudaFree(s->d_small);

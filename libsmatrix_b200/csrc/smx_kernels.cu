@@ -421,10 +421,15 @@ __device__ __forceinline__ void finish_growth(smx_row_t* e, const Hdr& h, ull* n
   e->meta = (h.meta & ~(SMX_META_CAPLOG | SMX_META_GROW)) | newlog;
 }
 
-/* one warp per growing row (old bucket < 2^SMX_BIG_LOG cells) */
+/* one warp per growing row (old bucket < 2^SMX_BIG_LOG cells).  New buckets of up to
+ * 2^SMX_SMEM_MIGRATE_LOG cells — the bulk of all growth events — are built in shared memory and
+ * written out as whole lines (streaming); larger ones are filled in place with global CAS. */
+#define SMX_SMEM_MIGRATE_LOG 8u
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
+  __shared__ ull sbuf[SMX_BLOCK / SMX_WARP][1u << SMX_SMEM_MIGRATE_LOG];
   const uint32_t lane = lane_id();
+  const uint32_t wib = threadIdx.x / SMX_WARP;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
   const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
   for (uint32_t j = warp; j < n_grow; j += nwarps) {
@@ -436,11 +441,29 @@ k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
     ull* ob = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
     ull* nb = (ull*)(region + p.off);
     const uint32_t cap = 1u << caplog;
-    for (uint32_t s = lane; s < cap; s += SMX_WARP) {
-      const ull c = ob[s];
-      if (c != 0ull) {
-        place_cell(nb, p.newlog, c);
-        ob[s] = 0ull; /* recycled buckets are always zero */
+    if (p.newlog <= SMX_SMEM_MIGRATE_LOG) {
+      ull* sb = sbuf[wib];
+      const uint32_t ncap = 1u << p.newlog, nsec = ncap >> 2;
+      for (uint32_t i = lane; i < ncap; i += SMX_WARP) sb[i] = 0ull;
+      __syncwarp();
+      for (uint32_t s0 = lane; s0 < cap; s0 += SMX_WARP) {
+        const ull c = ob[s0];
+        if (c == 0ull) continue;
+        ob[s0] = 0ull; /* vacated buckets are always zero */
+        uint32_t sidx = smx_mix_col((uint32_t)c) & (nsec - 1u);
+        for (bool placed = false; !placed; sidx = (sidx + 1u) & (nsec - 1u))
+          for (int k = 0; k < 4 && !placed; ++k)
+            placed = (atomicCAS(&sb[4u * sidx + k], 0ull, c) == 0ull); /* same probe order as slot_upsert */
+      }
+      __syncwarp();
+      for (uint32_t i = lane; i < ncap; i += SMX_WARP) nb[i] = sb[i];
+    } else {
+      for (uint32_t s0 = lane; s0 < cap; s0 += SMX_WARP) {
+        const ull c = ob[s0];
+        if (c != 0ull) {
+          place_cell(nb, p.newlog, c);
+          ob[s0] = 0ull;
+        }
       }
     }
     __syncwarp();

@@ -14,8 +14,11 @@ U32 = np.uint32
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(params=["default", "chunk65536", "partitioned"])
+@pytest.fixture(params=["default", "chunk65536", "partitioned", "arena"])
 def make(request, monkeypatch):
+    if request.param == "arena":                           # slab + directory carved from a reserved arena
+        monkeypatch.setenv("SMATRIX_ARENA_GIB", "2")
+        monkeypatch.setenv("SMATRIX_DIR_LOG2", "12")
     if request.param == "chunk65536":
         monkeypatch.setenv("SMATRIX_CHUNK", "65536")       # multi-chunk batches
         monkeypatch.setenv("SMATRIX_DIR_LOG2", "12")       # directory growth from 4096 entries
