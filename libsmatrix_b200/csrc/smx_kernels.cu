@@ -46,7 +46,7 @@ typedef unsigned long long ull;
 #define SMX_BLOCK (8 * SMX_WARP) /* 256 threads: 8 blocks/SM = 2048 resident threads */
 #endif
 
-enum { ST_OK = 0, ST_DEFER = 1, ST_LATE = 2 };
+enum { ST_OK = 0, ST_DEFER = 1, ST_LATE = 2, ST_DIRFULL = 3 };
 enum { DIR_FOUND = 0, DIR_CREATED = 1, DIR_MISS = 2, DIR_FULL = 3 };
 
 /* ------------------------------------------------------------------------------------------
@@ -271,10 +271,7 @@ __device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t
   smx_row_t* e;
   Hdr h;
   int r = dir_find(V, x, true, &e, &h);
-  if (r == DIR_FULL) {
-    agg_inc(&V.ctl->n_dirfull);
-    return ST_DEFER;
-  }
+  if (r == DIR_FULL) return ST_DIRFULL; /* counted per block by the caller */
   if (pass == SMX_PASS_COL0) {
     apply_value<OP>(&e->c0, v);
     /* column 0 of this row turns non-zero inside this batch: remember the first such op
@@ -305,6 +302,13 @@ template <int OP>
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* list, uint32_t m,
          int preagg) {
+  /* ops that are turned away are staged per block and appended to the retry list with ONE global
+   * atomic per block: in a round where most ops are refused (directory at its limit) per-warp
+   * atomics on the same counter would serialise ~1 M times */
+  __shared__ uint32_t s_defer[4 * SMX_BLOCK];
+  __shared__ uint32_t s_ndefer, s_ndirfull, s_base;
+  if (threadIdx.x == 0) { s_ndefer = 0u; s_ndirfull = 0u; }
+  __syncthreads();
   const uint32_t lane = lane_id();
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t m_up = (m + (SMX_WARP - 1)) / SMX_WARP * SMX_WARP; /* whole warps stay in the loop */
@@ -351,9 +355,23 @@ k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* lis
       const int ls = __shfl_sync(SMX_FULL, status, act ? leader : (int)lane);
       if (act && !lead) status = ls;
     }
-    if (act && status == ST_DEFER) S.defer_out[agg_inc(&V.ctl->n_defer)] = pos;
-    else if (act && status == ST_LATE) S.late[agg_inc(&V.ctl->n_late)] = pos;
+    if (act && (status == ST_DEFER || status == ST_DIRFULL)) {
+      const uint32_t k = atomicAdd(&s_ndefer, 1u);
+      if (k < 4u * SMX_BLOCK) s_defer[k] = pos;
+      else S.defer_out[agg_inc(&V.ctl->n_defer)] = pos; /* cannot happen with the launch geometry; safe anyway */
+      if (status == ST_DIRFULL) atomicAdd(&s_ndirfull, 1u);
+    } else if (act && status == ST_LATE) {
+      S.late[agg_inc(&V.ctl->n_late)] = pos;
+    }
   }
+  __syncthreads();
+  const uint32_t nd = s_ndefer < 4u * SMX_BLOCK ? s_ndefer : 4u * SMX_BLOCK;
+  if (threadIdx.x == 0 && nd) {
+    s_base = atomicAdd(&V.ctl->n_defer, nd);
+    if (s_ndirfull) atomicAdd(&V.ctl->n_dirfull, s_ndirfull);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < nd; k += blockDim.x) S.defer_out[s_base + k] = s_defer[k];
 }
 
 /* ------------------------------------------------------------------------------------------

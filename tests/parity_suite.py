@@ -292,7 +292,7 @@ def scenario_many_rows(make, n_rows: int):
     vs = np.ones(len(xs), U32)
     apply_both(m, ref, "incr", xs, ys, vs)
     assert m.stat("rows") == n_rows
-    assert m.stat("dir_cap") >= 2 * n_rows
+    assert m.stat("dir_cap") >= 4 * n_rows
     sample = rng.integers(0, len(xs), 20000)
     compare(m, ref, ids[:: max(1, n_rows // 3000)], xs[sample], ys[sample])
     assert m.stat("nnz") == len(np.unique(xs.astype(np.uint64) << np.uint64(32) | ys))
