@@ -241,7 +241,13 @@ class ShardedSparseMatrix:
 
     def _routed(self, xs, ys, vals, ordered=False, nmax=None):
         """-> (rx, ry, rv, rord, n_recv) through peer memory when possible, else NCCL all-to-all."""
-        if self._ensure_peers(nmax if nmax is not None else self._nmax(xs.numel())):
+        for attempt in (0, 1):
+            if attempt == 0 and (self._peers is None or not self._use_p2p):
+                continue      # nothing set up yet: size the inboxes first (collective decision below)
+            if attempt == 1 and not self._ensure_peers(nmax if nmax is not None else self._nmax(xs.numel())):
+                break
+            # with inboxes in place the count matrix itself tells every rank whether they suffice,
+            # so the steady state needs no extra all-reduce
             r = self._route_p2p(xs, ys, vals, ordered=ordered)
             if r is not None:
                 _, _, rx, ry, rv, rord, _ = r
@@ -251,7 +257,9 @@ class ShardedSparseMatrix:
 
     def _write(self, op: int, xs, ys, vals, ordered: bool):
         n = xs.numel()
-        nmax = self._nmax(n)    # every rank must take the same decisions (the exchanges are collective)
+        piped = self.PIPELINE_MIN < (1 << 40)
+        # every rank must take the same decisions (the exchanges are collective)
+        nmax = self._nmax(n) if (piped or self._peers is None) else None
         if ordered:
             rx, ry, rv, rord, n_recv = self._routed(xs, ys, vals, ordered=True, nmax=nmax)
             if n_recv:
@@ -260,7 +268,7 @@ class ShardedSparseMatrix:
                                                      n_recv)
             return
         apply = (self.local.incr_batch, self.local.decr_batch)[op]
-        pieces = max(1, -(-nmax // self.PIPELINE_PIECE)) if nmax >= self.PIPELINE_MIN else 1
+        pieces = max(1, -(-nmax // self.PIPELINE_PIECE)) if (piped and nmax >= self.PIPELINE_MIN) else 1
         if pieces == 1:
             rx, ry, rv, _, n_recv = self._routed(xs, ys, vals, nmax=nmax)
             if n_recv:
@@ -325,11 +333,21 @@ class ShardedSparseMatrix:
                                           opos.data_ptr(), n)
         return out
 
-    def get_batch(self, xs, ys, out=None):
-        if self._ensure_peers(self._nmax(xs.numel())):
-            r = self._read_p2p(self.local.get_batch, xs, ys, out)
+    def _read_routed(self, fn, xs, ys, out):
+        for attempt in (0, 1):
+            if attempt == 0 and (self._peers is None or not self._use_p2p):
+                continue
+            if attempt == 1 and not self._ensure_peers(self._nmax(xs.numel())):
+                break
+            r = self._read_p2p(fn, xs, ys, out)
             if r is not None:
                 return r
+        return None
+
+    def get_batch(self, xs, ys, out=None):
+        r = self._read_routed(self.local.get_batch, xs, ys, out)
+        if r is not None:
+            return r
         send, recv, rx, ry, _, opos, _ = self._route(xs, ys, None, want_pos=True)
         ans = self.local.get_batch(rx, ry) if rx.numel() else self._buf(0)
         self._sync_torch()
@@ -346,10 +364,9 @@ class ShardedSparseMatrix:
         return out
 
     def rowlen_batch(self, xs):
-        if self._ensure_peers(self._nmax(xs.numel())):
-            r = self._read_p2p(self.local.rowlen_batch, xs, None, None)
-            if r is not None:
-                return r
+        r = self._read_routed(self.local.rowlen_batch, xs, None, None)
+        if r is not None:
+            return r
         send, recv, rx, _, _, opos, _ = self._route(xs, None, None, want_pos=True)
         ans = self.local.rowlen_batch(rx) if rx.numel() else self._buf(0)
         self._sync_torch()
