@@ -37,14 +37,17 @@ class _PeerBuffers:
     write into — all peer-mapped through CUDA IPC, i.e. plain stores over NVLink / NVSwitch."""
     GENS = 3            # routed / in flight / being applied (see ShardedSparseMatrix._write)
     ARRAYS = ("x", "y", "v", "o", "b")
+    LOCAL_ONLY = ("p",)  # inverse permutation of my own queries: never touched by a peer
 
     def __init__(self, sm: "ShardedSparseMatrix", cap_ops: int):
         self.sm, self.cap, self.gen = sm, int(cap_ops), 0
         lib, h = sm._lib, sm.router._handle()
         self.local = {(g, a): int(lib.smatrix_b200_dev_alloc(h, self.cap * 4))
-                      for g in range(self.GENS) for a in self.ARRAYS}
+                      for g in range(self.GENS) for a in self.ARRAYS + self.LOCAL_ONLY}
         mine = {}
         for k, ptr in self.local.items():
+            if k[1] in self.LOCAL_ONLY:
+                continue
             buf = (C.c_ubyte * 64)()
             if lib.smatrix_b200_ipc_export(h, ptr, buf) != 0:
                 raise RuntimeError("cudaIpcGetMemHandle failed")
@@ -219,11 +222,11 @@ class ShardedSparseMatrix:
             tab[2 * W + o] = pb.peer[o][(g, "v")] + off if vals is not None else 0
             tab[3 * W + o] = pb.peer[o][(g, "o")] + off if ordered else 0
             tab[4 * W + o] = int(send_base[o])
-        opos = self._slot(f"pp{g}", n) if want_pos else None
+        opos = DevPtr(pb.local[(g, "p")], n) if want_pos else None     # preallocated with the inboxes
         bias = int(cnt[:me].sum())                       # global index of my first op (rank-major order)
         if n:
             lib.smatrix_b200_route_p2p(rh, ptr(xs), ptr(ys), ptr(vals), n, W, tab.ctypes.data,
-                                       bias & 0xFFFFFFFF, ptr(opos))
+                                       bias & 0xFFFFFFFF, opos.ptr if opos else None)
         dist.barrier(group=self.group)                   # every rank's runs have landed
         n_recv = int(cnt[:, me].sum())
         dp = lambda a, used: DevPtr(pb.local[(g, a)], n_recv) if used else None
@@ -309,10 +312,14 @@ class ShardedSparseMatrix:
         """Queries travel through the inboxes; every owner's read kernel writes its answers straight
         into the requester's answer buffer (peer memory), which the requester then gathers into
         input order."""
+        import time as _t
+        dbg = os.environ.get("SMX_ROUTE_DEBUG") == "1"
+        t0 = _t.perf_counter()
         r = self._route_p2p(xs, ys, None, want_pos=True)
         if r is None:
             return None
         cnt, g, rx, ry, _, _, opos = r
+        t1 = _t.perf_counter()
         pb, me, off = self._peers, self.rank, 0
         for s_ in range(self.world):              # one launch per sender's run
             c = int(cnt[s_][me])
@@ -324,13 +331,18 @@ class ShardedSparseMatrix:
                 else:
                     fn(qx, out=dst)
                 off += c
+        t2 = _t.perf_counter()
         dist.barrier(group=self.group)             # all answers have landed
+        t3 = _t.perf_counter()
         n = xs.numel()
         if out is None:
             out = self._buf(n)
         if n:
             self._lib.smatrix_b200_gather(self.router._handle(), out.data_ptr(), pb.local[(g, "b")],
-                                          opos.data_ptr(), n)
+                                          opos.ptr, n)
+        if dbg and self.rank == 0:
+            print(f"[route] read n={n}: route {1e3*(t1-t0):.2f} ms, owners' kernels {1e3*(t2-t1):.2f}, "
+                  f"barrier {1e3*(t3-t2):.2f}, gather {1e3*(_t.perf_counter()-t3):.2f}", file=__import__("sys").stderr, flush=True)
         return out
 
     def _read_routed(self, fn, xs, ys, out):
