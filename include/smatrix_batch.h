@@ -49,6 +49,15 @@ void smatrix_rowlen_batch(smatrix_t* self, const uint32_t* xs, size_t n, uint32_
 uint64_t smatrix_getrow_batch(smatrix_t* self, const uint32_t* xs, size_t n, uint64_t* offsets,
                               uint32_t* pairs, uint64_t pairs_cap);
 
+/* The read side of the co-occurrence recommender for a batch of items
+ * (examples/cf_recommender.c:50-86, neighbors_for_item + cf_cosine): for every item a and every
+ * pair (b, cc) of a's row — including the column-0 pair, as the example does — ids = b and
+ * score = cc / (sqrt(total_a) * sqrt(total_b)), where total_x = value at (x, 0) (1 if total_b is 0)
+ * and the score is 0 if the denominator is 0 or smaller than cc.  CSR like smatrix_getrow_batch:
+ * offsets[0..n], ids / scores with capacity `cap` entries; size query with ids == NULL. */
+uint64_t smatrix_cf_neighbors_batch(smatrix_t* self, const uint32_t* items, size_t n,
+                                    uint64_t* offsets, uint32_t* ids, double* scores, uint64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "smatrix_rowlen_batch": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "smatrix_getrow_batch": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                           C.c_uint64]),
+    "smatrix_cf_neighbors_batch": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_uint64]),
     # include/smatrix_b200.h
     "smatrix_b200_open": (C.c_void_p, [C.c_char_p, C.c_int]),
     "smatrix_b200_device": (C.c_int, [C.c_void_p]),

@@ -726,6 +726,58 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
   return total;
 }
 
+/* neighbours + cosine scores for a batch of items (examples/cf_recommender.c:50-86) */
+uint64_t smatrix_cf_neighbors_batch(smatrix_t* s, const uint32_t* items, size_t n, uint64_t* offsets,
+                                    uint32_t* ids, double* scores, uint64_t cap) {
+  if (n == 0) {
+    if (offsets) { uint64_t zero = 0; enter(s); CK(cudaMemcpy(offsets, &zero, 8, cudaMemcpyDefault)); leave(s); }
+    return 0;
+  }
+  if (n >= 0xFFFFFFFFull) smx_die("cf_neighbors_batch: too many items in one call");
+  enter(s);
+  const uint32_t nn = (uint32_t)n;
+  const int dev = is_device_ptr(items);
+  const uint32_t tiles = smx_scan_scratch_items(nn);
+  ensure_tmp(s, (size_t)nn * 8, ((size_t)nn + 1 + tiles) * 8);
+  const uint32_t* d_items = items;
+  if (!dev) {
+    CK(cudaMemcpyAsync(s->d_tmp, items, (size_t)nn * 4, cudaMemcpyHostToDevice, s->stream));
+    d_items = s->d_tmp;
+  }
+  const uint64_t total = plan_rows(s, d_items, nn, s->d_tmp + nn);
+  if (offsets) CK(cudaMemcpyAsync(offsets, s->d_tmp64, ((size_t)nn + 1) * 8, cudaMemcpyDefault, s->stream));
+  if (ids && scores && total <= cap && total > 0) {
+    if (total * 8 > s->d_rowbuf_bytes) {
+      if (s->d_rowbuf) cudaFree(s->d_rowbuf);
+      s->d_rowbuf_bytes = (size_t)total * 8;
+      s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
+    }
+    smx_launch_getrow_fill(s->stream, view_of(s), d_items, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
+    const int out_dev = is_device_ptr(ids);
+    if (is_device_ptr(scores) != out_dev) smx_die("batch arrays must be all host or all device pointers");
+    uint32_t* d_ids = ids;
+    double* d_scores = scores;
+    void* tmp = NULL;
+    if (!out_dev) {
+      tmp = dmalloc(s, (size_t)total * 12 + 64);
+      d_scores = (double*)tmp;
+      d_ids = (uint32_t*)((char*)tmp + (size_t)total * 8);
+    }
+    smx_launch_cf_scores(s->stream, view_of(s), d_items, nn, s->d_tmp64, s->d_rowbuf, d_ids, d_scores);
+    s->n_launches += 2;
+    if (!out_dev) {
+      CK(cudaMemcpyAsync(ids, d_ids, (size_t)total * 4, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaMemcpyAsync(scores, d_scores, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      CK(cudaFree(tmp));
+    }
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+  return total;
+}
+
 /* ------------------------------------------------------------------------------ single ops */
 static uint32_t single_write(smatrix_t* s, int api_op, uint32_t x, uint32_t y, uint32_t v) {
   enter(s);

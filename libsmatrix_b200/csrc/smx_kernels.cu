@@ -803,6 +803,35 @@ k_getrow_big(smx_view_t V, const uint32_t* xs, const uint32_t* big_list, uint32_
   }
 }
 
+/* ---- the read side of the co-occurrence recommender (examples/cf_recommender.c:50-86) ------
+ * one warp per item a: total_a = value at (a, 0); for every pair (b, cc) of a's row (already
+ * compacted into `pairs`): total_b = value at (b, 0), 1 if zero; score = cc / (sqrt(total_a) *
+ * sqrt(total_b)), 0 if the denominator is 0 or smaller than cc (cf_cosine, :67-86).  IEEE double
+ * sqrt / mul / div are correctly rounded on the device too, so scores are bit-exact with the CPU. */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_cf_scores(smx_view_t V, const uint32_t* items, uint32_t n, const ull* offsets, const uint32_t* pairs,
+            uint32_t* ids, double* scores) {
+  const uint32_t lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
+  const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
+  for (uint32_t i = warp; i < n; i += nwarps) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t a_total = 0u;
+    if (dir_find(V, items[i], false, &e, &h) == DIR_FOUND) a_total = h.c0;
+    const double sa = sqrt((double)a_total);
+    for (ull k = offsets[i] + lane; k < offsets[i + 1]; k += SMX_WARP) {
+      const uint32_t b = pairs[2 * k], cc = pairs[2 * k + 1];
+      uint32_t b_total = 0u;
+      if (dir_find(V, b, false, &e, &h) == DIR_FOUND) b_total = h.c0;
+      if (b_total == 0u) b_total = 1u;
+      const double num = (double)cc, den = sa * sqrt((double)b_total);
+      ids[k] = b;
+      scores[k] = (den == 0.0 || num > den) ? 0.0 : num / den;
+    }
+  }
+}
+
 /* ---- snapshot support (file mode, reference src/smatrix.c:30-72) --------------------------- */
 /* all row ids of the directory, in no particular order */
 __global__ void __launch_bounds__(SMX_BLOCK) k_list_rows(smx_view_t V, uint32_t* keys, uint32_t* counter) {
@@ -1164,6 +1193,13 @@ extern "C" void smx_launch_load_fixup(smx_stream_t st, smx_view_t v, const uint3
                                       const uint32_t* slogs, uint32_t n) {
   if (!n) return;
   SMX_LAUNCH(k_load_fixup, grid_for(n), SMX_BLOCK, st, v, xs, slogs, n);
+}
+extern "C" void smx_launch_cf_scores(smx_stream_t st, smx_view_t v, const uint32_t* items, uint32_t n,
+                                     const uint64_t* offsets, const uint32_t* pairs, uint32_t* ids,
+                                     double* scores) {
+  if (!n) return;
+  SMX_LAUNCH(k_cf_scores, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, items, n, (const ull*)offsets,
+             pairs, ids, scores);
 }
 extern "C" void smx_launch_count_nnz(smx_stream_t st, smx_view_t v) {
   SMX_LAUNCH(k_count_nnz, grid_for(v.dir_cap), SMX_BLOCK, st, v);

@@ -191,6 +191,20 @@ class SparseMatrix:
             assert got == total
         return offsets, pairs
 
+    def cf_neighbors_batch(self, items):
+        """examples/cf_recommender.c:50-86 for a batch of items -> (offsets[n+1], ids[total], scores[total])."""
+        items = np.ascontiguousarray(items, dtype=np.uint32)
+        n = len(items)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        total = int(self._lib.smatrix_cf_neighbors_batch(self._handle(), items.ctypes.data, n,
+                                                         offsets.ctypes.data, None, None, 0))
+        ids = np.zeros(total, dtype=np.uint32)
+        scores = np.zeros(total, dtype=np.float64)
+        if total:
+            self._lib.smatrix_cf_neighbors_batch(self._handle(), items.ctypes.data, n, offsets.ctypes.data,
+                                                 ids.ctypes.data, scores.ctypes.data, total)
+        return offsets, ids, scores
+
     # ---- device controls (include/smatrix_b200.h) --------------------------------------------
     def stat(self, name: str) -> int:
         return int(self._lib.smatrix_b200_stat(self._handle(), binding.STAT[name]))

@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+using std::sqrt;
 
 #define SMX_WARP 1
 #define __global__

@@ -375,3 +375,28 @@ def scenario_read_path_zipf(make, n_rows: int = 3000, max_len: int = 20000, seed
     sample = rng.integers(0, len(xs), 5000)
     compare(m, ref, np.concatenate([ids, np.array([1, 2, 3], U32)]), xs[sample], ys[sample])
     m.close(); ref.close()
+
+
+def scenario_cf_read_side(make, n_baskets: int = 2000, n_items: int = 300):
+    """SURVEY.md 8f N4 — neighbors_for_item + cf_cosine (examples/cf_recommender.c:50-86) for a batch of
+    items against the same arithmetic done on the CPU with the checker's get / getrow; IEEE double
+    sqrt, multiply and divide are correctly rounded on both sides, so the scores match bit for bit."""
+    rng = np.random.default_rng(53)
+    xs, ys = cf_stream(rng, n_baskets, n_items)
+    m, ref = make(), checker()
+    m.incr_batch(xs, ys, None); ref.apply("incr", xs, ys, np.ones(len(xs), U32))
+    items = np.concatenate([np.arange(1, n_items + 1, dtype=U32)[::3], np.array([0, 99999], U32)])
+    offsets, ids, scores = m.cf_neighbors_batch(items)
+    o2, p2 = ref.getrow_many(items)
+    assert (offsets == o2).all()
+    for i, a in enumerate(items):
+        lo, hi = int(offsets[i]), int(offsets[i + 1])
+        got = dict(zip(ids[lo:hi].tolist(), scores[lo:hi].tolist()))
+        a_total = ref.get(int(a), 0)
+        want = {}
+        for b, cc in p2[lo:hi]:
+            b_total = ref.get(int(b), 0) or 1
+            den = np.sqrt(np.float64(a_total)) * np.sqrt(np.float64(b_total))
+            want[int(b)] = 0.0 if (den == 0.0 or np.float64(cc) > den) else float(np.float64(cc) / den)
+        assert got == want, f"item {a}"
+    m.close(); ref.close()

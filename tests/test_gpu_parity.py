@@ -99,6 +99,10 @@ def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=20000, max_len=200000)
 
 
+def test_cf_read_side(make_default):
+    ps.scenario_cf_read_side(make_default, n_baskets=20000, n_items=2000)
+
+
 def test_snapshot_interchange(tmp_path):
     import snapshot_suite as ss
     ss.scenario_snapshot_interchange(lambda f: SparseMatrix(f), tmp_path)

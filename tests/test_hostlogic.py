@@ -93,6 +93,10 @@ def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=300, max_len=3000)
 
 
+def test_cf_read_side(make):
+    ps.scenario_cf_read_side(make, n_baskets=300, n_items=80)
+
+
 def test_snapshot_interchange(sim, tmp_path, monkeypatch):
     import snapshot_suite as ss
     monkeypatch.setenv("SMATRIX_DIR_LOG2", "6")
