@@ -224,23 +224,35 @@ static char* slab_reserve(smatrix_t* s, size_t bytes) {
 }
 
 /* ------------------------------------------------------------------------------ scratch */
+/* Per-chunk scratch comes from the arena when there is one (sized once for the largest chunk, never
+ * freed on its own), so that a table with a reserved arena makes no cudaMalloc call at all while
+ * batches are applied; otherwise it is cudaMalloc'ed and regrown on demand. */
+static void* scratch_alloc(smatrix_t* s, size_t bytes) {
+  return s->arena_bytes ? (void*)slab_reserve(s, bytes) : dmalloc(s, bytes);
+}
+static void scratch_free(smatrix_t* s, void* p) {
+  if (p && !s->arena_bytes) cudaFree(p);
+}
+
 static void ensure_lists(smatrix_t* s, uint32_t n) {
   if (n <= s->list_cap) return;
   uint32_t cap = s->list_cap ? s->list_cap : 1024;
   while (cap < n) cap *= 2;
   if (cap > s->chunk_max) cap = s->chunk_max > n ? s->chunk_max : n;
+  if (s->arena_bytes && cap < s->chunk_max) cap = s->chunk_max; /* once, at full size */
   if (s->list_cap) {
     CK(cudaStreamSynchronize(s->stream));
-    cudaFree(s->defer[0]); cudaFree(s->defer[1]); cudaFree(s->lists.late); cudaFree(s->lists.grow);
-    cudaFree(s->lists.t0rows); cudaFree(s->lists.plan); cudaFree(s->lists.big);
+    scratch_free(s, s->defer[0]); scratch_free(s, s->defer[1]); scratch_free(s, s->lists.late);
+    scratch_free(s, s->lists.grow); scratch_free(s, s->lists.t0rows); scratch_free(s, s->lists.plan);
+    scratch_free(s, s->lists.big);
   }
-  s->defer[0] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
-  s->defer[1] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
-  s->lists.late = (uint32_t*)dmalloc(s, (size_t)cap * 4);
-  s->lists.grow = (uint32_t*)dmalloc(s, (size_t)cap * 4);
-  s->lists.t0rows = (uint32_t*)dmalloc(s, (size_t)cap * 4);
-  s->lists.plan = (smx_plan_t*)dmalloc(s, (size_t)cap * sizeof(smx_plan_t));
-  s->lists.big = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->defer[0] = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
+  s->defer[1] = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
+  s->lists.late = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
+  s->lists.grow = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
+  s->lists.t0rows = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
+  s->lists.plan = (smx_plan_t*)scratch_alloc(s, (size_t)cap * sizeof(smx_plan_t));
+  s->lists.big = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
   s->list_cap = cap;
 }
 
@@ -411,10 +423,10 @@ static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
   if (n > s->part_cap) {
     if (s->part_cap) {
       CK(cudaStreamSynchronize(s->stream));
-      for (int a = 0; a < 4; a++) cudaFree(s->part[a]);
+      for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
     }
     s->part_cap = s->list_cap > n ? s->list_cap : n;
-    for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)dmalloc(s, (size_t)s->part_cap * 4);
+    for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)scratch_alloc(s, (size_t)s->part_cap * 4);
   }
   ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
@@ -468,9 +480,9 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   if (n_late) run_pass(s, ops, op, SMX_PASS_LATE, s->lists.late, n_late);
   if (api_op == 2) { /* set: last writer in input order wins */
     if (n > s->addrs_cap) {
-      if (s->addrs) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->addrs); }
+      if (s->addrs) { CK(cudaStreamSynchronize(s->stream)); scratch_free(s, s->addrs); }
       s->addrs_cap = s->list_cap > n ? s->list_cap : n;
-      s->addrs = (uint64_t*)dmalloc(s, (size_t)s->addrs_cap * 8);
+      s->addrs = (uint64_t*)scratch_alloc(s, (size_t)s->addrs_cap * 8);
     }
     smx_launch_set_max(s->stream, view_of(s), ops, s->addrs);
     smx_launch_set_commit(s->stream, ops, s->addrs);
@@ -1198,12 +1210,13 @@ void smatrix_close(smatrix_t* s) {
   cudaFree(s->d_small);
   cudaFreeHost(s->h_small);
   if (s->list_cap) {
-    cudaFree(s->defer[0]); cudaFree(s->defer[1]); cudaFree(s->lists.late); cudaFree(s->lists.grow);
-    cudaFree(s->lists.t0rows); cudaFree(s->lists.plan); cudaFree(s->lists.big);
+    scratch_free(s, s->defer[0]); scratch_free(s, s->defer[1]); scratch_free(s, s->lists.late);
+    scratch_free(s, s->lists.grow); scratch_free(s, s->lists.t0rows); scratch_free(s, s->lists.plan);
+    scratch_free(s, s->lists.big);
   }
-  if (s->addrs) cudaFree(s->addrs);
+  scratch_free(s, s->addrs);
   if (s->part_cap)
-    for (int a = 0; a < 4; a++) cudaFree(s->part[a]);
+    for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
   if (s->stage_cap)
     for (int b = 0; b < 2; b++)
       for (int a = 0; a < 3; a++) cudaFree(s->stage[b][a]);
