@@ -294,6 +294,7 @@ def main_ours(a):
     incr_mops = K * B * world / (ms_build * 1e-3) / 1e6
     del xs, ys
     nnz_local, rows_local = m.stat("nnz"), m.stat("rows")
+    vsum_local = m.stat("value_sum")     # every op added 1: the table-wide sum must equal the op count
     stats = {k: m.stat(k) for k in ("dir_cap", "slab_bytes", "device_bytes", "row_grows", "dir_grows")}
 
     # ---- timed gets (50 % hits): all queries resident first
@@ -317,6 +318,7 @@ def main_ours(a):
     m.set_kernel_timing(False)
     get_mops = G * world / (ms_get * 1e-3) / 1e6
     hits = int((out != 0).sum().item())
+    odd_hits = int((out[1::2] != 0).sum().item()) if (rank * G) % 2 == 0 else int((out[0::2] != 0).sum().item())
     del qx, qy, out
 
     # ---- read path on the same table (BASELINE config 4 shape): rowlen over all rows, getrow of 2 M rows
@@ -360,11 +362,15 @@ def main_ours(a):
         e2e = run_e2e(a, torch, dev, local, with_arena(lambda: SparseMatrix(device=local)), B, K, prefill, n_batches)
 
     if world > 1:
-        t = torch.tensor([nnz_local, rows_local], dtype=torch.int64, device=dev)
+        t = torch.tensor([nnz_local, rows_local, vsum_local], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
-        nnz_total, rows_seen = int(t[0].item()), int(t[1].item())
+        nnz_total, rows_seen, vsum_total = int(t[0].item()), int(t[1].item()), int(t[2].item())
     else:
-        nnz_total, rows_seen = nnz_local, rows_local
+        nnz_total, rows_seen, vsum_total = nnz_local, rows_local, vsum_local
+    applied = n_batches * B * world
+    checks = {"value_sum": vsum_total, "ops_applied": applied, "value_sum_ok": vsum_total == applied,
+              "hit_fraction_exact": (odd_hits == 0 and hits == G - G // 2) if world == 1 else (odd_hits == 0),
+              "rows_ok": rows_seen <= rows_total}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -417,7 +423,7 @@ def main_ours(a):
                    "on-demand cudaMalloc is the fallback and costs 0.3-8 ms/step on this pool",
                    "chunk_ops": int(os.environ.get("SMATRIX_CHUNK", 1 << 25)),
                    "parallelism": f"row-hash shard x{world}" if world > 1 else "single GPU"},
-        "get_mops": get_mops, "get_ms": ms_get, "get_hit_fraction": hits / G,
+        "get_mops": get_mops, "get_ms": ms_get, "get_hit_fraction": hits / G, "checks": checks,
         "nnz": nnz_total, "rows_present": rows_seen, "prefill_s": t_prefill,
         "table": stats, "clocks": clocks, "gpu_launches": launches, "upsert_rounds": rounds,
         "host_phase_ms_per_step": phases, "step_ms": step_ms, "step_upsert_kernel_ms": kern_ms,

@@ -39,7 +39,8 @@ enum {
   SMX_STAT_KERNEL_NS = 9,   /* device time of the dominant (update / get) kernels, ns, when timing is on */
   /* host wall-clock per phase of the write path since set_kernel_timing(1), ns */
   SMX_STAT_NS_PARTITION = 10, SMX_STAT_NS_UPSERT = 11, SMX_STAT_NS_GROW_PLAN = 12,
-  SMX_STAT_NS_SLAB = 13, SMX_STAT_NS_MIGRATE = 14, SMX_STAT_NS_DIR = 15
+  SMX_STAT_NS_SLAB = 13, SMX_STAT_NS_MIGRATE = 14, SMX_STAT_NS_DIR = 15,
+  SMX_STAT_VALUE_SUM = 16   /* sum of every stored value mod 2^64 (scans the whole table) */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 

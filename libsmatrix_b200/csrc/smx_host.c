@@ -1280,6 +1280,13 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
       read_ctl(s);
       r = s->h_ctl->scratch;
       break;
+    case SMX_STAT_VALUE_SUM:
+      CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
+      smx_launch_sum_values(s->stream, view_of(s));
+      s->n_launches++;
+      read_ctl(s);
+      r = s->h_ctl->scratch;
+      break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;
     case SMX_STAT_SLAB_BYTES: r = s->slab_bytes; break;
     case SMX_STAT_DEVICE_BYTES:

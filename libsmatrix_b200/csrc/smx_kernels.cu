@@ -871,6 +871,28 @@ k_load_fixup(smx_view_t V, const uint32_t* xs, const uint32_t* slogs, uint32_t n
   }
 }
 
+/* sum of every stored value (all cells + column 0) mod 2^64 -> ctl->scratch: one warp per
+ * directory entry walks that row's bucket.  For an incr-only build this must equal the sum of all
+ * increments — the size-independent invariant bench.py checks at full scale. */
+__global__ void __launch_bounds__(SMX_BLOCK) k_sum_values(smx_view_t V) {
+  const uint32_t lane = lane_id();
+  const ull warp = (blockIdx.x * (ull)blockDim.x + threadIdx.x) / SMX_WARP;
+  const ull nwarps = (ull)gridDim.x * blockDim.x / SMX_WARP;
+  ull acc = 0;
+  for (ull pos = warp; pos < V.dir_cap; pos += nwarps) {
+    const smx_row_t* e = V.dir + pos;
+    const Hdr h = ld_hdr(e);
+    if (!(h.meta & SMX_META_USED)) continue;
+    if (lane == 0) acc += h.c0;
+    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    const ull* base = (caplog == SMX_INLINE_LOG) ? (const ull*)e->inl : (const ull*)h.slots;
+    const ull cap = 1ull << caplog;
+    for (ull c = lane; c < cap; c += SMX_WARP) acc += base[c] >> 32;
+  }
+  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(SMX_FULL, acc, d);
+  if (lane == 0 && acc) atomicAdd(&V.ctl->scratch, acc);
+}
+
 /* nnz = sum over rows of live + (c0 != 0) -> ctl->scratch */
 __global__ void __launch_bounds__(SMX_BLOCK) k_count_nnz(smx_view_t V) {
   ull acc = 0;
@@ -1200,6 +1222,9 @@ extern "C" void smx_launch_cf_scores(smx_stream_t st, smx_view_t v, const uint32
   if (!n) return;
   SMX_LAUNCH(k_cf_scores, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, items, n, (const ull*)offsets,
              pairs, ids, scores);
+}
+extern "C" void smx_launch_sum_values(smx_stream_t st, smx_view_t v) {
+  SMX_LAUNCH(k_sum_values, grid_for(v.dir_cap * SMX_WARP), SMX_BLOCK, st, v);
 }
 extern "C" void smx_launch_count_nnz(smx_stream_t st, smx_view_t v) {
   SMX_LAUNCH(k_count_nnz, grid_for(v.dir_cap), SMX_BLOCK, st, v);

@@ -296,6 +296,7 @@ def scenario_many_rows(make, n_rows: int):
     sample = rng.integers(0, len(xs), 20000)
     compare(m, ref, ids[:: max(1, n_rows // 3000)], xs[sample], ys[sample])
     assert m.stat("nnz") == len(np.unique(xs.astype(np.uint64) << np.uint64(32) | ys))
+    assert m.stat("value_sum") == len(xs)        # every op added 1
     m.close(); ref.close()
 
 
