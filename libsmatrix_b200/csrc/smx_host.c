@@ -309,7 +309,8 @@ static void grow_rows(smatrix_t* s, uint32_t n_grow) {
   const uint32_t n_big = s->h_ctl->n_big;
   char* region = slab_reserve(s, bytes);
   double t2 = now_ns();
-  CK(cudaMemsetAsync(region, 0, bytes, s->stream));
+  /* buckets built in shared memory are written out whole; only in-place (global CAS) fills need zeros */
+  if (s->h_ctl->need_zero) CK(cudaMemsetAsync(region, 0, bytes, s->stream));
   smx_launch_migrate(s->stream, v, s->lists, n_grow, n_big, region);
   if (s->timing) CK(cudaStreamSynchronize(s->stream)); /* attribute the device time to this phase */
   s->n_launches += 1 + (n_big ? 2 : 0);
@@ -351,6 +352,7 @@ static void resize_dir(smatrix_t* s, uint64_t new_cap) {
 static void zero_round_counters(smatrix_t* s) {
   CK(cudaMemsetAsync(&s->d_ctl->n_defer, 0,
                      offsetof(smx_ctl_t, scratch) - offsetof(smx_ctl_t, n_defer), s->stream));
+  /* n_defer .. need_zero are contiguous and precede `scratch` */
 }
 
 /* Run one pass to completion: rounds of (launch, grow, re-run the ops that were turned away). */

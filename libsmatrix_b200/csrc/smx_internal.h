@@ -66,6 +66,8 @@ typedef struct {
   uint32_t n_grow;               /* rows queued for growth                                   */
   uint32_t n_big;                /* of those, rows whose OLD bucket is >= 2^SMX_BIG_LOG      */
   unsigned long long plan_bytes; /* bytes of new buckets planned by grow_plan                */
+  unsigned long long need_zero;  /* planned buckets that are filled in place (global CAS) and so
+                                    need a zeroed region; shared-memory-built buckets do not  */
   unsigned long long scratch;    /* misc: reductions (nnz, probe checksums)                  */
   /* persistent: rows per directory slice (slice = position >> dir_slice_shift); new rows are
    * refused in a slice at its limit, so that no region of the directory exceeds the load limit

@@ -298,8 +298,11 @@ __device__ __forceinline__ int upsert_one(const smx_view_t& V, const smx_lists_t
   return r2 == SLOT_FULL ? ST_DEFER : ST_OK;
 }
 
+#ifndef SMX_UPSERT_MIN_BLOCKS
+#define SMX_UPSERT_MIN_BLOCKS 8 /* 8 x 256 threads resident per SM: caps the kernel at 32 registers */
+#endif
 template <int OP>
-__global__ void __launch_bounds__(SMX_BLOCK)
+__global__ void __launch_bounds__(SMX_BLOCK, SMX_UPSERT_MIN_BLOCKS)
 k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* list, uint32_t m,
          int preagg) {
   /* ops that are turned away are staged per block and appended to the retry list with ONE global
@@ -377,6 +380,7 @@ k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* lis
 /* ------------------------------------------------------------------------------------------
  * K7: row growth (replaces smatrix_rmap_resize, :383-416)
  * ---------------------------------------------------------------------------------------- */
+#define SMX_SMEM_MIGRATE_LOG 8u /* new buckets up to 2^8 cells are built in shared memory by k_migrate */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
   const uint32_t lane = lane_id();
@@ -413,6 +417,7 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       p.off = base + incl - bytes;
       S.plan[j] = p;
       if (caplog >= SMX_BIG_LOG) S.big[agg_inc(&V.ctl->n_big)] = j;
+      if (newlog > SMX_SMEM_MIGRATE_LOG || caplog >= SMX_BIG_LOG) agg_inc64(&V.ctl->need_zero);
     }
   }
 }
@@ -442,7 +447,6 @@ __device__ __forceinline__ void finish_growth(smx_row_t* e, const Hdr& h, ull* n
 /* one warp per growing row (old bucket < 2^SMX_BIG_LOG cells).  New buckets of up to
  * 2^SMX_SMEM_MIGRATE_LOG cells — the bulk of all growth events — are built in shared memory and
  * written out as whole lines (streaming); larger ones are filled in place with global CAS. */
-#define SMX_SMEM_MIGRATE_LOG 8u
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
   __shared__ ull sbuf[SMX_BLOCK / SMX_WARP][1u << SMX_SMEM_MIGRATE_LOG];
@@ -467,7 +471,6 @@ k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
       for (uint32_t s0 = lane; s0 < cap; s0 += SMX_WARP) {
         const ull c = ob[s0];
         if (c == 0ull) continue;
-        ob[s0] = 0ull; /* vacated buckets are always zero */
         uint32_t sidx = smx_mix_col((uint32_t)c) & (nsec - 1u);
         for (bool placed = false; !placed; sidx = (sidx + 1u) & (nsec - 1u))
           for (int k = 0; k < 4 && !placed; ++k)
@@ -478,10 +481,7 @@ k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
     } else {
       for (uint32_t s0 = lane; s0 < cap; s0 += SMX_WARP) {
         const ull c = ob[s0];
-        if (c != 0ull) {
-          place_cell(nb, p.newlog, c);
-          ob[s0] = 0ull;
-        }
+        if (c != 0ull) place_cell(nb, p.newlog, c);
       }
     }
     __syncwarp();
@@ -501,10 +501,7 @@ k_migrate_big(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region) {
   const ull cap = 1ull << caplog;
   for (ull s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (ull)gridDim.x * blockDim.x) {
     const ull c = ob[s];
-    if (c != 0ull) {
-      place_cell(nb, p.newlog, c);
-      ob[s] = 0ull;
-    }
+    if (c != 0ull) place_cell(nb, p.newlog, c);
   }
 }
 __global__ void k_migrate_big_finish(smx_view_t V, smx_lists_t S, uint32_t n_big, char* region) {
