@@ -23,7 +23,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = shutil.which("nvcc") or os.path.join(CUDA_HOME, "bin", "nvcc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("SMX_NVCC_EXTRA", "").split()
 GCC_FLAGS = ["-O2", "-fPIC", "-Wall", "-Wextra", "-std=gnu11", f"-I{CUDA_HOME}/include"]
 
 

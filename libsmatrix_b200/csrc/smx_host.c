@@ -1166,15 +1166,17 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
   if (s->parts_log_max > 8) s->parts_log_max = 8;
+  s->arena_bytes = (size_t)env_u32("SMATRIX_ARENA_GIB", 0) << 30;
+  if (s->arena_bytes) push_segment(s, (char*)dmalloc(s, s->arena_bytes), s->arena_bytes);
   s->dir_cap = 1ull << s->dir_log_min;
-  s->dir = (smx_row_t*)dmalloc(s, (size_t)s->dir_cap * sizeof(smx_row_t));
+  s->dir_in_arena = s->arena_bytes != 0; /* then nothing is cudaFree'd while batches are applied */
+  s->dir = s->dir_in_arena ? (smx_row_t*)slab_reserve(s, (size_t)s->dir_cap * sizeof(smx_row_t))
+                           : (smx_row_t*)dmalloc(s, (size_t)s->dir_cap * sizeof(smx_row_t));
   CK(cudaMemsetAsync(s->dir, 0, (size_t)s->dir_cap * sizeof(smx_row_t), s->stream));
   s->d_ctl = (smx_ctl_t*)dmalloc(s, sizeof(smx_ctl_t));
   CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(smx_ctl_t), s->stream));
   CK(cudaHostAlloc((void**)&s->h_ctl, sizeof(smx_ctl_t), cudaHostAllocDefault));
   memset(s->h_ctl, 0, sizeof(smx_ctl_t));
-  s->arena_bytes = (size_t)env_u32("SMATRIX_ARENA_GIB", 0) << 30;
-  if (s->arena_bytes) push_segment(s, (char*)dmalloc(s, s->arena_bytes), s->arena_bytes);
   s->d_small = (uint32_t*)dmalloc(s, 64 * 4);
   CK(cudaHostAlloc((void**)&s->h_small, 64 * 4, cudaHostAllocDefault));
   CK(cudaStreamSynchronize(s->stream));
