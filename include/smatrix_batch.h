@@ -33,6 +33,18 @@ void smatrix_decr_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
 void smatrix_set_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
                        const uint32_t* vals, size_t n);
 
+/* The same three calls, additionally returning what every single call would have returned
+ * (src/smatrix.c:230,241,252): out[i] = value of cell (xs[i], ys[i]) right after
+ * op i, as if the batch had been applied one op at a time in input order — so duplicate keys see
+ * each other's effect in order (running sums mod 2^32 for incr / decr; set returns its own value).
+ * Costs a look-up pass, a stable sort by cell and a segmented scan on top of the plain batch. */
+void smatrix_incr_batch_out(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
+                            const uint32_t* vals, size_t n, uint32_t* out);
+void smatrix_decr_batch_out(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
+                            const uint32_t* vals, size_t n, uint32_t* out);
+void smatrix_set_batch_out(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
+                           const uint32_t* vals, size_t n, uint32_t* out);
+
 /* n x smatrix_get (src/smatrix.c:174-185): out[i] = value at (xs[i], ys[i]) or 0. */
 void smatrix_get_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys, size_t n,
                        uint32_t* out);

@@ -95,6 +95,15 @@ struct smatrix_s {
   size_t d_tmp64_bytes;
   uint32_t* d_rowbuf;
   size_t d_rowbuf_bytes;
+  /* *_batch_out (exact per-op return values): scratch sized for bo_cap ops */
+  uint32_t bo_cap;
+  uint64_t* bo_addr[2];
+  uint32_t* bo_idx[2];
+  uint64_t* bo_seg;
+  uint64_t* bo_tiles;
+  uint32_t* bo_out;
+  void* bo_sort;
+  size_t bo_sort_bytes;
   uint32_t* d_big;      /* getrow: indices of big rows in the current query + per-row output cursors */
   uint32_t* d_cursors;
   size_t d_big_bytes;
@@ -572,6 +581,85 @@ void smatrix_decr_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
 void smatrix_set_batch(smatrix_t* self, const uint32_t* xs, const uint32_t* ys,
                        const uint32_t* vals, size_t n) {
   write_batch(self, 2, xs, ys, vals, n);
+}
+
+/* ---- N1: the same batches, returning every op's value as if applied one by one in input order ---- */
+static void ensure_batch_out(smatrix_t* s, uint32_t n) {
+  if (n <= s->bo_cap) return;
+  if (s->bo_cap) {
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->bo_addr[0]); cudaFree(s->bo_addr[1]); cudaFree(s->bo_idx[0]); cudaFree(s->bo_idx[1]);
+    cudaFree(s->bo_seg); cudaFree(s->bo_tiles); cudaFree(s->bo_out); cudaFree(s->bo_sort);
+  }
+  uint32_t cap = n < 4096 ? 4096 : n;
+  s->bo_addr[0] = (uint64_t*)dmalloc(s, (size_t)cap * 8);
+  s->bo_addr[1] = (uint64_t*)dmalloc(s, (size_t)cap * 8);
+  s->bo_idx[0] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->bo_idx[1] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->bo_seg = (uint64_t*)dmalloc(s, (size_t)cap * 8);
+  s->bo_tiles = (uint64_t*)dmalloc(s, ((size_t)smx_scan_scratch_items(cap) + 1) * 8);
+  s->bo_out = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+  s->bo_sort_bytes = smx_batch_out_sort_bytes(cap);
+  s->bo_sort = dmalloc(s, s->bo_sort_bytes);
+  s->bo_cap = cap;
+}
+
+static void chunk_out(smatrix_t* s, int api_op, const uint32_t* d_xs, const uint32_t* d_ys, const uint32_t* d_vs,
+                      uint32_t n, uint32_t* d_out) {
+  process_chunk(s, api_op, d_xs, d_ys, d_vs, n);
+  ensure_batch_out(s, n);
+  smx_ops_t ops;
+  ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = NULL; ops.v_const = 1u; ops.n = n;
+  smx_launch_batch_out(s->stream, view_of(s), ops, api_op == 2 ? SMX_OP_SETZERO : api_op, d_out, s->bo_addr[0],
+                       s->bo_addr[1], s->bo_idx[0], s->bo_idx[1], s->bo_seg, s->bo_tiles, s->bo_sort,
+                       s->bo_sort_bytes);
+  s->n_launches += 7;
+}
+
+static void write_batch_out(smatrix_t* s, int api_op, const uint32_t* xs, const uint32_t* ys, const uint32_t* vs,
+                            size_t n, uint32_t* out) {
+  if (n == 0) return;
+  if (!out) smx_die("batch_out: out must not be NULL");
+  enter(s);
+  const int dev = is_device_ptr(xs);
+  if (is_device_ptr(ys) != dev || (vs && is_device_ptr(vs) != dev) || is_device_ptr(out) != dev)
+    smx_die("batch arrays must be all host or all device pointers");
+  if (dev) {
+    for (size_t off = 0; off < n; off += s->chunk_max) {
+      const uint32_t len = (uint32_t)((n - off < s->chunk_max) ? n - off : s->chunk_max);
+      chunk_out(s, api_op, xs + off, ys + off, vs ? vs + off : NULL, len, out + off);
+    }
+    CK(cudaStreamSynchronize(s->stream));
+  } else {
+    uint32_t step = s->chunk_max < s->stage_max ? s->chunk_max : s->stage_max;
+    if (n < step) step = (uint32_t)n;
+    ensure_stage(s, step);
+    ensure_batch_out(s, step);
+    const uint32_t* src[3] = {xs, ys, vs};
+    for (size_t off = 0; off < n; off += step) {
+      const uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
+      for (int a = 0; a < 3; a++)
+        if (src[a]) CK(cudaMemcpyAsync(s->stage[0][a], src[a] + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
+      chunk_out(s, api_op, s->stage[0][0], s->stage[0][1], vs ? s->stage[0][2] : NULL, len, s->bo_out);
+      CK(cudaMemcpyAsync(out + off, s->bo_out, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+    }
+  }
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+void smatrix_incr_batch_out(smatrix_t* self, const uint32_t* xs, const uint32_t* ys, const uint32_t* vals,
+                            size_t n, uint32_t* out) {
+  write_batch_out(self, 0, xs, ys, vals, n, out);
+}
+void smatrix_decr_batch_out(smatrix_t* self, const uint32_t* xs, const uint32_t* ys, const uint32_t* vals,
+                            size_t n, uint32_t* out) {
+  write_batch_out(self, 1, xs, ys, vals, n, out);
+}
+void smatrix_set_batch_out(smatrix_t* self, const uint32_t* xs, const uint32_t* ys, const uint32_t* vals,
+                           size_t n, uint32_t* out) {
+  write_batch_out(self, 2, xs, ys, vals, n, out);
 }
 
 void smatrix_b200_apply_ordered(smatrix_t* s, int op, const uint32_t* d_xs, const uint32_t* d_ys,
@@ -1228,6 +1316,10 @@ void smatrix_close(smatrix_t* s) {
   if (s->d_tmp64) cudaFree(s->d_tmp64);
   if (s->d_rowbuf) cudaFree(s->d_rowbuf);
   if (s->d_big) cudaFree(s->d_big);
+  if (s->bo_cap) {
+    cudaFree(s->bo_addr[0]); cudaFree(s->bo_addr[1]); cudaFree(s->bo_idx[0]); cudaFree(s->bo_idx[1]);
+    cudaFree(s->bo_seg); cudaFree(s->bo_tiles); cudaFree(s->bo_out); cudaFree(s->bo_sort);
+  }
   cudaEventDestroy(s->stage_ready[0]); cudaEventDestroy(s->stage_ready[1]);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   cudaEventDestroy(s->t_start); cudaEventDestroy(s->t_stop);

@@ -124,6 +124,10 @@ void smx_launch_finalize_t0(smx_stream_t stream, smx_view_t v, const uint32_t* t
 void smx_launch_sync_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* rows, uint32_t n);
 void smx_launch_set_max(smx_stream_t stream, smx_view_t v, smx_ops_t ops, uint64_t* addrs);
 void smx_launch_set_commit(smx_stream_t stream, smx_ops_t ops, uint64_t* addrs); /* mark + commit */
+size_t smx_batch_out_sort_bytes(uint32_t n);
+void smx_launch_batch_out(smx_stream_t stream, smx_view_t v, smx_ops_t ops, int op, uint32_t* out,
+                          uint64_t* addrs_a, uint64_t* addrs_b, uint32_t* idx_a, uint32_t* idx_b,
+                          uint64_t* seg, uint64_t* tile_agg, void* sort_tmp, size_t sort_bytes);
 void smx_launch_get(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
                     uint32_t n, uint32_t* out);
 void smx_launch_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,

@@ -31,8 +31,11 @@
 #ifdef SMX_HOSTSIM
 #include "hostsim.h"
 #include "cuda_runtime_api.h"
+#include <algorithm>
+#include <vector>
 #else
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh> /* only for the optional *_batch_out ordering step (N1) */
 #define SMX_WARP 32
 #define SMX_LAUNCH(kern, grid, block, stream, ...) \
   kern<<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
@@ -45,6 +48,9 @@ typedef unsigned long long ull;
 #else
 #define SMX_BLOCK (8 * SMX_WARP) /* 256 threads: 8 blocks/SM = 2048 resident threads */
 #endif
+
+#define SCAN_PER_THREAD 8
+#define SCAN_TILE (SMX_BLOCK * SCAN_PER_THREAD)
 
 enum { ST_OK = 0, ST_DEFER = 1, ST_LATE = 2, ST_DIRFULL = 3 };
 enum { DIR_FOUND = 0, DIR_CREATED = 1, DIR_MISS = 2, DIR_FULL = 3 };
@@ -600,6 +606,117 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_set_commit(smx_ops_t O, const ull
   }
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * N1: exact per-op return values of an incr / decr batch: out[i] = value of the
+ * cell right after op i when the batch is applied in input order (src/smatrix.c:241,:252).
+ * The chunk is applied by the ordinary path first; then: (1) k_find_addr locates every op's cell,
+ * (2) a STABLE sort of the op indices by cell address (input order is kept inside a cell's group),
+ * (3) a segmented inclusive scan over the REVERSED sorted sequence gives, per op, the sum of its
+ * own and all later deltas of the same cell, (4) out[i] = final - (that sum - own delta).
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SMX_BLOCK) k_find_addr(smx_view_t V, smx_ops_t O, ull* addrs, uint32_t* iota) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x) {
+    smx_row_t* e;
+    Hdr h;
+    uint32_t* vp = nullptr;
+    if (dir_find(V, O.xs[i], false, &e, &h) == DIR_FOUND) {
+      const uint32_t y = O.ys[i];
+      if (y == 0u) vp = &e->c0;
+      else slot_find(e, h, y, &vp);
+    }
+    addrs[i] = (ull)vp;
+    iota[i] = i;
+  }
+}
+/* reversed sorted order: element q <-> sorted position n-1-q; flag = first of its group in that order */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_out_gather(smx_ops_t O, int negate, const ull* sorted_addr, const uint32_t* sorted_idx, ull* seg) {
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < O.n; q += gridDim.x * blockDim.x) {
+    const uint32_t p = O.n - 1u - q;
+    const uint32_t i = sorted_idx[p];
+    uint32_t v = O.vs ? O.vs[i] : O.v_const;
+    if (negate) v = 0u - v;
+    const bool head = (p == O.n - 1u) || (sorted_addr[p + 1] != sorted_addr[p]);
+    seg[q] = (ull)v | ((ull)(head ? 1u : 0u) << 32);
+  }
+}
+/* segmented inclusive scan of (flag, value) pairs: value = low 32 bits (mod 2^32), flag = bit 32 */
+__device__ __forceinline__ ull seg_op(ull a, ull b) { /* a then b */
+  return (b >> 32) ? b : (((a >> 32) << 32) | (uint32_t)((uint32_t)a + (uint32_t)b));
+}
+__global__ void __launch_bounds__(SMX_BLOCK) k_seg_tile(const ull* seg, uint32_t n, ull* tile_agg) {
+  __shared__ ull sh[SMX_BLOCK];
+  const ull first = (ull)blockIdx.x * SCAN_TILE + (ull)threadIdx.x * SCAN_PER_THREAD;
+  ull acc = 0;
+  for (int k = 0; k < SCAN_PER_THREAD; ++k)
+    if (first + k < n) acc = seg_op(acc, seg[first + k]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ull t = 0;
+    for (uint32_t k = 0; k < blockDim.x; ++k) t = seg_op(t, sh[k]);
+    tile_agg[blockIdx.x] = t;
+  }
+}
+__global__ void k_seg_tiles(ull* tile_agg, uint32_t n_tiles) { /* one thread: exclusive carry per tile */
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ull run = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+      const ull a = tile_agg[t];
+      tile_agg[t] = run;
+      run = seg_op(run, a);
+    }
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_seg_apply(ull* seg, uint32_t n, const ull* tile_carry) {
+  __shared__ ull sh[SMX_BLOCK];
+  const ull first = (ull)blockIdx.x * SCAN_TILE + (ull)threadIdx.x * SCAN_PER_THREAD;
+  ull c[SCAN_PER_THREAD];
+  ull acc = 0;
+  for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+    c[k] = (first + k < n) ? seg[first + k] : 0ull;
+    acc = seg_op(acc, c[k]);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ull run = tile_carry[blockIdx.x] & 0xFFFFFFFFull; /* a carry never carries a flag into the tile */
+    for (uint32_t k = 0; k < blockDim.x; ++k) {
+      const ull v = sh[k];
+      sh[k] = run;
+      run = seg_op(run, v);
+    }
+  }
+  __syncthreads();
+  ull run = sh[threadIdx.x] & 0xFFFFFFFFull;
+  for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+    if (first + k < n) {
+      run = seg_op(run, c[k]);
+      seg[first + k] = run;
+      run &= 0xFFFFFFFFull;
+    }
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_out_write(smx_ops_t O, int negate, const ull* sorted_addr, const uint32_t* sorted_idx, const ull* seg,
+            uint32_t* out) {
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < O.n; q += gridDim.x * blockDim.x) {
+    const uint32_t p = O.n - 1u - q;
+    const uint32_t i = sorted_idx[p];
+    uint32_t v = O.vs ? O.vs[i] : O.v_const;
+    if (negate) v = 0u - v;
+    const uint32_t* vp = (const uint32_t*)sorted_addr[p];
+    const uint32_t fin = vp ? __ldcg(vp) : 0u;
+    out[i] = fin - ((uint32_t)seg[q] - v); /* final minus the deltas applied after op i */
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK) k_fill_out(smx_ops_t O, uint32_t* out) { /* set returns its value */
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < O.n; i += gridDim.x * blockDim.x)
+    out[i] = O.vs ? O.vs[i] : O.v_const;
+}
+
 /* ------------------------------------------------------------------------------------------
  * K4 / K5: point reads
  * ---------------------------------------------------------------------------------------- */
@@ -650,8 +767,6 @@ k_row_counts(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* counts, uin
   }
 }
 
-#define SCAN_PER_THREAD 8
-#define SCAN_TILE (SMX_BLOCK * SCAN_PER_THREAD)
 
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_scan_tile_sums(const uint32_t* counts, uint32_t n, ull* tile_sums) {
@@ -1158,6 +1273,53 @@ extern "C" void smx_launch_set_commit(smx_stream_t st, smx_ops_t ops, uint64_t* 
   if (!ops.n) return;
   SMX_LAUNCH(k_set_mark, grid_for(ops.n), SMX_BLOCK, st, ops, (ull*)addrs);
   SMX_LAUNCH(k_set_commit, grid_for(ops.n), SMX_BLOCK, st, ops, (const ull*)addrs);
+}
+
+
+/* scratch layout for smx_launch_batch_out (all sized n): addrs[2] (u64), idx[2] (u32), seg (u64),
+ * tile_agg (u64, smx_scan_scratch_items(n)), plus the sort's temporary storage */
+extern "C" size_t smx_batch_out_sort_bytes(uint32_t n) {
+#ifdef SMX_HOSTSIM
+  (void)n;
+  return 64;
+#else
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const ull*)nullptr, (ull*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n, 0, 48);
+  return bytes + 256;
+#endif
+}
+extern "C" void smx_launch_batch_out(smx_stream_t st, smx_view_t v, smx_ops_t ops, int op, uint32_t* out,
+                                     uint64_t* addrs_a, uint64_t* addrs_b, uint32_t* idx_a, uint32_t* idx_b,
+                                     uint64_t* seg, uint64_t* tile_agg, void* sort_tmp, size_t sort_bytes) {
+  if (!ops.n) return;
+  const uint32_t n = ops.n;
+  if (op == SMX_OP_SETZERO) { /* set: the value just written */
+    SMX_LAUNCH(k_fill_out, grid_for(n), SMX_BLOCK, st, ops, out);
+    return;
+  }
+  SMX_LAUNCH(k_find_addr, grid_for(n), SMX_BLOCK, st, v, ops, (ull*)addrs_a, idx_a);
+#ifdef SMX_HOSTSIM
+  (void)sort_tmp; (void)sort_bytes;
+  {
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return addrs_a[a] < addrs_a[b]; });
+    for (uint32_t p = 0; p < n; p++) { addrs_b[p] = addrs_a[order[p]]; idx_b[p] = order[p]; }
+  }
+#else
+  /* LSD radix sort: stable, so ops of one cell stay in input order (device addresses fit in 48 bits) */
+  cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, (const ull*)addrs_a, (ull*)addrs_b, (const uint32_t*)idx_a,
+                                  idx_b, (int)n, 0, 48, (cudaStream_t)st);
+#endif
+  const int negate = (op == SMX_OP_DECR) ? 1 : 0;
+  const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  SMX_LAUNCH(k_out_gather, grid_for(n), SMX_BLOCK, st, ops, negate, (const ull*)addrs_b, (const uint32_t*)idx_b, (ull*)seg);
+  SMX_LAUNCH(k_seg_tile, tiles, SMX_BLOCK, st, (const ull*)seg, n, (ull*)tile_agg);
+  SMX_LAUNCH(k_seg_tiles, 1, 1, st, (ull*)tile_agg, tiles);
+  SMX_LAUNCH(k_seg_apply, tiles, SMX_BLOCK, st, (ull*)seg, n, (const ull*)tile_agg);
+  SMX_LAUNCH(k_out_write, grid_for(n), SMX_BLOCK, st, ops, negate, (const ull*)addrs_b, (const uint32_t*)idx_b,
+             (const ull*)seg, out);
 }
 
 extern "C" void smx_launch_get(smx_stream_t st, smx_view_t v, const uint32_t* xs, const uint32_t* ys,

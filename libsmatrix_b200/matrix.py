@@ -140,6 +140,30 @@ class SparseMatrix:
     def set_batch(self, xs, ys, vals=None):
         self._write(self._lib.smatrix_set_batch, xs, ys, vals)
 
+    def _write_out(self, fn, xs, ys, vals):
+        """-> out[i] = what the single-op call i would have returned (input order)."""
+        keep: list = []
+        px, py, pv = self._arg(xs, keep), self._arg(ys, keep), self._arg(vals, keep)
+        if _is_torch(keep[0]):
+            import torch
+            n = keep[0].numel()
+            out = torch.empty(n, dtype=torch.int32, device=keep[0].device)
+            fn(self._handle(), px, py, pv, n, out.data_ptr())
+            return out
+        n = len(keep[0])
+        out = np.empty(n, dtype=np.uint32)
+        fn(self._handle(), px, py, pv, n, out.ctypes.data)
+        return out
+
+    def incr_batch_out(self, xs, ys, vals=None):
+        return self._write_out(self._lib.smatrix_incr_batch_out, xs, ys, vals)
+
+    def decr_batch_out(self, xs, ys, vals=None):
+        return self._write_out(self._lib.smatrix_decr_batch_out, xs, ys, vals)
+
+    def set_batch_out(self, xs, ys, vals=None):
+        return self._write_out(self._lib.smatrix_set_batch_out, xs, ys, vals)
+
     def get_batch(self, xs, ys, out=None):
         keep: list = []
         px, py = self._arg(xs, keep), self._arg(ys, keep)

@@ -401,3 +401,27 @@ def scenario_cf_read_side(make, n_baskets: int = 2000, n_items: int = 300):
             want[int(b)] = 0.0 if (den == 0.0 or np.float64(cc) > den) else float(np.float64(cc) / den)
         assert got == want, f"item {a}"
     m.close(); ref.close()
+
+
+def scenario_batch_out(make, n: int = 40000):
+    """SURVEY.md 8f N1 — per-op return values of batches = the return values of the reference's
+    single-op calls applied in input order (src/smatrix.c:230,241,252), with heavy key duplication,
+    column 0, wrap-around and growth inside the batch."""
+    rng = np.random.default_rng(59)
+    m, ref = make(), checker()
+    for op in ("incr", "decr", "set", "incr"):
+        xs = (rng.zipf(1.4, n) % 60).astype(U32)
+        ys = (rng.zipf(1.4, n) % 45).astype(U32)                 # includes column 0
+        vs = rng.integers(1, 2**32, n, dtype=np.uint64).astype(U32)
+        if op != "set":                                           # keep column 0 inside the safe domain
+            vs = np.where(ys == 0, (vs % 1000) + 1, vs).astype(U32)
+        if op == "decr":
+            ys = np.where(ys == 0, U32(1), ys).astype(U32)
+        got = np.asarray(getattr(m, op + "_batch_out")(xs, ys, vs))
+        want = ref.apply(op, xs, ys, vs, want_out=True)
+        assert (got == want).all(), f"{op}: {int((got != want).sum())} return values differ"
+    got = np.asarray(m.incr_batch_out(xs, ys, None))             # vals == NULL: every value is 1
+    want = ref.apply("incr", xs, ys, np.ones(n, U32), want_out=True)
+    assert (got == want).all()
+    compare(m, ref, np.arange(62), xs, ys)
+    m.close(); ref.close()

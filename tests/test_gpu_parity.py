@@ -99,6 +99,24 @@ def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=20000, max_len=200000)
 
 
+def test_batch_out(make):
+    ps.scenario_batch_out(make, n=400000)
+
+
+def test_batch_out_device_pointers():
+    import torch
+    m, ref = SparseMatrix(), ps.checker()
+    rng = np.random.default_rng(61)
+    n = 500000
+    xs = rng.integers(0, 2000, n).astype(U32); ys = rng.integers(1, 50, n).astype(U32)
+    vs = rng.integers(0, 2**32, n, dtype=np.uint64).astype(U32)
+    dev = torch.device("cuda", m.device)
+    t = lambda a: torch.from_numpy(a.view(np.int32)).to(dev)
+    got = m.incr_batch_out(t(xs), t(ys), t(vs)).cpu().numpy().view(U32)
+    assert (got == ref.apply("incr", xs, ys, vs, want_out=True)).all()
+    m.close(); ref.close()
+
+
 def test_cf_read_side(make_default):
     ps.scenario_cf_read_side(make_default, n_baskets=20000, n_items=2000)
 

@@ -93,6 +93,10 @@ def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=300, max_len=3000)
 
 
+def test_batch_out(make):
+    ps.scenario_batch_out(make, n=6000)
+
+
 def test_cf_read_side(make):
     ps.scenario_cf_read_side(make, n_baskets=300, n_items=80)
 
