@@ -182,3 +182,32 @@ double drv_bench_c2_get(void* get, void* h, int threads, uint64_t seed_get, uint
   p.ycols = ycols;
   return run_threads(p, threads);
 }
+
+/* ---------------------------------------------------------------- full-scale parity digests */
+/* Per row: {rowlen, number of pairs, sum of columns, sum of values, sum of column*value} (uint64,
+ * wrapping), computed through the library's own rowlen / getrow calls.  Order independent, so it
+ * can be compared with digests computed from another implementation's getrow output. */
+void drv_row_digests(fn_x rowlen, fn_row getrow, void* h, const uint32_t* xs, size_t n, uint64_t* out5) {
+  size_t cap = 1024;
+  uint32_t* buf = malloc(cap * 8);
+  for (size_t i = 0; i < n; i++) {
+    uint64_t len = rowlen(h, xs[i]);
+    if (len + 2 > cap) {
+      cap = (len + 2) * 2;
+      buf = realloc(buf, cap * 8);
+    }
+    uint32_t got = getrow(h, xs[i], buf, (size_t)(len + 2) * 8);
+    uint64_t sc = 0, sv = 0, sp = 0;
+    for (uint32_t k = 0; k < got; k++) {
+      sc += buf[2 * k];
+      sv += buf[2 * k + 1];
+      sp += (uint64_t)buf[2 * k] * (uint64_t)buf[2 * k + 1];
+    }
+    out5[5 * i + 0] = len;
+    out5[5 * i + 1] = got;
+    out5[5 * i + 2] = sc;
+    out5[5 * i + 3] = sv;
+    out5[5 * i + 4] = sp;
+  }
+  free(buf);
+}
