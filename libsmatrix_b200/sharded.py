@@ -66,6 +66,14 @@ class _PeerBuffers:
                     raise RuntimeError("cudaIpcOpenMemHandle failed")
                 opened[k] = int(p)
             self.peer.append(opened)
+        if os.environ.get("SMX_ROUTE_WARM", "1") != "0":
+            # first stores through a freshly opened IPC mapping are slow (the mapping is completed
+            # lazily): push every peer array once now, so the first routed batch runs at NVLink speed
+            for r in range(sm.world):
+                if r != sm.rank:
+                    for k, p in self.peer[r].items():
+                        lib.smatrix_b200_memcpy(h, p, self.local[k], self.cap * 4)
+            dist.barrier(group=sm.group)
 
     def next_gen(self) -> int:
         self.gen = (self.gen + 1) % self.GENS
@@ -234,8 +242,8 @@ class ShardedSparseMatrix:
 
     # overlapped pieces (helper thread routes piece j+1 while piece j updates): measured slower than one
     # fused route per batch on B200 (7.4 vs 6.7 ms per 2^26 ops at N=2), so off unless asked for
-    PIPELINE_MIN = 1 << 62
-    PIPELINE_PIECE = 1 << 24
+    PIPELINE_MIN = int(os.environ.get("SMX_PIPELINE_MIN", 1 << 62))
+    PIPELINE_PIECE = int(os.environ.get("SMX_PIPELINE_PIECE", 1 << 25))
 
     def _nmax(self, n: int) -> int:
         t = torch.tensor([n], dtype=torch.int64, device=self.dev)
