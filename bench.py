@@ -58,6 +58,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-probes", action="store_true")
+    p.add_argument("--phase-series", action="store_true", help="diagnostic: host phase split of every step on stderr")
     p.add_argument("--cpu-sample", type=int, default=16_000_000, help="ops in the CPU baseline sample")
     p.add_argument("--ref-step", type=int, default=2_000_000, help="ops per step of the reference arm")
     return p.parse_args()
@@ -273,6 +274,8 @@ def main_ours(a):
     wall0 = time.time()
     m.timer_start()
     step_ms, kern_ms, prev_k = [], [], 0
+    PHASES = ("partition", "upsert", "grow_plan", "slab", "migrate", "dir")
+    prev_ph = [0.0] * len(PHASES) + [m.stat("rounds"), m.stat("launches")]
     for j in range(K):
         t_s = time.perf_counter()
         m.incr_batch(xs[j], ys[j], None)        # synchronous: returns when the device is done
@@ -280,6 +283,11 @@ def main_ours(a):
         k_now = m.stat("kernel_ns")
         kern_ms.append(round((k_now - prev_k) / 1e6, 2))
         prev_k = k_now
+        if a.phase_series and rank == 0:
+            now = [m.stat("ns_" + k) / 1e6 for k in PHASES] + [m.stat("rounds"), m.stat("launches")]
+            print(f"step {j}: {step_ms[-1]} ms; " + ", ".join(f"{k} {now[i] - prev_ph[i]:.2f}" for i, k in enumerate(PHASES))
+                + f"; rounds {now[-2] - prev_ph[-2]}, launches {now[-1] - prev_ph[-1]}", file=sys.stderr)
+            prev_ph = now
     ms_build = m.timer_stop_ms()
     barrier()
     wall1 = time.time()

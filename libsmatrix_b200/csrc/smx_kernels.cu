@@ -1101,10 +1101,15 @@ k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, uint32_t dir_m
 /* Tiled partition: a block stages a tile of ops in shared memory sorted by part, reserves one
  * contiguous range per part with a single global atomic, and writes whole runs — so every
  * (tile, part) run reaches L2 as full sectors no matter how many parts there are.  Order inside a
- * part is not the input order (osrc carries the original index). */
+ * part is not the input order (osrc carries the original index).
+ * The kernel is latency-bound, not bandwidth-bound, so the tile loop is software-pipelined: the next
+ * tile's x / y loads are issued before this tile is written out, the cursor atomics fly while the
+ * tile is being staged, and every warp keeps its own copy of the (tiny) prefix table instead of
+ * waiting at a barrier for one warp to build it. */
 #define PART_ITEMS 8
 #define PART_TILE (SMX_BLOCK * PART_ITEMS)
-template <bool HAS_V, bool HAS_POS> /* shared memory only for what is used: 24 - 40 KB per block */
+#define PART_PER_LANE (SMX_MAX_PARTS / SMX_WARP)
+template <bool HAS_V, bool HAS_POS> /* shared memory only for what is used: 34 - 42 KB per block */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
                     uint32_t world, uint32_t dir_mask, uint32_t shift, ull* cursors, uint32_t* oxs,
@@ -1112,49 +1117,104 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
                     uint32_t* opos, const ull* dst_tab, uint32_t src_bias) {
   __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_i[PART_TILE];
   __shared__ uint32_t s_v[HAS_V ? PART_TILE : 1], s_p[HAS_POS ? PART_TILE : 1];
+  __shared__ unsigned char s_part[PART_TILE];
+  __shared__ uint32_t hist[2][SMX_MAX_PARTS];
+  __shared__ unsigned short off[SMX_BLOCK / SMX_WARP][SMX_MAX_PARTS]; /* < PART_TILE */
+  __shared__ ull gdelta[SMX_MAX_PARTS]; /* global index of a run's first op minus its place in the tile */
   if (!HAS_V) vs = nullptr;
-  if (!HAS_POS) opos = nullptr;
-  __shared__ uint32_t hist[SMX_MAX_PARTS], off[SMX_MAX_PARTS];
-  __shared__ ull gbase[SMX_MAX_PARTS];
+  const bool want_pos = opos && !src_in; /* s_i = input position when src_in == NULL */
+  const uint32_t lane = lane_id(), wib = threadIdx.x / SMX_WARP;
+  unsigned short* myoff = off[wib];
   const uint32_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (uint32_t k = threadIdx.x; k < 2u * SMX_MAX_PARTS; k += blockDim.x) (&hist[0][0])[k] = 0u;
+  uint32_t x[PART_ITEMS], y[PART_ITEMS];
+  if (blockIdx.x < n_tiles) {
+    const uint32_t base = blockIdx.x * PART_TILE;
+#pragma unroll
+    for (int k = 0; k < PART_ITEMS; ++k) {
+      const uint32_t j = base + k * blockDim.x + threadIdx.x;
+      x[k] = j < n ? xs[j] : 0u;
+      y[k] = (ys && j < n) ? ys[j] : 0u;
+    }
+  }
+  __syncthreads();
+  uint32_t buf = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1u) {
     const uint32_t base = tile * PART_TILE;
     const uint32_t cnt = (n - base < PART_TILE) ? n - base : PART_TILE;
-    for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
-    __syncthreads();
-    uint32_t x[PART_ITEMS], rank[PART_ITEMS];
+    uint32_t* h = hist[buf];
+    uint32_t pr[PART_ITEMS]; /* part << 16 | rank inside the tile's run */
 #pragma unroll
     for (int k = 0; k < PART_ITEMS; ++k) {
       const uint32_t j = k * blockDim.x + threadIdx.x;
       if (j < cnt) {
-        x[k] = xs[base + j];
-        rank[k] = atomicAdd(&hist[part_of(x[k], world, dir_mask, shift)], 1u);
+        const uint32_t p = part_of(x[k], world, dir_mask, shift);
+        pr[k] = (p << 16) | atomicAdd(&h[p], 1u);
       }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) { /* world <= 256: a serial prefix is cheap next to the tile */
-      uint32_t run = 0;
-      for (uint32_t k = 0; k < world; ++k) { off[k] = run; run += hist[k]; }
+    __syncthreads(); /* (1) the tile's histogram is complete */
+    /* reserve the runs: one global atomic per non-empty part, not waited for until the tile is staged */
+#ifndef SMX_HOSTSIM
+    ull gb = 0ull;
+    if (threadIdx.x < world && h[threadIdx.x]) gb = atomicAdd(&cursors[threadIdx.x], (ull)h[threadIdx.x]);
+#endif
+    { /* every warp: exclusive prefix of the histogram into its own table */
+      uint32_t c[PART_PER_LANE], sum = 0u;
+#pragma unroll
+      for (int q = 0; q < PART_PER_LANE; ++q) {
+        c[q] = h[lane * PART_PER_LANE + q];
+        sum += c[q];
+      }
+      uint32_t incl = sum;
+      for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(SMX_FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int q = 0; q < PART_PER_LANE; ++q) {
+        myoff[lane * PART_PER_LANE + q] = (unsigned short)run;
+        run += c[q];
+      }
+      __syncwarp();
     }
-    for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
-      gbase[k] = hist[k] ? atomicAdd(&cursors[k], (ull)hist[k]) : 0ull;
-    __syncthreads();
 #pragma unroll
     for (int k = 0; k < PART_ITEMS; ++k) {
       const uint32_t j = k * blockDim.x + threadIdx.x;
       if (j < cnt) {
-        const uint32_t at = off[part_of(x[k], world, dir_mask, shift)] + rank[k];
+        const uint32_t p = pr[k] >> 16;
+        const uint32_t at = myoff[p] + (pr[k] & 0xFFFFu);
         s_x[at] = x[k];
-        if (ys) s_y[at] = ys[base + j];
+        s_y[at] = y[k];
+        s_part[at] = (unsigned char)p;
         if (vs) s_v[at] = vs[base + j];
         s_i[at] = src_in ? src_in[base + j] : base + j; /* carry the caller's order index */
       }
     }
-    __syncthreads();
+    { /* next tile's loads fly while this one is written out */
+      const uint32_t next = tile + gridDim.x;
+      if (next < n_tiles) {
+        const uint32_t nb = next * PART_TILE;
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+          const uint32_t j = nb + k * blockDim.x + threadIdx.x;
+          x[k] = j < n ? xs[j] : 0u;
+          y[k] = (ys && j < n) ? ys[j] : 0u;
+        }
+      }
+    }
+#ifdef SMX_HOSTSIM
+    for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
+      gdelta[k] = (h[k] ? atomicAdd(&cursors[k], (ull)h[k]) : 0ull) - myoff[k];
+#else
+    if (threadIdx.x < world) gdelta[threadIdx.x] = gb - myoff[threadIdx.x];
+#endif
+    for (uint32_t k = threadIdx.x; k < SMX_MAX_PARTS; k += blockDim.x) hist[buf ^ 1u][k] = 0u; /* for the next tile */
+    __syncthreads(); /* (2) the tile is staged and its runs are reserved */
     for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
       const uint32_t xx = s_x[j];
-      const uint32_t p = part_of(xx, world, dir_mask, shift);
-      ull at = gbase[p] + (j - off[p]);
+      const uint32_t p = s_part[j];
+      ull at = gdelta[p] + j;
       if (dst_tab) {
         /* fused with the exchange: part p's run goes straight into owner p's inbox — a peer
          * mapping over NVLink (or local memory for p == this rank).  dst_tab = [x | y | v | src |
@@ -1173,12 +1233,16 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
       /* inverse permutation, for reads: input position -> routed position (staged in shared
        * memory so that it is written coalesced).  A tile's ops land in one run per part, so a
        * later gather through opos reads long contiguous runs. */
-      if (opos && !src_in) s_p[s_i[j] - base] = (uint32_t)at; /* s_i = input position when src_in == NULL */
+      if (want_pos) {
+        if (HAS_POS) s_p[s_i[j] - base] = (uint32_t)at;
+        else opos[s_i[j]] = (uint32_t)at; /* values AND positions: no caller on a hot path, no staging */
+      }
     }
-    __syncthreads();
-    if (opos && !src_in)
+    if (HAS_POS && want_pos) {
+      __syncthreads();
       for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) opos[base + j] = s_p[j];
-    __syncthreads();
+    }
+    __syncthreads(); /* (3) before the next tile overwrites the staging arrays */
   }
 }
 
@@ -1435,8 +1499,7 @@ extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs
     SMX_LAUNCH(k, grid, SMX_BLOCK, st, xs, ys, vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, \
                osrc, src_in, opos, (const ull*)dst_tab, src_bias);                                   \
   }
-  if (vs && pos) SMX_SCATTER(true, true)
-  else if (vs) SMX_SCATTER(true, false)
+  if (vs) SMX_SCATTER(true, false)
   else if (pos) SMX_SCATTER(false, true)
   else SMX_SCATTER(false, false)
 #undef SMX_SCATTER
