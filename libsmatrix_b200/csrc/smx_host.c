@@ -423,7 +423,7 @@ static void maybe_shrink_dir(smatrix_t* s) {
 /* Reorder a chunk so that ops on rows of the same directory slice are adjacent: the slice of the
  * directory (a few MB) then stays in L2 while its ops are applied, and a row header costs one
  * DRAM read + one write-back per chunk instead of one per op.  idx keeps the input order. */
-static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
+static void partition_chunk(smatrix_t* s, smx_ops_t* ops, int* has_col0) {
   const uint32_t n = ops->n;
   uint32_t dir_log = 0;
   while ((1ull << dir_log) < s->dir_cap) dir_log++;
@@ -439,15 +439,16 @@ static void partition_chunk(smatrix_t* s, smx_ops_t* ops) {
     s->part_cap = s->list_cap > n ? s->list_cap : n;
     for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)scratch_alloc(s, (size_t)s->part_cap * 4);
   }
-  ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
+  ensure_tmp(s, 0, 2 * (SMX_MAX_PARTS_H + 1) * 8);
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
-  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
-  unsigned long long h[SMX_MAX_PARTS_H], cur[SMX_MAX_PARTS_H];
+  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H + 1;
+  unsigned long long h[SMX_MAX_PARTS_H + 1], cur[SMX_MAX_PARTS_H];
   double t0 = now_ns();
-  CK(cudaMemsetAsync(d_counts, 0, parts * 8, s->stream));
-  smx_launch_partition_count(s->stream, ops->xs, n, parts, (uint32_t)(s->dir_cap - 1), shift, d_counts);
-  CK(cudaMemcpyAsync(h, d_counts, parts * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemsetAsync(d_counts, 0, (parts + 1) * 8, s->stream));
+  smx_launch_partition_count(s->stream, ops->xs, ops->ys, n, parts, (uint32_t)(s->dir_cap - 1), shift, d_counts);
+  CK(cudaMemcpyAsync(h, d_counts, (parts + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  *has_col0 = h[parts] != 0; /* the count pass saw every y: no column-0 op, no column-0 pass */
   unsigned long long at = 0;
   for (uint32_t p = 0; p < parts; p++) { cur[p] = at; at += h[p]; }
   CK(cudaMemcpyAsync(d_cursors, cur, parts * 8, cudaMemcpyHostToDevice, s->stream));
@@ -478,10 +479,11 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   smx_ops_t ops;
   ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = d_ords; ops.v_const = 1u; ops.n = n;
 
-  if (n >= s->part_min) partition_chunk(s, &ops);
+  int has_col0 = 1;
+  if (n >= s->part_min) partition_chunk(s, &ops, &has_col0);
   const int op = (api_op == 2) ? SMX_OP_SETZERO : api_op;
   CK(cudaMemsetAsync(&s->d_ctl->n_late, 0, 2 * sizeof(uint32_t), s->stream));
-  run_pass(s, ops, op, SMX_PASS_COL0, NULL, n);
+  if (has_col0) run_pass(s, ops, op, SMX_PASS_COL0, NULL, n);
   run_pass(s, ops, op, SMX_PASS_EARLY, NULL, n);
   if (s->h_ctl->n_t0) { /* column 0 of these rows turns non-zero now: sync their rowlen state (z = 0 so far) */
     smx_launch_sync_rowlen(s->stream, view_of(s), s->lists.t0rows, s->h_ctl->n_t0);
@@ -1525,7 +1527,7 @@ void smatrix_b200_partition_count(smatrix_t* s, const uint32_t* d_xs, size_t n, 
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
   unsigned long long h[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
-  smx_launch_partition_count(s->stream, d_xs, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
+  smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
   CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   for (uint32_t r = 0; r < world; r++) h_counts[r] = h[r];
@@ -1590,7 +1592,7 @@ void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t*
   unsigned long long* d_cursors = d_counts + 64;
   unsigned long long h[64], cur[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
-  smx_launch_partition_count(s->stream, d_xs, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
+  smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
   CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   unsigned long long at = 0;

@@ -158,9 +158,9 @@ void smx_launch_probe_atomic(smx_stream_t stream, uint32_t* buf, uint64_t n_word
 /* part = owner rank when shift == SMX_PART_OWNER, else directory slice (mix_row(x) & dir_mask) >> shift */
 #define SMX_PART_OWNER 0xFFFFFFFFu
 #define SMX_MAX_PARTS_H 256u
-void smx_launch_partition_count(smx_stream_t stream, const uint32_t* xs, uint32_t n, uint32_t world,
-                                uint32_t dir_mask, uint32_t shift,
-                                unsigned long long* counts /* [world], zeroed */);
+void smx_launch_partition_count(smx_stream_t stream, const uint32_t* xs, const uint32_t* ys /* or NULL */,
+                                uint32_t n, uint32_t world, uint32_t dir_mask, uint32_t shift,
+                                unsigned long long* counts /* [world + 1], zeroed; [world] = ops with y == 0 */);
 void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const uint32_t* ys,
                                   const uint32_t* vs, uint32_t n, uint32_t world,
                                   uint32_t dir_mask, uint32_t shift,

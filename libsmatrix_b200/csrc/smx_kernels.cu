@@ -1086,16 +1086,22 @@ k_probe_atomic(uint32_t* buf, ull n_words, ull accesses) {
 __device__ __forceinline__ uint32_t part_of(uint32_t x, uint32_t world, uint32_t dir_mask, uint32_t shift) {
   return shift == 0xFFFFFFFFu ? smx_mix_owner(x) % world : (smx_mix_row(x) & dir_mask) >> shift;
 }
+/* counts[part] += ops of that part; with ys, counts[world] += ops on column 0 (a chunk without any
+ * lets the host skip the column-0 pass, which would only scan the chunk) */
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_partition_count(const uint32_t* xs, uint32_t n, uint32_t world, uint32_t dir_mask, uint32_t shift,
-                  ull* counts) {
-  __shared__ uint32_t hist[SMX_MAX_PARTS];
-  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
+k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t world, uint32_t dir_mask,
+                  uint32_t shift, ull* counts) {
+  __shared__ uint32_t hist[SMX_MAX_PARTS + 1];
+  for (uint32_t k = threadIdx.x; k <= world; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  uint32_t zeros = 0u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     atomicAdd(&hist[part_of(xs[i], world, dir_mask, shift)], 1u);
+    if (ys && ys[i] == 0u) ++zeros;
+  }
+  if (zeros) atomicAdd(&hist[world], zeros);
   __syncthreads();
-  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
+  for (uint32_t k = threadIdx.x; k <= world; k += blockDim.x)
     if (hist[k]) atomicAdd(&counts[k], (ull)hist[k]);
 }
 /* Tiled partition: a block stages a tile of ops in shared memory sorted by part, reserves one
@@ -1477,11 +1483,11 @@ extern "C" void smx_launch_probe_atomic(smx_stream_t st, uint32_t* buf, uint64_t
   SMX_LAUNCH(k_probe_atomic, grid_for(accesses), SMX_BLOCK, st, buf, (ull)n_words, (ull)accesses);
 }
 
-extern "C" void smx_launch_partition_count(smx_stream_t st, const uint32_t* xs, uint32_t n,
-                                           uint32_t world, uint32_t dir_mask, uint32_t shift,
-                                           unsigned long long* counts) {
+extern "C" void smx_launch_partition_count(smx_stream_t st, const uint32_t* xs, const uint32_t* ys,
+                                           uint32_t n, uint32_t world, uint32_t dir_mask,
+                                           uint32_t shift, unsigned long long* counts) {
   if (!n) return;
-  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, n, world, dir_mask, shift, counts);
+  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, ys, n, world, dir_mask, shift, counts);
 }
 extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs, const uint32_t* ys,
                                              const uint32_t* vs, uint32_t n, uint32_t world,
