@@ -52,6 +52,7 @@ struct smatrix_s {
   int device;
   cudaStream_t stream;
   cudaStream_t copy_stream;
+  cudaStream_t read_stream[2]; /* with stream + copy_stream: four pieces of a host-pointer read in flight */
   pthread_mutex_t mu;
 
   smx_row_t* dir;
@@ -713,22 +714,31 @@ void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, siz
       timed_collect(s);
     }
   } else {
-    uint32_t step = n < s->stage_max ? (uint32_t)n : s->stage_max;
-    if (step > (1u << 23) && n > step) step = 1u << 23; /* enough pieces to overlap */
-    ensure_stage(s, step);
-    int b = 0;
-    for (size_t off = 0; off < n; off += step, b ^= 1) {
+    /* four pieces in flight: the two staging buffers are used as halves, piece k owns slot k & 3 and
+     * runs entirely on that slot's stream (upload, look up, download in stream order).  The upload
+     * of a piece then overlaps the look-ups and downloads of the three before it (PCIe is full
+     * duplex), so the call is bound by the upload alone; small pieces keep the un-overlapped first
+     * upload and last download short. */
+    uint32_t step = s->stage_max / 2 < 1024 ? 1024 : s->stage_max / 2;
+    if (step > (1u << 22)) step = 1u << 22;
+    if (n < step) step = (uint32_t)n;
+    ensure_stage(s, 2 * step);
+    cudaStream_t sts[4] = {s->stream, s->copy_stream, s->read_stream[0], s->read_stream[1]};
+    uint32_t k = 0;
+    for (size_t off = 0; off < n; off += step, k++) {
       const uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
-      /* piece k runs entirely on stream (k & 1) with staging buffer (k & 1): upload, look up,
-       * download in stream order, so the upload of one piece overlaps the look-up and the
-       * download of the previous one (PCIe is full duplex) */
-      cudaStream_t st = b ? s->copy_stream : s->stream;
-      CK(cudaMemcpyAsync(s->stage[b][0], xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(s->stage[b][1], ys + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
-      smx_launch_get(st, view_of(s), s->stage[b][0], s->stage[b][1], len, s->stage[b][2]);
+      const uint32_t q = k & 3u;
+      cudaStream_t st = sts[q];
+      uint32_t* const* buf = s->stage[q >> 1];
+      const size_t half = (size_t)(q & 1u) * step;
+      CK(cudaMemcpyAsync(buf[0] + half, xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(buf[1] + half, ys + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
+      smx_launch_get(st, view_of(s), buf[0] + half, buf[1] + half, len, buf[2] + half);
       s->n_launches++;
-      CK(cudaMemcpyAsync(out + off, s->stage[b][2], (size_t)len * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(out + off, buf[2] + half, (size_t)len * 4, cudaMemcpyDeviceToHost, st));
     }
+    CK(cudaStreamSynchronize(s->read_stream[0]));
+    CK(cudaStreamSynchronize(s->read_stream[1]));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->copy_stream));
   }
@@ -1237,6 +1247,8 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   }
   CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->read_stream[0], cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->read_stream[1], cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&s->stage_ready[0], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s->stage_ready[1], cudaEventDisableTiming));
   CK(cudaEventCreate(&s->ev0));
@@ -1327,6 +1339,7 @@ void smatrix_close(smatrix_t* s) {
   cudaEventDestroy(s->t_start); cudaEventDestroy(s->t_stop);
   cudaStreamDestroy(s->stream);
   cudaStreamDestroy(s->copy_stream);
+  cudaStreamDestroy(s->read_stream[0]); cudaStreamDestroy(s->read_stream[1]);
   free(s->fname);
   leave(s);
   pthread_mutex_destroy(&s->mu);
