@@ -467,14 +467,15 @@ def run_e2e(a, torch, dev, local, make_matrix, B, K, prefill, n_batches):
         m.gen_c2_ops(SEED_BUILD, k * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
         m.incr_batch(dx, dy, None)
     rounds0 = m.stat("rounds")
-    secs = 0.0
+    secs, series = 0.0, []
     for j in range(K):
         m.gen_c2_ops(SEED_BUILD, (prefill + j) * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
         hx.copy_(dx); hy.copy_(dy)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         m.incr_batch(hx, hy, None)               # returns after the device finished (synchronous API)
-        secs += time.perf_counter() - t0
+        series.append(round((time.perf_counter() - t0) * 1e3, 2))
+        secs += series[-1] * 1e-3
     rounds = m.stat("rounds") - rounds0
     incr = K * B / secs / 1e6
     # gets through host buffers: queries up, values down
@@ -494,7 +495,7 @@ def run_e2e(a, torch, dev, local, make_matrix, B, K, prefill, n_batches):
         done += cnt
     m.close()
     return {"value": incr, "unit": "Mops/s", "h2d_bytes_per_step": 8 * B,
-            "d2h_bytes_per_step": 1072 * max(1, rounds // max(K, 1)), "ms_per_step": secs / K * 1e3,
+            "d2h_bytes_per_step": 1072 * max(1, rounds // max(K, 1)), "ms_per_step": secs / K * 1e3, "step_ms": series,
             "get_mops": G / gsecs / 1e6, "get_h2d_bytes_per_step": 8 * B, "get_d2h_bytes_per_step": 4 * B,
             "note": "pinned host arrays through smatrix_incr_batch / smatrix_get_batch; wall clock around the call"}
 

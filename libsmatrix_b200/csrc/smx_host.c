@@ -282,14 +282,15 @@ static void ensure_tmp(smatrix_t* s, size_t bytes32, size_t bytes64) {
 static void ensure_stage(smatrix_t* s, uint32_t n) {
   if (n <= s->stage_cap) return;
   uint32_t cap = n < 4096 ? 4096 : n;
+  if (s->arena_bytes && cap < s->stage_max) cap = s->stage_max; /* from the arena: once, at full size */
   if (s->stage_cap) {
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaStreamSynchronize(s->copy_stream));
     for (int b = 0; b < 2; b++)
-      for (int a = 0; a < 3; a++) cudaFree(s->stage[b][a]);
+      for (int a = 0; a < 3; a++) scratch_free(s, s->stage[b][a]);
   }
   for (int b = 0; b < 2; b++)
-    for (int a = 0; a < 3; a++) s->stage[b][a] = (uint32_t*)dmalloc(s, (size_t)cap * 4);
+    for (int a = 0; a < 3; a++) s->stage[b][a] = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
   s->stage_cap = cap;
 }
 
@@ -1325,7 +1326,7 @@ void smatrix_close(smatrix_t* s) {
     for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
   if (s->stage_cap)
     for (int b = 0; b < 2; b++)
-      for (int a = 0; a < 3; a++) cudaFree(s->stage[b][a]);
+      for (int a = 0; a < 3; a++) scratch_free(s, s->stage[b][a]);
   if (s->d_tmp) cudaFree(s->d_tmp);
   if (s->d_tmp64) cudaFree(s->d_tmp64);
   if (s->d_rowbuf) cudaFree(s->d_rowbuf);
