@@ -12,7 +12,7 @@ tail -2 gpurun_out/r1_bench.err
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r1_launches.csv \
   python bench.py --no-e2e --no-cpu --no-probes > gpurun_out/r1_ncu_launches.log 2>&1; echo "ncu list exit $?"
 timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none \
-  -k regex:'k_upsert|k_get' -s 150 -c 40 --csv --log-file gpurun_out/r1_traffic_full.csv \
+  -k regex:'k_upsert|k_get' -s 60 -c 32 --csv --log-file gpurun_out/r1_traffic_full.csv \
   python bench.py --no-e2e --no-cpu --no-probes --gets 134217728 > gpurun_out/r1_ncu_traffic.log 2>&1; echo "ncu traffic exit $?"
 ARGS="--steps 3 --warmup 1 --batch 16777216 --total-ops 503316480 --rows 3250000 --gets 33554432 --no-e2e --no-cpu --no-probes --arena-gib 16"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_upsert' -s 64 -c 6 -o gpurun_out/r1_prof_quarter_upsert python bench.py $ARGS > gpurun_out/r1_ncu_full.log 2>&1; echo "ncu full upsert exit $?"
