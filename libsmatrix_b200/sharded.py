@@ -321,16 +321,18 @@ class ShardedSparseMatrix:
         into the requester's answer buffer (peer memory), which the requester then gathers into
         input order."""
         import time as _t
-        dbg = os.environ.get("SMX_ROUTE_DEBUG") == "1"
+        dbg = os.environ.get("SMX_ROUTE_DEBUG") in ("1", "2")
         t0 = _t.perf_counter()
         r = self._route_p2p(xs, ys, None, want_pos=True)
         if r is None:
             return None
         cnt, g, rx, ry, _, _, opos = r
         t1 = _t.perf_counter()
-        pb, me, off = self._peers, self.rank, 0
-        for s_ in range(self.world):              # one launch per sender's run
-            c = int(cnt[s_][me])
+        pb, me = self._peers, self.rank
+        starts = np.concatenate([[0], np.cumsum(cnt[:, me])])   # sender s's run inside my inbox
+        for i in range(self.world):               # one launch per sender's run, staggered: at any moment
+            s_ = (me + i) % self.world            # the ranks answer DIFFERENT requesters (a shift
+            c, off = int(cnt[s_][me]), int(starts[s_])   # permutation), not all the same one
             if c:
                 dst = DevPtr(pb.peer[s_][(g, "b")] + 4 * int(cnt[s_][:me].sum()), c)
                 qx = DevPtr(rx.ptr + 4 * off, c)
@@ -338,7 +340,6 @@ class ShardedSparseMatrix:
                     fn(qx, DevPtr(ry.ptr + 4 * off, c), out=dst)
                 else:
                     fn(qx, out=dst)
-                off += c
         t2 = _t.perf_counter()
         dist.barrier(group=self.group)             # all answers have landed
         t3 = _t.perf_counter()
@@ -348,8 +349,8 @@ class ShardedSparseMatrix:
         if n:
             self._lib.smatrix_b200_gather(self.router._handle(), out.data_ptr(), pb.local[(g, "b")],
                                           opos.ptr, n)
-        if dbg and self.rank == 0:
-            print(f"[route] read n={n}: route {1e3*(t1-t0):.2f} ms, owners' kernels {1e3*(t2-t1):.2f}, "
+        if dbg and (self.rank == 0 or os.environ.get("SMX_ROUTE_DEBUG") == "2"):
+            print(f"[route] rank {self.rank} read n={n}: route {1e3*(t1-t0):.2f} ms, owners' kernels {1e3*(t2-t1):.2f}, "
                   f"barrier {1e3*(t3-t2):.2f}, gather {1e3*(_t.perf_counter()-t3):.2f}", file=__import__("sys").stderr, flush=True)
         return out
 
