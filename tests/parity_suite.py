@@ -355,6 +355,36 @@ def scenario_benchmark_pattern(make, threads: int = 8, rounds: int = 16):
     m.close(); ref.close()
 
 
+def splitmix64(z):
+    """SURVEY.md 8(d) RNG: r = splitmix64(seed + i), vectorised (uint64 wrap-around intended)."""
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def scenario_uniform_grid(make, n_ops: int = 4_000_000, side: int = 10000, pieces: int = 3):
+    """BASELINE config 1 as BASELINE.json words it (SURVEY.md 8d "C1b"): uniform-random incr over a
+    side x side grid, x = (r >> 32) % side, y = r % side, seed 1.  Row 0 and column 0 are ordinary
+    members of the grid here, so ~n/side ops land on column 0 of random rows at random moments:
+    rowlen depends on when (Q1) and must still match the sequential reference.  Exhaustive compare:
+    every distinct key of the stream, every row."""
+    with np.errstate(over="ignore"):
+        r = splitmix64(np.uint64(1) + np.arange(n_ops, dtype=np.uint64))
+    xs = ((r >> np.uint64(32)) % np.uint64(side)).astype(U32)
+    ys = ((r & np.uint64(0xFFFFFFFF)) % np.uint64(side)).astype(U32)
+    m, ref = make(), checker()
+    for px, py in zip(np.array_split(xs, pieces), np.array_split(ys, pieces)):
+        m.incr_batch(px, py, None)
+        ref.apply("incr", px, py, np.ones(len(px), U32))
+    keys = np.unique((xs.astype(np.uint64) << np.uint64(32)) | ys.astype(np.uint64))
+    qx, qy = (keys >> np.uint64(32)).astype(U32), (keys & np.uint64(0xFFFFFFFF)).astype(U32)
+    compare(m, ref, np.arange(side + 3, dtype=U32), np.concatenate([qx, qx]), np.concatenate([qy, qy + U32(side)]))
+    assert m.stat("nnz") == len(keys)
+    m.close(); ref.close()
+
+
 def scenario_read_path_zipf(make, n_rows: int = 3000, max_len: int = 20000, seed: int = 31):
     """BASELINE config 4 shape: rows with Zipf lengths P(k) ~ k^-1.7 on [1, max_len], distinct random
     uint32 columns >= 1, random non-zero values; rowlen over all rows, then getrow over all rows,

@@ -95,6 +95,10 @@ def test_benchmark_pattern(make):
     ps.scenario_benchmark_pattern(make, threads=32, rounds=32)      # 1 036 288 ops per cell at T=32 x 32
 
 
+def test_uniform_grid_c1b(make):
+    ps.scenario_uniform_grid(make, n_ops=8_000_000, side=10000)
+
+
 def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=20000, max_len=200000)
 

@@ -89,6 +89,10 @@ def test_benchmark_pattern(make):
     ps.scenario_benchmark_pattern(make, threads=4, rounds=3)
 
 
+def test_uniform_grid_c1b(make):
+    ps.scenario_uniform_grid(make, n_ops=30000, side=300)
+
+
 def test_read_path_zipf(make):
     ps.scenario_read_path_zipf(make, n_rows=300, max_len=3000)
 
