@@ -366,8 +366,8 @@ def main_ours(a):
 
     # ---- e2e: the same build through host (pinned) buffers
     e2e = None
-    if not a.no_e2e and world == 1:
-        e2e = run_e2e(a, torch, dev, local, with_arena(lambda: SparseMatrix(device=local)), B, K, prefill, n_batches)
+    if not a.no_e2e:
+        e2e = run_e2e(a, torch, dev, mk, gen, B, K, prefill, n_batches, rank, world, barrier, max_over_ranks)
 
     if world > 1:
         t = torch.tensor([nnz_local, rows_local, vsum_local], dtype=torch.int64, device=dev)
@@ -448,56 +448,67 @@ def main_ours(a):
         dist.destroy_process_group()
 
 
-def run_e2e(a, torch, dev, local, make_matrix, B, K, prefill, n_batches):
-    """Same stream, HOST buffers: each timed step is one smatrix_incr_batch(host pointers) call —
-    H2D of the batch, the update, and the D2H reads of the control block."""
+def run_e2e(a, torch, dev, make_matrix, gen, B, K, prefill, n_batches, rank, world, barrier, max_over_ranks):
+    """Same stream, HOST buffers: each timed step is one incr_batch(host arrays) call per rank —
+    H2D of the batch, (N > 1: the route,) the update, and the D2H reads of the control block.
+    Per step: barrier, wall clock around the call, max over ranks."""
+    rows_total = a.rows * world
+    first_of = lambda k: (k * world + rank) * B
     dx = torch.empty(B, dtype=torch.int32, device=dev)
     dy = torch.empty(B, dtype=torch.int32, device=dev)
     hx = torch.empty(B, dtype=torch.int32, pin_memory=True)
     hy = torch.empty(B, dtype=torch.int32, pin_memory=True)
     scratch = make_matrix()                      # warm-up of the host-pointer path (W steps, other seed)
+    g = gen or scratch
     for w in range(a.warmup):
-        scratch.gen_c2_ops(98, w * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
+        g.gen_c2_ops(98, (rank * a.warmup + w) * B, B, rows_total, a.ycols, dx.data_ptr(), dy.data_ptr())
         hx.copy_(dx); hy.copy_(dy)
         torch.cuda.synchronize()
         scratch.incr_batch(hx, hy, None)
     scratch.close()
     m = make_matrix()
+    if world > 1:
+        m.reserve_route(B)
+    g = gen or m
     for k in range(prefill):
-        m.gen_c2_ops(SEED_BUILD, k * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
+        g.gen_c2_ops(SEED_BUILD, first_of(k), B, rows_total, a.ycols, dx.data_ptr(), dy.data_ptr())
         m.incr_batch(dx, dy, None)
     rounds0 = m.stat("rounds")
     secs, series = 0.0, []
     for j in range(K):
-        m.gen_c2_ops(SEED_BUILD, (prefill + j) * B, B, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
+        g.gen_c2_ops(SEED_BUILD, first_of(prefill + j), B, rows_total, a.ycols, dx.data_ptr(), dy.data_ptr())
         hx.copy_(dx); hy.copy_(dy)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         m.incr_batch(hx, hy, None)               # returns after the device finished (synchronous API)
-        series.append(round((time.perf_counter() - t0) * 1e3, 2))
-        secs += series[-1] * 1e-3
+        dt = max_over_ranks(time.perf_counter() - t0)
+        series.append(round(dt * 1e3, 2))
+        secs += dt
     rounds = m.stat("rounds") - rounds0
-    incr = K * B / secs / 1e6
+    incr = K * B * world / secs / 1e6
     # gets through host buffers: queries up, values down
     G = min(a.gets, 4 * B)
-    n_build = n_batches * B
+    n_build = n_batches * B * world
     hq = torch.empty(B, dtype=torch.int32, pin_memory=True)
     hr = torch.empty(B, dtype=torch.int32, pin_memory=True)
     gsecs, done = 0.0, 0
     while done < G:
         cnt = min(B, G - done)
-        m.gen_c2_queries(SEED_GET, SEED_BUILD, done, cnt, n_build, a.rows, a.ycols, dx.data_ptr(), dy.data_ptr())
+        g.gen_c2_queries(SEED_GET, SEED_BUILD, rank * G + done, cnt, n_build, rows_total, a.ycols,
+                         dx.data_ptr(), dy.data_ptr())
         hx.copy_(dx); hq.copy_(dy)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         m.get_batch(hx[:cnt], hq[:cnt], hr[:cnt])
-        gsecs += time.perf_counter() - t0
+        gsecs += max_over_ranks(time.perf_counter() - t0)
         done += cnt
     m.close()
-    return {"value": incr, "unit": "Mops/s", "h2d_bytes_per_step": 8 * B,
-            "d2h_bytes_per_step": 1072 * max(1, rounds // max(K, 1)), "ms_per_step": secs / K * 1e3, "step_ms": series,
-            "get_mops": G / gsecs / 1e6, "get_h2d_bytes_per_step": 8 * B, "get_d2h_bytes_per_step": 4 * B,
-            "note": "pinned host arrays through smatrix_incr_batch / smatrix_get_batch; wall clock around the call"}
+    return {"value": incr, "unit": "Mops/s", "h2d_bytes_per_step": 8 * B * world,
+            "d2h_bytes_per_step": 1072 * max(1, rounds // max(K, 1)) * world, "ms_per_step": secs / K * 1e3, "step_ms": series,
+            "get_mops": G * world / gsecs / 1e6, "get_h2d_bytes_per_step": 8 * B * world, "get_d2h_bytes_per_step": 4 * B * world,
+            "note": "pinned host arrays through incr_batch / get_batch (N = 1: the C-ABI smatrix_incr_batch / smatrix_get_batch "
+                    "with host pointers; N > 1: the sharded API stages each rank's slice, then routes); barrier, wall clock "
+                    "around the call, max over ranks"}
 
 
 def _json_only_stdout():

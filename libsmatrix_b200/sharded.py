@@ -20,6 +20,7 @@ commutes), so the result is identical.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import numpy as np
@@ -123,6 +124,57 @@ class ShardedSparseMatrix:
             b = torch.empty(max(n + n // 8, 1024), dtype=torch.int32, device=self.dev)
             self._bufs[name] = b
         return b[:n]
+
+    def _up(self, name: str, t):
+        """Host arrays (numpy or CPU tensors, ideally pinned) are staged into a reusable device
+        buffer on torch's current stream; device tensors pass through."""
+        if t is None:
+            return None
+        if isinstance(t, np.ndarray):
+            t = torch.from_numpy(t.view(np.int32))
+        if t.device == self.dev:
+            return t
+        d = self._slot("up_" + name, t.numel())
+        d.copy_(t, non_blocking=True)
+        return d
+
+    HOST_PIECE = 1 << 24
+
+    def _host_pieces(self, arrays, n: int):
+        """Order-free host batches: yield (lo, hi, device tensors) piece by piece; the upload of
+        piece k+1 runs on a side stream while the caller routes / applies piece k.  Collective: every
+        rank yields the same number of pieces (its own may be empty)."""
+        pieces = max(1, -(-self._nmax(n) // self.HOST_PIECE))
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.dev) if self._cuda else None
+        as_t = lambda t: None if t is None else (torch.from_numpy(t.view(np.int32)) if isinstance(t, np.ndarray) else t)
+        arrays = [as_t(t) for t in arrays]
+
+        def issue(k):
+            lo, hi = k * n // pieces, (k + 1) * n // pieces
+            out = []
+            ctx = torch.cuda.stream(self._side) if self._side is not None else contextlib.nullcontext()
+            with ctx:
+                for i, t in enumerate(arrays):
+                    if t is None:
+                        out.append(None)
+                        continue
+                    d = self._slot(f"hp{k & 1}_{i}", hi - lo)
+                    d.copy_(t[lo:hi], non_blocking=True)
+                    out.append(d)
+                ev = None
+                if self._side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+            return lo, hi, out, ev
+
+        cur = issue(0)
+        for k in range(pieces):
+            nxt = issue(k + 1) if k + 1 < pieces else None
+            if cur[3] is not None:
+                cur[3].synchronize()
+            yield cur[0], cur[1], cur[2]
+            cur = nxt
 
     def _sync_torch(self):
         if self._cuda:
@@ -307,14 +359,27 @@ class ShardedSparseMatrix:
                 apply(rx, ry, rv)
 
     # ------------------------------------------------------------------ collective batch API
+    # xs / ys / vals: this rank's slice, as device tensors (zero-copy) or host arrays (staged first)
+    def _is_dev(self, t) -> bool:
+        return torch.is_tensor(t) and t.device == self.dev
+
+    def _write_any(self, op: int, xs, ys, vals, ordered: bool):
+        if self._is_dev(xs) or ordered:
+            # ordered batches keep the documented global order (rank-major over whole slices): one piece
+            self._write(op, self._up("x", xs), self._up("y", ys), self._up("v", vals), ordered)
+            return
+        for _, _, (px, py, pv) in self._host_pieces([xs, ys, vals], len(xs)):
+            self._write(op, px, py, pv, False)
+
     def incr_batch(self, xs, ys, vals=None, ordered: bool = True):
-        self._write(0, xs, ys, vals, ordered)
+        self._write_any(0, xs, ys, vals, ordered)
 
     def decr_batch(self, xs, ys, vals=None, ordered: bool = True):
-        self._write(1, xs, ys, vals, ordered)
+        self._write_any(1, xs, ys, vals, ordered)
 
     def set_batch(self, xs, ys, vals=None):
-        self._write(2, xs, ys, vals, True)     # last writer in GLOBAL input order wins
+        # last writer in GLOBAL input order wins
+        self._write(2, self._up("x", xs), self._up("y", ys), self._up("v", vals), True)
 
     def _read_p2p(self, fn, xs, ys, out):
         """Queries travel through the inboxes; every owner's read kernel writes its answers straight
@@ -366,6 +431,27 @@ class ShardedSparseMatrix:
         return None
 
     def get_batch(self, xs, ys, out=None):
+        if not self._is_dev(xs):      # host arrays: piece-wise, uploads and downloads overlap the look-ups
+            n = len(xs)
+            host_out = out if out is not None else np.empty(n, dtype=np.uint32)
+            h = torch.from_numpy(host_out.view(np.int32)) if isinstance(host_out, np.ndarray) else host_out
+            down_ev = [None, None]          # answers go down on their own stream: PCIe is full duplex
+            for k, (lo, hi, (px, py)) in enumerate(self._host_pieces([xs, ys], n)):
+                if down_ev[k & 1] is not None:
+                    down_ev[k & 1].synchronize()           # the answer buffer of piece k-2 is free again
+                ans = self.get_batch(px, py, self._slot(f"hp_ans{k & 1}", hi - lo))
+                if self._cuda:
+                    if not hasattr(self, "_side_down"):
+                        self._side_down = torch.cuda.Stream(self.dev)
+                    with torch.cuda.stream(self._side_down):
+                        h[lo:hi].copy_(ans, non_blocking=True)     # `ans` is complete: the library call is synchronous
+                        down_ev[k & 1] = torch.cuda.Event()
+                        down_ev[k & 1].record(self._side_down)
+                else:
+                    h[lo:hi].copy_(ans)
+            if self._cuda:
+                self._side_down.synchronize()
+            return host_out
         r = self._read_routed(self.local.get_batch, xs, ys, out)
         if r is not None:
             return r

@@ -33,7 +33,7 @@ def main():
     t = lambda a: torch.from_numpy(a.view(np.int32).copy()).to(dev)
     sl = lambda k: slice(rank * k // world, (rank + 1) * k // world)
     ref.apply("incr", xs, ys, vs)
-    m.incr_batch(t(xs[sl(n)]), t(ys[sl(n)]), t(vs[sl(n)]))                 # ordered (default)
+    m.incr_batch(xs[sl(n)], ys[sl(n)], vs[sl(n)])                          # ordered (default); host arrays are staged
     gx = rng.integers(0, 300, 50000).astype(U32) * U32(2654435761)
     gy = rng.integers(1, 40, 50000).astype(U32)
     gv = rng.integers(1, 2**32, 50000, dtype=np.uint64).astype(U32)
@@ -49,6 +49,7 @@ def main():
     qy = np.concatenate([ally[rank::7], rng.integers(0, 130, 1000).astype(U32)])
     got = m.get_batch(t(qx), t(qy)).cpu().numpy().view(U32)
     assert (got == ref.get_many(qx, qy)).all(), f"rank {rank}: sharded get mismatch"
+    assert (m.get_batch(qx, qy) == got).all(), f"rank {rank}: host-array get differs from device-array get"
     rows = np.unique(allx)[rank::world]
     got = m.rowlen_batch(t(rows)).cpu().numpy().view(U32)
     assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
