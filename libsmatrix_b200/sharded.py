@@ -4,10 +4,18 @@
 
 One process per GPU (torch.distributed, backend nccl over NVLink/NVSwitch).  Every rank holds a
 complete private table for the rows it owns.  A batch call is collective: each rank passes ITS
-slice of the batch; the slice is bucketed by owner on the device (K8, smatrix_b200_partition),
-the per-owner counts are exchanged, one all-to-all-v moves the (x, y, value) triples, and each
-rank updates only its own shard.  Reads add the reverse all-to-all-v and un-permute the answers
-into input order.
+slice of the batch (device tensors, or host arrays that are staged piece by piece); the slice is
+bucketed by owner on the device (K8) and moved to the owners, and each rank updates only its own
+shard.  Two routes:
+
+  * peer memory (default on CUDA): the per-owner counts are all-gathered (world x world, tiny) and
+    ONE scatter kernel writes every owner's run straight into that owner's inbox — symmetric
+    buffers mapped through CUDA IPC, plain stores over NVLink (smatrix_b200_route_p2p).  Reads: the
+    owners' look-up kernels write the answers straight into the requester's answer buffer, in a
+    staggered order so that no GPU is ever the target of all the others at once, and the
+    requester un-permutes them (smatrix_b200_gather).
+  * NCCL (fallback; gloo on CPU for the tests): partition into a send buffer, one all-to-all-v of
+    the (x, y, value) triples, reverse all-to-all-v for reads.
 
 Input order.  The collective batch is the concatenation of the ranks' slices in rank order.
 Routing permutes ops, and two results depend on order: which duplicate `set` wins, and the
@@ -110,6 +118,7 @@ class ShardedSparseMatrix:
         self._pool = None
         self._bufs: dict[str, torch.Tensor] = {}
         self._gen = 0
+        self._side = self._side_down = None      # upload / download streams of the host-array path
         self._cuda = _lib_path is None
         self.dev = torch.device("cuda", device) if self._cuda else torch.device("cpu")
 
@@ -145,8 +154,8 @@ class ShardedSparseMatrix:
         piece k+1 runs on a side stream while the caller routes / applies piece k.  Collective: every
         rank yields the same number of pieces (its own may be empty)."""
         pieces = max(1, -(-self._nmax(n) // self.HOST_PIECE))
-        if not hasattr(self, "_side"):
-            self._side = torch.cuda.Stream(self.dev) if self._cuda else None
+        if self._side is None and self._cuda:
+            self._side = torch.cuda.Stream(self.dev)
         as_t = lambda t: None if t is None else (torch.from_numpy(t.view(np.int32)) if isinstance(t, np.ndarray) else t)
         arrays = [as_t(t) for t in arrays]
 
@@ -441,7 +450,7 @@ class ShardedSparseMatrix:
                     down_ev[k & 1].synchronize()           # the answer buffer of piece k-2 is free again
                 ans = self.get_batch(px, py, self._slot(f"hp_ans{k & 1}", hi - lo))
                 if self._cuda:
-                    if not hasattr(self, "_side_down"):
+                    if self._side_down is None:
                         self._side_down = torch.cuda.Stream(self.dev)
                     with torch.cuda.stream(self._side_down):
                         h[lo:hi].copy_(ans, non_blocking=True)     # `ans` is complete: the library call is synchronous

@@ -42,6 +42,13 @@ def main():
     ref.apply("incr", fx, fy, np.ones(9000, np.uint32))
     fs = slice(rank * 9000 // world, (rank + 1) * 9000 // world)
     m.incr_batch(t(fx[fs]), t(fy[fs]), None, ordered=False)
+    # the same kind of stream as HOST arrays: staged piece by piece (3 - 4 pieces here)
+    m.PIPELINE_MIN, m.HOST_PIECE = 1 << 62, 1300
+    hx = rng.integers(0, 3000, 9000).astype(np.uint32) * np.uint32(2654435761)
+    hy = rng.integers(1, 60, 9000).astype(np.uint32)
+    ref.apply("incr", hx, hy, np.ones(9000, np.uint32))
+    m.incr_batch(hx[fs], hy[fs], None, ordered=False)
+    xs = np.concatenate([xs, fx, hx]); ys = np.concatenate([ys, fy, hy])
     # set with duplicate keys across ranks: the last writer in GLOBAL input order must win
     gx = rng.integers(0, 50, 6000).astype(np.uint32) * np.uint32(2654435761)
     gy = rng.integers(1, 20, 6000).astype(np.uint32)
@@ -55,6 +62,7 @@ def main():
     qy = np.concatenate([ys[rank::5], rng.integers(0, 70, 300).astype(np.uint32)])
     got = m.get_batch(t(qx), t(qy)).numpy().view(np.uint32)
     assert (got == ref.get_many(qx, qy)).all(), f"rank {rank}: sharded get mismatch"
+    assert (m.get_batch(qx, qy) == got).all(), f"rank {rank}: host-array get differs"   # piece-wise path
     rows = np.unique(xs)[rank::2]
     got = m.rowlen_batch(t(rows)).numpy().view(np.uint32)
     assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
