@@ -37,7 +37,12 @@ typedef struct smatrix_s smatrix_t;
 
 /* replaces src/smatrix.c:74-111.  fname == NULL: memory-only matrix on the device chosen by
  * $SMATRIX_DEVICE (default 0).  fname != NULL: the table is loaded from that .smx file if it
- * exists and written back to it by smatrix_close (snapshot persistence). */
+ * exists and written back to it by smatrix_close (snapshot persistence).
+ * DURABILITY differs from the reference: the reference's IO thread streams dirty rows to the
+ * file all the time (src/smatrix.c:418-596); here the file changes only in smatrix_close and in
+ * smatrix_b200_snapshot (smatrix_b200.h) — written to a temporary file, fsync'ed, then renamed
+ * over the old one, so the file on disk is always a complete snapshot.  Updates made after the
+ * last snapshot are lost if the process dies (every "libsmatrix error" path abort()s). */
 smatrix_t* smatrix_open(const char* fname);
 
 /* replaces src/smatrix.c:113-133.  Writes the snapshot (file mode) and frees all device memory. */

@@ -15,8 +15,17 @@ extern "C" {
 /* smatrix_open on an explicit CUDA device ordinal (smatrix_open uses $SMATRIX_DEVICE, default 0).
  * Environment read at open: SMATRIX_ARENA_GIB (reserve that much slab memory up front instead of
  * cudaMalloc'ing segments on demand), SMATRIX_CHUNK (ops per internal chunk, default 2^25),
- * SMATRIX_DIR_LOG2 (initial directory size), SMATRIX_PREAGG (warp pre-aggregation on/off). */
+ * SMATRIX_DIR_LOG2 (initial directory size), SMATRIX_PREAGG (warp pre-aggregation on/off),
+ * SMATRIX_RECYCLE (free lists of vacated buckets on/off), SMATRIX_PRESIZE (distinct-row estimate
+ * that sizes the directory before a chunk of new rows, on/off). */
 smatrix_t* smatrix_b200_open(const char* fname, int device);
+
+/* File-backed handles: write the snapshot NOW (temporary file, fsync, atomic rename) and return 0
+ * on success, -1 on failure (or when the handle has no file).  The reference streams dirty rows to
+ * its file continuously from an IO thread (src/smatrix.c:418-596); this build persists only here
+ * and in smatrix_close, so a process that abort()s in between loses the updates since the last
+ * snapshot — call this at the checkpoints the application can afford. */
+int   smatrix_b200_snapshot(smatrix_t* self);
 
 int   smatrix_b200_device(smatrix_t* self);   /* CUDA device ordinal                            */
 void* smatrix_b200_stream(smatrix_t* self);   /* the cudaStream_t every kernel is launched on   */
@@ -40,7 +49,10 @@ enum {
   /* host wall-clock per phase of the write path since set_kernel_timing(1), ns */
   SMX_STAT_NS_PARTITION = 10, SMX_STAT_NS_UPSERT = 11, SMX_STAT_NS_GROW_PLAN = 12,
   SMX_STAT_NS_SLAB = 13, SMX_STAT_NS_MIGRATE = 14, SMX_STAT_NS_DIR = 15,
-  SMX_STAT_VALUE_SUM = 16   /* sum of every stored value mod 2^64 (scans the whole table) */
+  SMX_STAT_VALUE_SUM = 16,  /* sum of every stored value mod 2^64 (scans the whole table) */
+  SMX_STAT_LIVE_BUCKET_BYTES = 17, /* bytes of slab buckets rows own right now (scans the directory) */
+  SMX_STAT_FREE_BYTES = 18, /* bytes of vacated buckets waiting on the free lists              */
+  SMX_STAT_RECYCLED = 19    /* row growths served from the free lists so far                   */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 

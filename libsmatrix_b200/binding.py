@@ -41,6 +41,7 @@ PROTOTYPES = {
                                                C.c_void_p, C.c_uint64]),
     # include/smatrix_b200.h
     "smatrix_b200_open": (C.c_void_p, [C.c_char_p, C.c_int]),
+    "smatrix_b200_snapshot": (C.c_int, [C.c_void_p]),
     "smatrix_b200_device": (C.c_int, [C.c_void_p]),
     "smatrix_b200_stream": (C.c_void_p, [C.c_void_p]),
     "smatrix_b200_sync": (None, [C.c_void_p]),
@@ -79,7 +80,8 @@ PROTOTYPES = {
 
 STAT = {"rows": 0, "nnz": 1, "dir_cap": 2, "slab_bytes": 3, "device_bytes": 4, "launches": 5,
         "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9, "ns_partition": 10, "ns_upsert": 11,
-        "ns_grow_plan": 12, "ns_slab": 13, "ns_migrate": 14, "ns_dir": 15, "value_sum": 16}
+        "ns_grow_plan": 12, "ns_slab": 13, "ns_migrate": 14, "ns_dir": 15, "value_sum": 16,
+        "live_bucket_bytes": 17, "free_bytes": 18, "recycled": 19}
 
 _cache: dict[str, C.CDLL] = {}
 

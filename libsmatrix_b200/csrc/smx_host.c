@@ -50,6 +50,7 @@ typedef struct {
 
 struct smatrix_s {
   int device;
+  int prev_device; /* the caller's current device, restored by leave() */
   cudaStream_t stream;
   cudaStream_t copy_stream;
   cudaStream_t read_stream[2]; /* with stream + copy_stream: four pieces of a host-pointer read in flight */
@@ -110,7 +111,12 @@ struct smatrix_s {
   size_t d_big_bytes;
   uint32_t n_big_rows;
 
-  uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows;
+  unsigned long long* free_ptr[SMX_CLASSES]; /* device stacks of vacated buckets, per size class */
+  uint32_t free_cap[SMX_CLASSES];
+  int recycle;                               /* SMATRIX_RECYCLE (default 1) */
+  int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
+
+  uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
   double phase_ns[8];
   int timing;
   cudaEvent_t ev0, ev1, t_start, t_stop;
@@ -254,7 +260,7 @@ static void ensure_lists(smatrix_t* s, uint32_t n) {
     CK(cudaStreamSynchronize(s->stream));
     scratch_free(s, s->defer[0]); scratch_free(s, s->defer[1]); scratch_free(s, s->lists.late);
     scratch_free(s, s->lists.grow); scratch_free(s, s->lists.t0rows); scratch_free(s, s->lists.plan);
-    scratch_free(s, s->lists.big);
+    scratch_free(s, s->lists.big); scratch_free(s, s->lists.mid);
   }
   s->defer[0] = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
   s->defer[1] = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
@@ -263,6 +269,7 @@ static void ensure_lists(smatrix_t* s, uint32_t n) {
   s->lists.t0rows = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
   s->lists.plan = (smx_plan_t*)scratch_alloc(s, (size_t)cap * sizeof(smx_plan_t));
   s->lists.big = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
+  s->lists.mid = (uint32_t*)scratch_alloc(s, (size_t)cap * 4);
   s->list_cap = cap;
 }
 
@@ -309,6 +316,28 @@ static void timed_collect(smatrix_t* s) { /* call after the stream has been sync
   }
 }
 
+/* make room on the free-list stacks for the buckets this round vacates (k_grow_plan counted them
+ * per class); stacks grow geometrically and are only as large as the table needs them */
+static void ensure_free_stacks(smatrix_t* s) {
+  for (uint32_t c = SMX_MIN_SLAB_LOG; c < SMX_CLASSES; c++) {
+    const uint32_t incoming = s->h_ctl->grow_from[c];
+    if (!incoming) continue;
+    const int32_t have = s->h_ctl->free_cnt[c] > 0 ? s->h_ctl->free_cnt[c] : 0;
+    const uint64_t need = (uint64_t)have + incoming;
+    if (need <= s->free_cap[c]) continue;
+    uint64_t cap = s->free_cap[c] ? s->free_cap[c] : 256;
+    while (cap < need) cap *= 2;
+    if (cap > 0x7FFFFFFFull) smx_die("free list of class %u too long", c);
+    unsigned long long* nb = (unsigned long long*)dmalloc(s, (size_t)cap * 8);
+    if (have) CK(cudaMemcpyAsync(nb, s->free_ptr[c], (size_t)have * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(&s->d_ctl->free_stack[c], &nb, sizeof nb, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream)); /* &nb is a stack variable; the old stack may be freed now */
+    if (s->free_ptr[c]) CK(cudaFree(s->free_ptr[c]));
+    s->free_ptr[c] = nb;
+    s->free_cap[c] = (uint32_t)cap;
+  }
+}
+
 static void grow_rows(smatrix_t* s, uint32_t n_grow) {
   smx_view_t v = view_of(s);
   double t0 = now_ns();
@@ -317,18 +346,59 @@ static void grow_rows(smatrix_t* s, uint32_t n_grow) {
   read_ctl(s);
   double t1 = now_ns();
   const size_t bytes = (size_t)s->h_ctl->plan_bytes;
-  const uint32_t n_big = s->h_ctl->n_big;
-  char* region = slab_reserve(s, bytes);
+  const uint32_t n_big = s->h_ctl->n_big, n_mid = s->h_ctl->n_mid;
+  char* region = bytes ? slab_reserve(s, bytes) : NULL;
+  if (s->recycle) {
+    ensure_free_stacks(s);
+    smx_launch_free_push(s->stream, v, s->lists, n_grow);
+    s->n_launches++;
+  }
   double t2 = now_ns();
   /* buckets built in shared memory are written out whole; only in-place (global CAS) fills need zeros */
-  if (s->h_ctl->need_zero) CK(cudaMemsetAsync(region, 0, bytes, s->stream));
-  smx_launch_migrate(s->stream, v, s->lists, n_grow, n_big, region);
+  if (bytes && s->h_ctl->need_zero) CK(cudaMemsetAsync(region, 0, bytes, s->stream));
+  smx_launch_migrate(s->stream, v, s->lists, n_grow, n_mid, n_big, region);
   if (s->timing) CK(cudaStreamSynchronize(s->stream)); /* attribute the device time to this phase */
-  s->n_launches += 1 + (n_big ? 2 : 0);
+  s->n_launches += (n_grow > n_mid + n_big ? 1 : 0) + (n_mid ? 1 : 0) + (n_big ? 2 : 0);
   s->n_row_grows += n_grow;
+  s->n_recycled += s->h_ctl->n_recycled;
   s->phase_ns[PH_GROW_PLAN] += t1 - t0;
   s->phase_ns[PH_SLAB] += t2 - t1;
   s->phase_ns[PH_MIGRATE] += now_ns() - t2;
+}
+
+/* A chunk of mostly NEW rows would overflow a small directory and waste a whole round finding that
+ * out (every op turned away, then one resize per doubling).  Estimate the chunk's distinct rows
+ * with one streaming pass (linear counting) and size the directory for them up front. */
+/* ln(r) for 0 < r <= 1 without libm (bindings link the static archive without -lm):
+ * r = f * 2^-k with f in [0.5, 1), ln f = 2 atanh((f-1)/(f+1)) by its series (|y| <= 1/3) */
+static double ln_unit(double r) {
+  int k = 0;
+  while (r < 0.5) { r *= 2.0; k++; }
+  const double y = (r - 1.0) / (r + 1.0), y2 = y * y;
+  double term = y, sum = 0.0;
+  for (int i = 1; i < 40; i += 2) { sum += term / (double)i; term *= y2; }
+  return 2.0 * sum - (double)k * 0.69314718055994530942;
+}
+#define SMX_SKETCH_BITS_LOG 25u
+static void resize_dir(smatrix_t* s, uint64_t new_cap);
+static uint64_t pow2_at_least(uint64_t v);
+static void presize_dir(smatrix_t* s, const smx_ops_t* ops) {
+  const uint64_t n = ops->n, used = s->h_ctl->dir_used;
+  if (n < s->part_min || !s->presize) return;      /* small batches: the grow loop is cheap        */
+  if (used + n <= s->dir_cap / 4) return;          /* fits even if every op creates a row           */
+  if (4 * used >= n) return;                       /* mostly existing rows: let the grow loop decide */
+  const uint64_t m = 1ull << SMX_SKETCH_BITS_LOG;
+  ensure_tmp(s, (size_t)(m / 8), 0);
+  CK(cudaMemsetAsync(s->d_tmp, 0, (size_t)(m / 8), s->stream));
+  CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
+  smx_launch_sketch(s->stream, ops->xs, ops->n, s->d_tmp, SMX_SKETCH_BITS_LOG, s->d_ctl);
+  s->n_launches += 2;
+  read_ctl(s);
+  const double zeros = (double)s->h_ctl->scratch;
+  double est = zeros >= 1.0 ? -(double)m * ln_unit(zeros / (double)m) : (double)n;
+  if (est > (double)n) est = (double)n;
+  const uint64_t cap = pow2_at_least((uint64_t)(4.0 * ((double)used + 1.1 * est)) + 64);
+  if (cap > s->dir_cap) resize_dir(s, cap);
 }
 
 static uint64_t pow2_at_least(uint64_t v) {
@@ -424,15 +494,18 @@ static void maybe_shrink_dir(smatrix_t* s) {
 
 /* Reorder a chunk so that ops on rows of the same directory slice are adjacent: the slice of the
  * directory (a few MB) then stays in L2 while its ops are applied, and a row header costs one
- * DRAM read + one write-back per chunk instead of one per op.  idx keeps the input order. */
-static void partition_chunk(smatrix_t* s, smx_ops_t* ops, int* has_col0) {
+ * DRAM read + one write-back per chunk instead of one per op.  Ops on column 0 go to parts of their
+ * own behind all the others: [other ops by slice | column-0 ops by slice], so each pass runs over
+ * a dense range.  The input-order index travels along (part[3]) only when something depends on it:
+ * a set batch, a chunk that writes column 0, or a caller-supplied order.
+ * Returns 1 if the chunk was partitioned; *n_main = number of ops that are not on column 0. */
+static int partition_chunk(smatrix_t* s, smx_ops_t* ops, int api_op, uint32_t* n_main) {
   const uint32_t n = ops->n;
   uint32_t dir_log = 0;
   while ((1ull << dir_log) < s->dir_cap) dir_log++;
   uint32_t parts_log = dir_log > s->slice_log ? dir_log - s->slice_log : 0; /* default: slices of 2^17 entries = 8 MiB */
   if (parts_log > s->parts_log_max) parts_log = s->parts_log_max;
-  if (parts_log == 0) return;
-  const uint32_t parts = 1u << parts_log, shift = dir_log - parts_log;
+  const uint32_t slices = 1u << parts_log, parts = 2u * slices, shift = dir_log - parts_log;
   if (n > s->part_cap) {
     if (s->part_cap) {
       CK(cudaStreamSynchronize(s->stream));
@@ -441,29 +514,43 @@ static void partition_chunk(smatrix_t* s, smx_ops_t* ops, int* has_col0) {
     s->part_cap = s->list_cap > n ? s->list_cap : n;
     for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)scratch_alloc(s, (size_t)s->part_cap * 4);
   }
-  ensure_tmp(s, 0, 2 * (SMX_MAX_PARTS_H + 1) * 8);
+  ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
-  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H + 1;
-  unsigned long long h[SMX_MAX_PARTS_H + 1], cur[SMX_MAX_PARTS_H];
+  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
+  unsigned long long h[SMX_MAX_PARTS_H], cur[SMX_MAX_PARTS_H];
   double t0 = now_ns();
-  CK(cudaMemsetAsync(d_counts, 0, (parts + 1) * 8, s->stream));
-  smx_launch_partition_count(s->stream, ops->xs, ops->ys, n, parts, (uint32_t)(s->dir_cap - 1), shift, d_counts);
-  CK(cudaMemcpyAsync(h, d_counts, (parts + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemsetAsync(d_counts, 0, parts * 8, s->stream));
+  smx_launch_partition_count(s->stream, ops->xs, ops->ys, n, parts, (uint32_t)(s->dir_cap - 1), shift, slices, d_counts);
+  CK(cudaMemcpyAsync(h, d_counts, parts * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
-  *has_col0 = h[parts] != 0; /* the count pass saw every y: no column-0 op, no column-0 pass */
   unsigned long long at = 0;
-  for (uint32_t p = 0; p < parts; p++) { cur[p] = at; at += h[p]; }
+  for (uint32_t p = 0; p < parts; p++) {
+    if (p == slices) *n_main = (uint32_t)at;
+    cur[p] = at;
+    at += h[p];
+  }
+  const int want_idx = api_op == 2 || *n_main != n || ops->idx != NULL;
   CK(cudaMemcpyAsync(d_cursors, cur, parts * 8, cudaMemcpyHostToDevice, s->stream));
   smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, (uint32_t)(s->dir_cap - 1),
-                               shift, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
-                               s->part[3], ops->idx, NULL, NULL, 0);
+                               shift, slices, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
+                               want_idx ? s->part[3] : NULL, ops->idx, NULL, NULL, 0);
   s->n_launches += 2;
   if (s->timing) CK(cudaStreamSynchronize(s->stream));
   s->phase_ns[PH_PARTITION] += now_ns() - t0;
   ops->xs = s->part[0];
   ops->ys = s->part[1];
   if (ops->vs) ops->vs = s->part[2];
-  ops->idx = s->part[3];
+  ops->idx = want_idx ? s->part[3] : NULL;
+  return 1;
+}
+
+static smx_ops_t ops_range(smx_ops_t o, uint32_t first, uint32_t count) {
+  o.xs += first;
+  o.ys += first;
+  if (o.vs) o.vs += first;
+  if (o.idx) o.idx += first;
+  o.n = count;
+  return o;
 }
 
 static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs, const uint32_t* d_ys,
@@ -481,18 +568,24 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   smx_ops_t ops;
   ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = d_ords; ops.v_const = 1u; ops.n = n;
 
-  int has_col0 = 1;
-  if (n >= s->part_min) partition_chunk(s, &ops, &has_col0);
+  presize_dir(s, &ops);
+  uint32_t n_main = n;
+  const int parted = (n >= s->part_min) ? partition_chunk(s, &ops, api_op, &n_main) : 0;
+  /* partitioned: [0, n_main) = ops on columns != 0, [n_main, n) = ops on column 0 (dense ranges);
+   * otherwise both passes scan the whole chunk and pick their ops by column */
+  const smx_ops_t ops0 = parted ? ops_range(ops, n_main, n - n_main) : ops;
+  const smx_ops_t opsm = parted ? ops_range(ops, 0, n_main) : ops;
   const int op = (api_op == 2) ? SMX_OP_SETZERO : api_op;
   CK(cudaMemsetAsync(&s->d_ctl->n_late, 0, 2 * sizeof(uint32_t), s->stream));
-  if (has_col0) run_pass(s, ops, op, SMX_PASS_COL0, NULL, n);
-  run_pass(s, ops, op, SMX_PASS_EARLY, NULL, n);
+  s->h_ctl->n_late = s->h_ctl->n_t0 = 0;
+  if (ops0.n) run_pass(s, ops0, op, SMX_PASS_COL0, NULL, ops0.n);
+  if (opsm.n) run_pass(s, opsm, op, SMX_PASS_EARLY, NULL, opsm.n);
   if (s->h_ctl->n_t0) { /* column 0 of these rows turns non-zero now: sync their rowlen state (z = 0 so far) */
     smx_launch_sync_rowlen(s->stream, view_of(s), s->lists.t0rows, s->h_ctl->n_t0);
     s->n_launches++;
   }
   const uint32_t n_late = s->h_ctl->n_late;
-  if (n_late) run_pass(s, ops, op, SMX_PASS_LATE, s->lists.late, n_late);
+  if (n_late) run_pass(s, opsm, op, SMX_PASS_LATE, s->lists.late, n_late);
   if (api_op == 2) { /* set: last writer in input order wins */
     if (n > s->addrs_cap) {
       if (s->addrs) { CK(cudaStreamSynchronize(s->stream)); scratch_free(s, s->addrs); }
@@ -522,12 +615,22 @@ static int is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+/* Every entry point runs on the handle's GPU and puts the caller's current device back afterwards,
+ * so a process that holds handles on several GPUs (or mixes the library with other CUDA code) never
+ * finds its current device changed by a call. */
 static void enter(smatrix_t* s) {
   if (!s) smx_die("NULL matrix handle");
   pthread_mutex_lock(&s->mu);
-  CK(cudaSetDevice(s->device));
+  int cur = s->device;
+  if (cudaGetDevice(&cur) != cudaSuccess) { (void)cudaGetLastError(); cur = s->device; }
+  s->prev_device = cur;
+  if (cur != s->device) CK(cudaSetDevice(s->device));
 }
-static void leave(smatrix_t* s) { pthread_mutex_unlock(&s->mu); }
+static void leave(smatrix_t* s) {
+  const int back = s->prev_device, mine = s->device;
+  if (back != mine) (void)cudaSetDevice(back);
+  pthread_mutex_unlock(&s->mu);
+}
 
 static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint32_t* ys,
                         const uint32_t* vs, size_t n) {
@@ -1008,6 +1111,16 @@ static int write_all(int fd, const void* buf, size_t bytes, uint64_t at) {
   return 0;
 }
 
+static void sync_parent_dir(const char* fname) { /* make the rename itself durable */
+  char* dir = strdup(fname);
+  if (!dir) return;
+  char* slash = strrchr(dir, '/');
+  if (slash) *(slash == dir ? slash + 1 : slash) = 0;
+  int dfd = open(slash ? dir : ".", O_RDONLY);
+  if (dfd != -1) { (void)fsync(dfd); close(dfd); }
+  free(dir);
+}
+
 /* caller holds the handle lock */
 static int snapshot_save(smatrix_t* s) {
   size_t fl = strlen(s->fname);
@@ -1123,9 +1236,14 @@ static int snapshot_save(smatrix_t* s) {
     if (cnt && write_all(fd, dir_entries + lo * SMX_F_DIR_SLOT, cnt * SMX_F_DIR_SLOT, bpos + SMX_F_DIR_HEAD)) rc = -1;
   }
   if (rc == 0 && ftruncate(fd, (off_t)fpos) == -1) rc = -1; /* unused directory entries read back as zeros */
+  if (rc == 0 && fsync(fd) == -1) rc = -1; /* the data is on disk before the old file is replaced */
   if (close(fd) == -1) rc = -1;
   if (rc == 0 && rename(tmp, s->fname) == -1) rc = -1;
-  if (rc) perror("libsmatrix: writing the snapshot failed");
+  if (rc == 0) sync_parent_dir(s->fname);
+  if (rc) {
+    perror("libsmatrix: writing the snapshot failed");
+    unlink(tmp); /* the previous snapshot, if any, is still intact */
+  }
   if (d_keys) cudaFree(d_keys);
   free(dir_entries); free(h_keys); free(h_slog); free(h_off); free(h_pairs); free(out); free(tmp);
   return rc;
@@ -1263,6 +1381,8 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   if (s->chunk_max < 1) s->chunk_max = 1;
   if (s->chunk_max > (1u << 30)) s->chunk_max = 1u << 30;
   s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
+  s->recycle = (int)env_u32("SMATRIX_RECYCLE", 1);
+  s->presize = (int)env_u32("SMATRIX_PRESIZE", 1);
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
@@ -1308,7 +1428,10 @@ void smatrix_close(smatrix_t* s) {
   enter(s);
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaStreamSynchronize(s->copy_stream));
-  if (s->fname) snapshot_save(s);
+  if (s->fname && snapshot_save(s) != 0) { /* close() is void (src/smatrix.h:88): be loud instead */
+    printf("libsmatrix error: could not write %s; the previous snapshot (if any) was kept\n", s->fname);
+    fflush(stdout);
+  }
   for (int i = 0; i < s->nsegs; i++) cudaFree(s->segs[i].base);
   free(s->segs);
   if (!s->dir_in_arena) cudaFree(s->dir);
@@ -1319,8 +1442,10 @@ void smatrix_close(smatrix_t* s) {
   if (s->list_cap) {
     scratch_free(s, s->defer[0]); scratch_free(s, s->defer[1]); scratch_free(s, s->lists.late);
     scratch_free(s, s->lists.grow); scratch_free(s, s->lists.t0rows); scratch_free(s, s->lists.plan);
-    scratch_free(s, s->lists.big);
+    scratch_free(s, s->lists.big); scratch_free(s, s->lists.mid);
   }
+  for (uint32_t c = 0; c < SMX_CLASSES; c++)
+    if (s->free_ptr[c]) cudaFree(s->free_ptr[c]);
   scratch_free(s, s->addrs);
   if (s->part_cap)
     for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
@@ -1348,6 +1473,14 @@ void smatrix_close(smatrix_t* s) {
 }
 
 /* ------------------------------------------------------------------------------ controls */
+int smatrix_b200_snapshot(smatrix_t* s) {
+  if (!s->fname) return -1;
+  enter(s);
+  CK(cudaStreamSynchronize(s->stream));
+  const int rc = snapshot_save(s);
+  leave(s);
+  return rc;
+}
 int smatrix_b200_device(smatrix_t* s) { return s->device; }
 void* smatrix_b200_stream(smatrix_t* s) { return (void*)s->stream; }
 void smatrix_b200_sync(smatrix_t* s) {
@@ -1399,6 +1532,19 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
       read_ctl(s);
       r = s->h_ctl->scratch;
       break;
+    case SMX_STAT_LIVE_BUCKET_BYTES:
+      CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
+      smx_launch_live_bytes(s->stream, view_of(s));
+      s->n_launches++;
+      read_ctl(s);
+      r = s->h_ctl->scratch;
+      break;
+    case SMX_STAT_FREE_BYTES:
+      read_ctl(s);
+      for (uint32_t c = SMX_MIN_SLAB_LOG; c < SMX_CLASSES; c++)
+        if (s->h_ctl->free_cnt[c] > 0) r += (uint64_t)s->h_ctl->free_cnt[c] * (8ull << c);
+      break;
+    case SMX_STAT_RECYCLED: r = s->n_recycled; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;
     case SMX_STAT_SLAB_BYTES: r = s->slab_bytes; break;
     case SMX_STAT_DEVICE_BYTES:
@@ -1541,7 +1687,7 @@ void smatrix_b200_partition_count(smatrix_t* s, const uint32_t* d_xs, size_t n, 
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
   unsigned long long h[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
-  smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
+  smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, 0, d_counts);
   CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   for (uint32_t r = 0; r < world; r++) h_counts[r] = h[r];
@@ -1564,7 +1710,7 @@ void smatrix_b200_route_p2p(smatrix_t* s, const uint32_t* d_xs, const uint32_t* 
   unsigned long long* d_tab = (unsigned long long*)s->d_tmp64 + 128;
   CK(cudaMemsetAsync(d_cursors, 0, 64 * 8, s->stream));
   CK(cudaMemcpyAsync(d_tab, h_dst, 5 * (size_t)world * 8, cudaMemcpyHostToDevice, s->stream));
-  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER,
+  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER, 0,
                                d_cursors, NULL, NULL, NULL, NULL, NULL, d_out_pos, d_tab, src_bias);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
@@ -1606,7 +1752,7 @@ void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t*
   unsigned long long* d_cursors = d_counts + 64;
   unsigned long long h[64], cur[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
-  smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, d_counts);
+  smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, 0, d_counts);
   CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   unsigned long long at = 0;
@@ -1616,7 +1762,7 @@ void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t*
     h_counts[r] = h[r];
   }
   CK(cudaMemcpyAsync(d_cursors, cur, world * 8, cudaMemcpyHostToDevice, s->stream));
-  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER,
+  smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER, 0,
                                d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL, d_out_pos, NULL, 0);
   s->n_launches += 2;
   CK(cudaStreamSynchronize(s->stream));

@@ -40,6 +40,12 @@ extern "C" {
 #define SMX_MIN_SLAB_LOG 4u     /* first slab bucket: 16 cells = 128 B (src/smatrix.h:21)     */
 #define SMX_MAX_CAPLOG  31u
 #define SMX_BIG_LOG     13u     /* buckets >= 2^13 cells are re-placed / compacted grid-wide  */
+#define SMX_MID_LOG     9u      /* buckets of 2^9 .. 2^12 cells are re-placed by one block each */
+#define SMX_ZERO_LOG    9u      /* vacated buckets >= 2^9 cells are zeroed when they are vacated, so a
+                                   recycled one can be filled in place; smaller ones are always built in
+                                   shared memory and written out whole */
+#define SMX_CLASSES     32u     /* bucket size classes = log2(cells)                          */
+#define SMX_PLAN_RECYCLED (1ull << 63) /* smx_plan_t.off is the address of a recycled bucket, not an offset */
 
 typedef struct {
   uint32_t key;    /* row id x                                  } claimed together by one   */
@@ -65,10 +71,18 @@ typedef struct {
   uint32_t n_dirfull;            /*   ... because the directory was at its load limit        */
   uint32_t n_grow;               /* rows queued for growth                                   */
   uint32_t n_big;                /* of those, rows whose OLD bucket is >= 2^SMX_BIG_LOG      */
-  unsigned long long plan_bytes; /* bytes of new buckets planned by grow_plan                */
+  uint32_t n_mid;                /*           rows whose OLD bucket is 2^SMX_MID_LOG .. 2^(SMX_BIG_LOG-1) */
+  uint32_t n_recycled;           /* planned buckets taken from the free lists                */
+  unsigned long long plan_bytes; /* bytes of FRESH slab planned by grow_plan                 */
   unsigned long long need_zero;  /* planned buckets that are filled in place (global CAS) and so
                                     need a zeroed region; shared-memory-built buckets do not  */
+  uint32_t grow_from[SMX_CLASSES]; /* growing rows per OLD size class = buckets about to be vacated */
   unsigned long long scratch;    /* misc: reductions (nnz, probe checksums)                  */
+  /* persistent: vacated buckets, one stack of addresses per size class (src/smatrix.c:383-416 frees the
+   * old row map on every resize; here k_free_push recycles it and k_grow_plan takes from the stacks
+   * before it plans fresh slab).  The host sizes the stacks (free_stack) before every push. */
+  int32_t free_cnt[SMX_CLASSES];
+  unsigned long long* free_stack[SMX_CLASSES];
   /* persistent: rows per directory slice (slice = position >> dir_slice_shift); new rows are
    * refused in a slice at its limit, so that no region of the directory exceeds the load limit
    * even when a chunk is applied slice by slice */
@@ -96,7 +110,8 @@ typedef struct {
 typedef struct {
   uint32_t entry;      /* directory index of the growing row                                 */
   uint32_t newlog;     /* log2 of the new bucket capacity                                    */
-  uint64_t off;        /* byte offset of the new bucket inside this round's slab region       */
+  uint64_t off;        /* byte offset of the new bucket inside this round's slab region, or
+                          SMX_PLAN_RECYCLED | address of a recycled bucket                      */
 } smx_plan_t;
 
 typedef struct {
@@ -106,6 +121,7 @@ typedef struct {
   uint32_t* t0rows;    /* [n]  row ids (x) whose column 0 turned non-zero in this chunk      */
   smx_plan_t* plan;    /* [n]                                                                */
   uint32_t* big;       /* [n]  plan indices of big rows                                      */
+  uint32_t* mid;       /* [n]  plan indices of mid-size rows                                 */
 } smx_lists_t;
 
 enum { SMX_OP_INCR = 0, SMX_OP_DECR = 1, SMX_OP_SETZERO = 2 };
@@ -117,8 +133,14 @@ typedef void* smx_stream_t;
 void smx_launch_upsert(smx_stream_t stream, smx_view_t v, smx_ops_t ops, smx_lists_t l, int op,
                        int pass, const uint32_t* list, uint32_t m, int preaggregate);
 void smx_launch_grow_plan(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow);
+void smx_launch_free_push(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow);
 void smx_launch_migrate(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow,
-                        uint32_t n_big, void* region_base);
+                        uint32_t n_mid, uint32_t n_big, void* region_base);
+/* distinct-row estimate (linear counting): set bit hash(x) of a zeroed bitmap of 2^bits_log bits,
+ * then count the zero bits into ctl->scratch */
+void smx_launch_sketch(smx_stream_t stream, const uint32_t* xs, uint32_t n, uint32_t* bitmap,
+                       uint32_t bits_log, smx_ctl_t* ctl);
+void smx_launch_live_bytes(smx_stream_t stream, smx_view_t v); /* sum of 8 << caplog over slab buckets -> ctl->scratch */
 void smx_launch_dir_rehash(smx_stream_t stream, smx_view_t from, smx_view_t to);
 void smx_launch_finalize_t0(smx_stream_t stream, smx_view_t v, const uint32_t* t0rows, uint32_t n);
 void smx_launch_sync_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* rows, uint32_t n);
@@ -155,15 +177,16 @@ void smx_launch_gen_c2_queries(smx_stream_t stream, uint64_t seed_get, uint64_t 
 void smx_launch_probe_read(smx_stream_t stream, const void* buf, uint64_t n_units, uint64_t accesses,
                            int width, smx_ctl_t* ctl);
 void smx_launch_probe_atomic(smx_stream_t stream, uint32_t* buf, uint64_t n_words, uint64_t accesses);
-/* part = owner rank when shift == SMX_PART_OWNER, else directory slice (mix_row(x) & dir_mask) >> shift */
+/* part = owner rank when shift == SMX_PART_OWNER, else directory slice (mix_row(x) & dir_mask) >> shift;
+ * split0 != 0 (slice mode, world = 2 * split0): ops on column 0 go to parts split0 .. 2*split0-1 */
 #define SMX_PART_OWNER 0xFFFFFFFFu
 #define SMX_MAX_PARTS_H 256u
 void smx_launch_partition_count(smx_stream_t stream, const uint32_t* xs, const uint32_t* ys /* or NULL */,
                                 uint32_t n, uint32_t world, uint32_t dir_mask, uint32_t shift,
-                                unsigned long long* counts /* [world + 1], zeroed; [world] = ops with y == 0 */);
+                                uint32_t split0, unsigned long long* counts /* [world], zeroed */);
 void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const uint32_t* ys,
                                   const uint32_t* vs, uint32_t n, uint32_t world,
-                                  uint32_t dir_mask, uint32_t shift,
+                                  uint32_t dir_mask, uint32_t shift, uint32_t split0,
                                   unsigned long long* cursors /* [world] start offsets */,
                                   uint32_t* oxs, uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
                                   const uint32_t* src_in /* NULL: osrc = position; else osrc = src_in[position] */,

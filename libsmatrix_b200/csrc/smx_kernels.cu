@@ -81,12 +81,14 @@ __host__ __device__ __forceinline__ ull smx_splitmix64(ull z) {
   return z ^ (z >> 31);
 }
 
-/* One 32-byte sector with a single 256-bit load that bypasses L1 (coherent at L2). */
+/* One 32-byte sector with a single 256-bit load that bypasses L1 (coherent at L2).  L2::64B: a
+ * miss fetches 64 bytes from DRAM instead of the whole 128-byte line (SASS LDG.E.ENL2.LTC64B.256);
+ * the random-touch rate is the same, the DRAM bytes per probe halve (profiles/r2_summary.md). */
 __device__ __forceinline__ void ld_sector(const void* p, ull c[4]) {
 #ifdef SMX_HOSTSIM
   memcpy(c, p, 32);
 #else
-  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.cg.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3])
                : "l"(p)
                : "memory");
@@ -153,11 +155,18 @@ __host__ __device__ __forceinline__ uint32_t rowlen_catch_up(uint32_t meta, uint
 /* ------------------------------------------------------------------------------------------
  * row directory: find or claim (replaces smatrix_cmap_lookup/probe/insert, :621-713)
  * ---------------------------------------------------------------------------------------- */
+/* Probe order: both 64-byte entries of the home 128-byte line first (the line is already paid for
+ * by the first probe), then the next line, and so on.  step -> position for home position p. */
+__host__ __device__ __forceinline__ ull dir_probe_pos(ull p, ull step, ull mask) {
+  return ((((p & ~1ull) + (step & ~1ull)) & mask) | ((p ^ step) & 1ull));
+}
+
 __device__ __forceinline__ int dir_find(const smx_view_t& V, uint32_t x, bool create,
                                         smx_row_t** out, Hdr* hdr) {
   const ull mask = V.dir_cap - 1;
-  ull pos = smx_mix_row(x) & mask;
-  for (ull step = 0; step < V.dir_cap; ++step, pos = (pos + 1) & mask) {
+  const ull home = smx_mix_row(x) & mask;
+  for (ull step = 0; step < V.dir_cap; ++step) {
+    const ull pos = dir_probe_pos(home, step, mask);
     smx_row_t* e = V.dir + pos;
     Hdr h = ld_hdr(e);
     if (h.meta & SMX_META_USED) {
@@ -165,12 +174,16 @@ __device__ __forceinline__ int dir_find(const smx_view_t& V, uint32_t x, bool cr
       continue;
     }
     if (!create) return DIR_MISS;
-    uint32_t* slice = &V.ctl->slice_used[pos >> V.slice_shift];
+    const uint32_t sl = (uint32_t)(pos >> V.slice_shift);
+    uint32_t* slice = &V.ctl->slice_used[sl];
     if (step >= 256 || __ldcg(slice) >= V.slice_limit) return DIR_FULL;
     const ull fresh = (ull)x | ((ull)(SMX_META_USED | SMX_INLINE_LOG) << 32);
     ull old = atomicCAS((ull*)e, 0ull, fresh);
     if (old == 0ull) {
-      atomicAdd(slice, 1u);
+      /* occupancy counter of the slice: in a partitioned chunk nearly every row created at the same
+       * time lives in the same slice, so the lanes that got here together add once for all of them */
+      const unsigned grp = __match_any_sync(__activemask(), sl);
+      if ((int)lane_id() == __ffs(grp) - 1) atomicAdd(slice, (uint32_t)__popc(grp));
       h.key = x; h.meta = SMX_META_USED | SMX_INLINE_LOG;
       h.slots = 0; h.live = 0; h.c0 = 0; h.t0inv = 0; h.want = 0;
       *out = e; *hdr = h;
@@ -189,10 +202,19 @@ __device__ __forceinline__ int dir_find(const smx_view_t& V, uint32_t x, bool cr
  * column bucket: find-or-claim + value update (replaces rmap_probe/insert, :343-380, and the
  * arithmetic of set/incr/decr, :230,:241,:252)
  * ---------------------------------------------------------------------------------------- */
+/* fire-and-forget add on a GLOBAL address: the bucket pointer comes out of a header word, so the
+ * compiler would otherwise emit a generic ATOM (a round trip to L2) instead of a RED */
+__device__ __forceinline__ void red_add(uint32_t* vp, uint32_t v) {
+#ifdef SMX_HOSTSIM
+  *vp += v;
+#else
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(vp), "r"(v) : "memory");
+#endif
+}
 template <int OP>
 __device__ __forceinline__ void apply_value(uint32_t* vp, uint32_t v) {
-  if (OP == SMX_OP_INCR) atomicAdd(vp, v);
-  else if (OP == SMX_OP_DECR) atomicAdd(vp, 0u - v);
+  if (OP == SMX_OP_INCR) red_add(vp, v);
+  else if (OP == SMX_OP_DECR) red_add(vp, 0u - v);
   else *(volatile uint32_t*)vp = 0u;
 }
 
@@ -345,15 +367,20 @@ k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* lis
       const bool dup = act && (peers != (1u << lane));
       if (__any_sync(SMX_FULL, dup)) {
         vsum = 0u;
-        uint32_t best = 0xFFFFFFFFu;
+        uint32_t best = 0xFFFFFFFFu, best_nz = 0xFFFFFFFFu;
+        int leader_nz = -1;
         for (int src = 0; src < SMX_WARP; ++src) { /* segmented sum + arg-min of ord */
           const uint32_t tv = __shfl_sync(SMX_FULL, v, src);
           const uint32_t to = __shfl_sync(SMX_FULL, ord, src);
           if ((peers >> src) & 1u) {
             vsum += tv;
             if (to < best) { best = to; leader = src; }
+            if (tv != 0u && to < best_nz) { best_nz = to; leader_nz = src; }
           }
         }
+        /* column 0: t0 is the first op that makes the value non-zero, so a zero delta cannot lead */
+        if (pass == SMX_PASS_COL0 && leader_nz >= 0) leader = leader_nz;
+        if (OP == SMX_OP_SETZERO && pass == SMX_PASS_COL0) vsum = leader_nz >= 0 ? 1u : 0u; /* only "is any value non-zero" matters */
         lead = act && (leader == (int)lane);
       }
     }
@@ -387,6 +414,11 @@ k_upsert(smx_view_t V, smx_ops_t O, smx_lists_t S, int pass, const uint32_t* lis
  * K7: row growth (replaces smatrix_rmap_resize, :383-416)
  * ---------------------------------------------------------------------------------------- */
 #define SMX_SMEM_MIGRATE_LOG 8u /* new buckets up to 2^8 cells are built in shared memory by k_migrate */
+#define SMX_MID_SMEM_LOG 12u    /* ... and up to 2^12 cells by k_migrate_mid (one block per row) */
+
+/* Plan the growth of the queued rows: new size class, and where the new bucket comes from — the
+ * free list of that class (a bucket some other row vacated earlier) or fresh slab (an offset into
+ * this round's region, handed out by a warp scan + one atomic per warp). */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
   const uint32_t lane = lane_id();
@@ -394,18 +426,39 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
   const uint32_t n_up = (n_grow + (SMX_WARP - 1)) / SMX_WARP * SMX_WARP;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_up; j += stride) {
     const bool act = j < n_grow;
-    ull bytes = 0;
+    ull bytes = 0, recycled = 0;
     uint32_t entry = 0, newlog = 0, caplog = 0;
     if (act) {
       entry = S.grow[j];
       Hdr h = ld_hdr(V.dir + entry);
       caplog = h.meta & SMX_META_CAPLOG;
       const ull need = 2ull * ((ull)h.live + (ull)h.want); /* load factor <= 1/2 after growth */
-      /* small buckets grow x4 (fewer growth waves, less vacated memory), big ones x2 */
-      newlog = caplog + (caplog < 8u ? 2u : 1u);
+      /* small buckets grow x8 (4 -> 32 -> 256 cells: two re-placements on the way to a 256-cell
+       * bucket instead of three, and less vacated memory), big ones x2 */
+      newlog = caplog + (caplog < 8u ? 3u : 1u);
+      if (newlog > 8u && caplog < 8u) newlog = 8u;
       if (newlog < SMX_MIN_SLAB_LOG) newlog = SMX_MIN_SLAB_LOG;
       while ((1ull << newlog) < need && newlog < SMX_MAX_CAPLOG) ++newlog;
-      bytes = 8ull << newlog;
+      /* take a vacated bucket of that class if there is one: one atomic per group of lanes that
+       * want the same class (only pops run in this kernel; pushes happen in k_free_push) */
+      {
+        const unsigned grp = __match_any_sync(__activemask(), newlog);
+        const int leader = __ffs(grp) - 1;
+        const int cnt = __popc(grp), rank = __popc(grp & ((1u << lane) - 1u));
+        int base = 0;
+        if ((int)lane == leader) {
+          base = atomicSub(&V.ctl->free_cnt[newlog], cnt);
+          if (base < cnt) atomicAdd(&V.ctl->free_cnt[newlog], cnt - (base > 0 ? base : 0));
+        }
+        base = __shfl_sync(grp, base, leader);
+        const int at = base - 1 - rank;
+        if (at >= 0) recycled = (ull)V.ctl->free_stack[newlog][at];
+      }
+      bytes = recycled ? 0ull : (8ull << newlog);
+      if (caplog > SMX_INLINE_LOG) { /* the bucket this row vacates, per class (sizes the stacks) */
+        const unsigned grp = __match_any_sync(__activemask(), caplog);
+        if ((int)lane == __ffs(grp) - 1) atomicAdd(&V.ctl->grow_from[caplog], (uint32_t)__popc(grp));
+      }
     }
     ull incl = bytes; /* inclusive warp scan */
     for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
@@ -420,11 +473,35 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       smx_plan_t p;
       p.entry = entry;
       p.newlog = newlog;
-      p.off = base + incl - bytes;
+      p.off = recycled ? (SMX_PLAN_RECYCLED | recycled) : (base + incl - bytes);
       S.plan[j] = p;
+      if (recycled) agg_inc(&V.ctl->n_recycled);
       if (caplog >= SMX_BIG_LOG) S.big[agg_inc(&V.ctl->n_big)] = j;
-      if (newlog > SMX_SMEM_MIGRATE_LOG || caplog >= SMX_BIG_LOG) agg_inc64(&V.ctl->need_zero);
+      else if (caplog >= SMX_MID_LOG) S.mid[agg_inc(&V.ctl->n_mid)] = j;
+      /* fresh buckets that are filled in place (global CAS) need a zeroed region */
+      const bool in_place = caplog >= SMX_BIG_LOG ||
+                            (caplog >= SMX_MID_LOG ? newlog > SMX_MID_SMEM_LOG : newlog > SMX_SMEM_MIGRATE_LOG);
+      if (in_place && !recycled) agg_inc64(&V.ctl->need_zero);
     }
+  }
+}
+
+/* Recycle the buckets the planned rows are about to vacate: push their addresses on the stack of
+ * their size class.  Runs after k_grow_plan (which only pops) and before the re-placement kernels
+ * (the header still holds the old bucket); nothing pops again before the next round's plan. */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_free_push(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
+  const uint32_t lane = lane_id();
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_grow; j += gridDim.x * blockDim.x) {
+    const Hdr h = ld_hdr(V.dir + S.plan[j].entry);
+    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    if (caplog <= SMX_INLINE_LOG) continue;
+    const unsigned grp = __match_any_sync(__activemask(), caplog);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(&V.ctl->free_cnt[caplog], __popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    V.ctl->free_stack[caplog][base + __popc(grp & ((1u << lane) - 1u))] = h.slots;
   }
 }
 
@@ -443,6 +520,17 @@ __device__ __forceinline__ void place_cell(ull* base, uint32_t caplog, ull cell)
     }
   }
 }
+/* the same, into a bucket under construction in shared memory */
+__device__ __forceinline__ void place_cell_smem(ull* sb, uint32_t nsec, ull c) {
+  uint32_t sidx = smx_mix_col((uint32_t)c) & (nsec - 1u);
+  for (bool placed = false; !placed; sidx = (sidx + 1u) & (nsec - 1u))
+    for (int k = 0; k < 4 && !placed; ++k)
+      placed = (atomicCAS(&sb[4u * sidx + k], 0ull, c) == 0ull); /* same probe order as slot_upsert */
+}
+
+__device__ __forceinline__ ull* plan_bucket(const smx_plan_t& p, char* region) {
+  return (p.off & SMX_PLAN_RECYCLED) ? (ull*)(p.off & ~SMX_PLAN_RECYCLED) : (ull*)(region + p.off);
+}
 
 __device__ __forceinline__ void finish_growth(smx_row_t* e, const Hdr& h, ull* nb, uint32_t newlog) {
   e->slots = (ull)nb;
@@ -450,7 +538,7 @@ __device__ __forceinline__ void finish_growth(smx_row_t* e, const Hdr& h, ull* n
   e->meta = (h.meta & ~(SMX_META_CAPLOG | SMX_META_GROW)) | newlog;
 }
 
-/* one warp per growing row (old bucket < 2^SMX_BIG_LOG cells).  New buckets of up to
+/* one warp per growing row with a small old bucket (< 2^SMX_MID_LOG cells).  New buckets of up to
  * 2^SMX_SMEM_MIGRATE_LOG cells — the bulk of all growth events — are built in shared memory and
  * written out as whole lines (streaming); larger ones are filled in place with global CAS. */
 __global__ void __launch_bounds__(SMX_BLOCK)
@@ -465,9 +553,9 @@ k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
     smx_row_t* e = V.dir + p.entry;
     const Hdr h = ld_hdr(e);
     const uint32_t caplog = h.meta & SMX_META_CAPLOG;
-    if (caplog >= SMX_BIG_LOG) continue;
+    if (caplog >= SMX_MID_LOG) continue;
     ull* ob = (caplog == SMX_INLINE_LOG) ? (ull*)e->inl : (ull*)h.slots;
-    ull* nb = (ull*)(region + p.off);
+    ull* nb = plan_bucket(p, region);
     const uint32_t cap = 1u << caplog;
     if (p.newlog <= SMX_SMEM_MIGRATE_LOG) {
       ull* sb = sbuf[wib];
@@ -476,11 +564,7 @@ k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
       __syncwarp();
       for (uint32_t s0 = lane; s0 < cap; s0 += SMX_WARP) {
         const ull c = ob[s0];
-        if (c == 0ull) continue;
-        uint32_t sidx = smx_mix_col((uint32_t)c) & (nsec - 1u);
-        for (bool placed = false; !placed; sidx = (sidx + 1u) & (nsec - 1u))
-          for (int k = 0; k < 4 && !placed; ++k)
-            placed = (atomicCAS(&sb[4u * sidx + k], 0ull, c) == 0ull); /* same probe order as slot_upsert */
+        if (c != 0ull) place_cell_smem(sb, nsec, c);
       }
       __syncwarp();
       for (uint32_t i = lane; i < ncap; i += SMX_WARP) nb[i] = sb[i];
@@ -495,6 +579,44 @@ k_migrate(smx_view_t V, smx_lists_t S, uint32_t n_grow, char* region) {
   }
 }
 
+/* mid-size rows (old bucket 2^SMX_MID_LOG .. 2^(SMX_BIG_LOG-1) cells): one BLOCK per row.  New
+ * buckets of up to 2^SMX_MID_SMEM_LOG cells are built in shared memory (32 KB) and streamed out;
+ * larger ones are filled in place.  The vacated bucket is zeroed (it goes to the free list). */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_migrate_mid(smx_view_t V, smx_lists_t S, uint32_t n_mid, char* region) {
+  __shared__ ull sb[1u << SMX_MID_SMEM_LOG];
+  for (uint32_t j = blockIdx.x; j < n_mid; j += gridDim.x) {
+    const smx_plan_t p = S.plan[S.mid[j]];
+    smx_row_t* e = V.dir + p.entry;
+    const Hdr h = ld_hdr(e);
+    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    ull* ob = (ull*)h.slots;
+    ull* nb = plan_bucket(p, region);
+    const uint32_t cap = 1u << caplog;
+    if (p.newlog <= SMX_MID_SMEM_LOG) {
+      const uint32_t ncap = 1u << p.newlog, nsec = ncap >> 2;
+      for (uint32_t i = threadIdx.x; i < ncap; i += blockDim.x) sb[i] = 0ull;
+      __syncthreads();
+      for (uint32_t s0 = threadIdx.x; s0 < cap; s0 += blockDim.x) {
+        const ull c = ob[s0];
+        ob[s0] = 0ull;
+        if (c != 0ull) place_cell_smem(sb, nsec, c);
+      }
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < ncap; i += blockDim.x) nb[i] = sb[i];
+    } else {
+      for (uint32_t s0 = threadIdx.x; s0 < cap; s0 += blockDim.x) {
+        const ull c = ob[s0];
+        ob[s0] = 0ull;
+        if (c != 0ull) place_cell(nb, p.newlog, c);
+      }
+    }
+    __syncthreads(); /* every thread has read the header and finished with sb */
+    if (threadIdx.x == 0) finish_growth(e, h, nb, p.newlog);
+    __syncthreads();
+  }
+}
+
 /* big rows: the whole grid (x) re-places one row (y) */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_migrate_big(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region) {
@@ -503,10 +625,11 @@ k_migrate_big(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region) {
   const Hdr h = ld_hdr(e);
   const uint32_t caplog = h.meta & SMX_META_CAPLOG;
   ull* ob = (ull*)h.slots;
-  ull* nb = (ull*)(region + p.off);
+  ull* nb = plan_bucket(p, region);
   const ull cap = 1ull << caplog;
   for (ull s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (ull)gridDim.x * blockDim.x) {
     const ull c = ob[s];
+    ob[s] = 0ull; /* the vacated bucket goes to the free list zeroed */
     if (c != 0ull) place_cell(nb, p.newlog, c);
   }
 }
@@ -515,7 +638,7 @@ __global__ void k_migrate_big_finish(smx_view_t V, smx_lists_t S, uint32_t n_big
     const smx_plan_t p = S.plan[S.big[b]];
     smx_row_t* e = V.dir + p.entry;
     const Hdr h = ld_hdr(e);
-    finish_growth(e, h, (ull*)(region + p.off), p.newlog);
+    finish_growth(e, h, plan_bucket(p, region), p.newlog);
   }
 }
 
@@ -532,8 +655,9 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_dir_rehash(smx_view_t from, smx_v
     ld_sector(o, a);
     if (!((a[0] >> 32) & SMX_META_USED)) continue;
     ld_sector((const char*)o + 32, b);
-    ull q = smx_mix_row((uint32_t)a[0]) & mask;
-    for (;;) {
+    const ull home = smx_mix_row((uint32_t)a[0]) & mask;
+    for (ull step = 0;; ++step) { /* same probe order as dir_find */
+      const ull q = dir_probe_pos(home, step, mask);
       ull* dst = (ull*)(to.dir + q);
       if (atomicCAS(dst, 0ull, a[0]) == 0ull) {
         dst[1] = a[1]; dst[2] = a[2]; dst[3] = a[3];
@@ -541,7 +665,6 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_dir_rehash(smx_view_t from, smx_v
         atomicAdd(&to.ctl->slice_used[q >> to.slice_shift], 1u);
         break;
       }
-      q = (q + 1) & mask;
     }
     ++moved;
   }
@@ -1017,6 +1140,43 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_count_nnz(smx_view_t V) {
   if (lane_id() == 0 && acc) atomicAdd(&V.ctl->scratch, acc);
 }
 
+/* Distinct-row estimate of a chunk by linear counting (one streaming pass): bit hash(x) of a zeroed
+ * bitmap of m = 2^bits_log bits is set; with Z zero bits left, distinct ~ -m ln(Z / m).  Lets the host
+ * size the directory for a chunk of mostly NEW rows before the first round instead of discovering
+ * the overflow through a round that turns nearly every op away (replaces the reference's repeated
+ * stop-the-world doubling, src/smatrix.c:715-741). */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_sketch_set(const uint32_t* xs, uint32_t n, uint32_t* bitmap, uint32_t bits_log) {
+  const uint32_t mask = (uint32_t)((1ull << bits_log) - 1ull);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t h = smx_mix_owner(xs[i]) & mask;
+    const uint32_t bit = 1u << (h & 31u);
+    if (!(__ldcg(&bitmap[h >> 5]) & bit)) atomicOr(&bitmap[h >> 5], bit);
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_sketch_count(const uint32_t* bitmap, uint32_t bits_log, smx_ctl_t* ctl) {
+  const ull words = (1ull << bits_log) / 32ull;
+  ull zeros = 0;
+  for (ull w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (ull)gridDim.x * blockDim.x)
+    zeros += 32u - (uint32_t)__popc(bitmap[w]);
+  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) zeros += __shfl_xor_sync(SMX_FULL, zeros, d);
+  if (lane_id() == 0 && zeros) atomicAdd(&ctl->scratch, zeros);
+}
+
+/* bytes of slab buckets that rows currently own -> ctl->scratch (the denominator of slab / live) */
+__global__ void __launch_bounds__(SMX_BLOCK) k_live_bytes(smx_view_t V) {
+  ull acc = 0;
+  for (ull pos = blockIdx.x * blockDim.x + threadIdx.x; pos < V.dir_cap;
+       pos += (ull)gridDim.x * blockDim.x) {
+    Hdr h = ld_hdr(V.dir + pos);
+    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    if ((h.meta & SMX_META_USED) && caplog > SMX_INLINE_LOG) acc += 8ull << caplog;
+  }
+  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(SMX_FULL, acc, d);
+  if (lane_id() == 0 && acc) atomicAdd(&V.ctl->scratch, acc);
+}
+
 /* ------------------------------------------------------------------------------------------
  * synthetic streams and roofline probes
  * ---------------------------------------------------------------------------------------- */
@@ -1082,26 +1242,27 @@ k_probe_atomic(uint32_t* buf, ull n_words, ull accesses) {
  * ---------------------------------------------------------------------------------------- */
 #define SMX_MAX_PARTS 256
 /* part = owner rank (shift == 0xFFFFFFFF: mix_owner(x) % world) or directory slice
- * ((mix_row(x) & dir_mask) >> shift, `world` slices) */
-__device__ __forceinline__ uint32_t part_of(uint32_t x, uint32_t world, uint32_t dir_mask, uint32_t shift) {
-  return shift == 0xFFFFFFFFu ? smx_mix_owner(x) % world : (smx_mix_row(x) & dir_mask) >> shift;
+ * ((mix_row(x) & dir_mask) >> shift).  With split0 != 0 (slice mode, `world` = 2 * split0 parts)
+ * ops on column 0 go to parts split0 .. 2*split0-1: the partitioned chunk is then
+ * [other ops by slice | column-0 ops by slice], and the column-0 pass and the main pass each run
+ * over a dense range instead of scanning the whole chunk with most lanes idle. */
+__device__ __forceinline__ uint32_t part_of(uint32_t x, uint32_t y, uint32_t world, uint32_t dir_mask,
+                                            uint32_t shift, uint32_t split0) {
+  if (shift == 0xFFFFFFFFu) return smx_mix_owner(x) % world;
+  const uint32_t sl = (smx_mix_row(x) & dir_mask) >> shift;
+  return (split0 && y == 0u) ? sl + split0 : sl;
 }
-/* counts[part] += ops of that part; with ys, counts[world] += ops on column 0 (a chunk without any
- * lets the host skip the column-0 pass, which would only scan the chunk) */
+/* counts[part] += ops of that part */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t world, uint32_t dir_mask,
-                  uint32_t shift, ull* counts) {
-  __shared__ uint32_t hist[SMX_MAX_PARTS + 1];
-  for (uint32_t k = threadIdx.x; k <= world; k += blockDim.x) hist[k] = 0u;
+                  uint32_t shift, uint32_t split0, ull* counts) {
+  __shared__ uint32_t hist[SMX_MAX_PARTS];
+  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
-  uint32_t zeros = 0u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    atomicAdd(&hist[part_of(xs[i], world, dir_mask, shift)], 1u);
-    if (ys && ys[i] == 0u) ++zeros;
-  }
-  if (zeros) atomicAdd(&hist[world], zeros);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    atomicAdd(&hist[part_of(xs[i], split0 ? ys[i] : 1u, world, dir_mask, shift, split0)], 1u);
   __syncthreads();
-  for (uint32_t k = threadIdx.x; k <= world; k += blockDim.x)
+  for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
     if (hist[k]) atomicAdd(&counts[k], (ull)hist[k]);
 }
 /* Tiled partition: a block stages a tile of ops in shared memory sorted by part, reserves one
@@ -1118,7 +1279,7 @@ k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t w
 template <bool HAS_V, bool HAS_POS> /* shared memory only for what is used: 34 - 42 KB per block */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
-                    uint32_t world, uint32_t dir_mask, uint32_t shift, ull* cursors, uint32_t* oxs,
+                    uint32_t world, uint32_t dir_mask, uint32_t shift, uint32_t split0, ull* cursors, uint32_t* oxs,
                     uint32_t* oys, uint32_t* ovs, uint32_t* osrc, const uint32_t* src_in,
                     uint32_t* opos, const ull* dst_tab, uint32_t src_bias) {
   __shared__ uint32_t s_x[PART_TILE], s_y[PART_TILE], s_i[PART_TILE];
@@ -1154,7 +1315,7 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
     for (int k = 0; k < PART_ITEMS; ++k) {
       const uint32_t j = k * blockDim.x + threadIdx.x;
       if (j < cnt) {
-        const uint32_t p = part_of(x[k], world, dir_mask, shift);
+        const uint32_t p = part_of(x[k], y[k], world, dir_mask, shift, split0);
         pr[k] = (p << 16) | atomicAdd(&h[p], 1u);
       }
     }
@@ -1290,7 +1451,7 @@ extern "C" void smx_launch_upsert(smx_stream_t st, smx_view_t v, smx_ops_t ops, 
   ull want_blocks = ((ull)m + 4ull * SMX_BLOCK - 1) / (4ull * SMX_BLOCK);
   if (want_blocks < 1) want_blocks = 1;
   const uint32_t grid = (uint32_t)want_blocks;
-  const int pre = (preaggregate && !list && pass == SMX_PASS_EARLY && SMX_WARP > 1) ? 1 : 0;
+  const int pre = (preaggregate && !list && pass != SMX_PASS_LATE && SMX_WARP > 1) ? 1 : 0;
   if (op == SMX_OP_INCR) {
     auto k = k_upsert<SMX_OP_INCR>;
     SMX_LAUNCH(k, grid, SMX_BLOCK, st, v, ops, l, pass, list, m, pre);
@@ -1308,16 +1469,36 @@ extern "C" void smx_launch_grow_plan(smx_stream_t st, smx_view_t v, smx_lists_t 
   SMX_LAUNCH(k_grow_plan, grid_for(n_grow), SMX_BLOCK, st, v, l, n_grow);
 }
 
-extern "C" void smx_launch_migrate(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_grow,
-                                   uint32_t n_big, void* region) {
+extern "C" void smx_launch_free_push(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_grow) {
   if (!n_grow) return;
-  SMX_LAUNCH(k_migrate, grid_for((ull)n_grow * SMX_WARP), SMX_BLOCK, st, v, l, n_grow, (char*)region);
+  SMX_LAUNCH(k_free_push, grid_for(n_grow), SMX_BLOCK, st, v, l, n_grow);
+}
+
+extern "C" void smx_launch_migrate(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_grow,
+                                   uint32_t n_mid, uint32_t n_big, void* region) {
+  if (!n_grow) return;
+  if (n_grow > n_mid + n_big)
+    SMX_LAUNCH(k_migrate, grid_for((ull)n_grow * SMX_WARP), SMX_BLOCK, st, v, l, n_grow, (char*)region);
+  if (n_mid) {
+    const uint32_t cap = (uint32_t)smx_grid_blocks();
+    SMX_LAUNCH(k_migrate_mid, n_mid < cap ? n_mid : cap, SMX_BLOCK, st, v, l, n_mid, (char*)region);
+  }
   for (uint32_t first = 0; first < n_big; first += 32768u) {
     const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
     dim3 grid(SMX_WARP > 1 ? 64u : 2u, cnt, 1u);
     SMX_LAUNCH(k_migrate_big, grid, SMX_BLOCK, st, v, l, first, (char*)region);
   }
   if (n_big) SMX_LAUNCH(k_migrate_big_finish, grid_for(n_big), SMX_BLOCK, st, v, l, n_big, (char*)region);
+}
+
+extern "C" void smx_launch_sketch(smx_stream_t st, const uint32_t* xs, uint32_t n, uint32_t* bitmap,
+                                  uint32_t bits_log, smx_ctl_t* ctl) {
+  if (!n) return;
+  SMX_LAUNCH(k_sketch_set, grid_for(n), SMX_BLOCK, st, xs, n, bitmap, bits_log);
+  SMX_LAUNCH(k_sketch_count, grid_for((1ull << bits_log) / 32u), SMX_BLOCK, st, (const uint32_t*)bitmap, bits_log, ctl);
+}
+extern "C" void smx_launch_live_bytes(smx_stream_t st, smx_view_t v) {
+  SMX_LAUNCH(k_live_bytes, grid_for(v.dir_cap), SMX_BLOCK, st, v);
 }
 
 extern "C" void smx_launch_dir_rehash(smx_stream_t st, smx_view_t from, smx_view_t to) {
@@ -1485,13 +1666,13 @@ extern "C" void smx_launch_probe_atomic(smx_stream_t st, uint32_t* buf, uint64_t
 
 extern "C" void smx_launch_partition_count(smx_stream_t st, const uint32_t* xs, const uint32_t* ys,
                                            uint32_t n, uint32_t world, uint32_t dir_mask,
-                                           uint32_t shift, unsigned long long* counts) {
+                                           uint32_t shift, uint32_t split0, unsigned long long* counts) {
   if (!n) return;
-  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, ys, n, world, dir_mask, shift, counts);
+  SMX_LAUNCH(k_partition_count, grid_for(n), SMX_BLOCK, st, xs, ys, n, world, dir_mask, shift, split0, counts);
 }
 extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs, const uint32_t* ys,
                                              const uint32_t* vs, uint32_t n, uint32_t world,
-                                             uint32_t dir_mask, uint32_t shift,
+                                             uint32_t dir_mask, uint32_t shift, uint32_t split0,
                                              unsigned long long* cursors, uint32_t* oxs,
                                              uint32_t* oys, uint32_t* ovs, uint32_t* osrc,
                                              const uint32_t* src_in, uint32_t* opos,
@@ -1502,7 +1683,7 @@ extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs
 #define SMX_SCATTER(V, P)                                                                            \
   {                                                                                                  \
     auto k = k_partition_scatter<V, P>;                                                              \
-    SMX_LAUNCH(k, grid, SMX_BLOCK, st, xs, ys, vs, n, world, dir_mask, shift, cursors, oxs, oys, ovs, \
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, xs, ys, vs, n, world, dir_mask, shift, split0, cursors, oxs, oys, ovs, \
                osrc, src_in, opos, (const ull*)dst_tab, src_bias);                                   \
   }
   if (vs) SMX_SCATTER(true, false)
