@@ -77,6 +77,24 @@ void smatrix_b200_gen_c2_queries(smatrix_t* self, uint64_t seed_get, uint64_t se
                                  uint64_t first, size_t count, uint64_t n_build, uint32_t rows,
                                  uint32_t ycols, uint32_t* d_xs, uint32_t* d_ys);
 
+/* C3 (co-occurrence build, examples/cf_recommender.c:35-47) and C4 (Zipf row lengths) streams.
+ * d_thr: inverse-CDF thresholds thr[k] = floor(2^64 * CDF(k+1)) (device array of `items` / `kmax`
+ * uint64, last = 2^64 - 1), built by the caller (bench.py / oracle) so host and device draw from the
+ * same table.  C3 op i: basket i/64 holds 8 Zipf item ids; op i%64 = (ids[n], 0) or (ids[n], ids[i']).
+ * C3 query j: build op r % n_build, odd j with y moved out of range.  C4: lens[r] = draw(seed + r);
+ * op i (given d_offs = exclusive prefix of lens, rows + 1 entries) = (r * 2654435761, a column that
+ * is distinct inside row r and never 0, an odd value). */
+void smatrix_b200_gen_c3_ops(smatrix_t* self, uint64_t seed, uint64_t first, size_t count,
+                             const uint64_t* d_thr, uint32_t items, uint32_t* d_xs, uint32_t* d_ys);
+void smatrix_b200_gen_c3_queries(smatrix_t* self, uint64_t seed_get, uint64_t seed_build, uint64_t first,
+                                 size_t count, uint64_t n_build, const uint64_t* d_thr, uint32_t items,
+                                 uint32_t* d_xs, uint32_t* d_ys);
+void smatrix_b200_gen_c4_lens(smatrix_t* self, uint64_t seed, uint64_t first, size_t count,
+                              const uint64_t* d_thr, uint32_t kmax, uint32_t* d_lens);
+void smatrix_b200_gen_c4_ops(smatrix_t* self, uint64_t seed, uint64_t first, size_t count,
+                             const uint64_t* d_offs, uint32_t rows, uint32_t* d_xs, uint32_t* d_ys,
+                             uint32_t* d_vs);
+
 /* Roofline denominators measured in the same process: random 32 B-sector reads and random 4 B
  * atomic adds over a `footprint_bytes` device buffer (`accesses` of them, counter-based
  * addresses).  Return achieved accesses per second. `width` = bytes per access (4/8/16/32). */
@@ -118,6 +136,27 @@ void smatrix_b200_route_p2p(smatrix_t* self, const uint32_t* d_xs, const uint32_
 int   smatrix_b200_ipc_export(smatrix_t* self, void* dptr, unsigned char* handle64);
 void* smatrix_b200_ipc_open(smatrix_t* self, const unsigned char* handle64);
 void  smatrix_b200_ipc_close(smatrix_t* self, void* p);
+
+/* Device-level pieces of smatrix_getrow_batch, used by the multi-GPU router (an owner answers rows
+ * that another rank asked for and writes the pairs straight into that rank's buffer):
+ *   row_counts_batch  d_counts[i] = pairs row d_xs[i] would return (0 if the row does not exist)
+ *   scan_counts       d_offsets[0..n] = exclusive prefix of d_counts; returns the total
+ *   getrow_fill_at    row i's pairs go to d_pairs + 2 * d_offsets[i] (local or peer memory)
+ *   route_offsets     the requester's side: offset of row i goes to the owner that holds the row,
+ *                     h_tab[2][world] = { first routed position of every owner's run, address of
+ *                     that owner's offset array } */
+void     smatrix_b200_row_counts_batch(smatrix_t* self, const uint32_t* d_xs, size_t n, uint32_t* d_counts);
+uint64_t smatrix_b200_scan_counts(smatrix_t* self, const uint32_t* d_counts, size_t n, uint64_t* d_offsets);
+void     smatrix_b200_getrow_fill_at(smatrix_t* self, const uint32_t* d_xs, size_t n,
+                                     const uint64_t* d_offsets, uint32_t* d_pairs);
+void     smatrix_b200_route_offsets(smatrix_t* self, const uint64_t* d_offsets, const uint32_t* d_pos,
+                                    size_t n, uint32_t world, const uint64_t* h_tab);
+int  smatrix_b200_is_device_ptr(smatrix_t* self, const void* p);   /* device (or managed) memory? */
+/* peers in the SAME process (one thread per GPU) need no IPC: enable direct access to `peer_device` */
+int  smatrix_b200_enable_peer(smatrix_t* self, int peer_device);
+/* asynchronous copy (any direction) on side stream `lane` (0..2); lane_sync waits for that lane */
+void smatrix_b200_memcpy_async(smatrix_t* self, void* dst, const void* src, size_t bytes, int lane);
+void smatrix_b200_lane_sync(smatrix_t* self, int lane);
 
 /* smatrix_{incr,decr,set}_batch (op = 0, 1, 2) on DEVICE arrays whose "input order" is given
  * explicitly: d_ords[i] (unique, < 2^32 - 1) is op i's place in the sequential order the result

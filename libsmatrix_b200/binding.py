@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_SO = os.path.join(HERE, "lib", "libsmatrix_b200.so")
+# $SMATRIX_B200_LIB selects another build of the same library (A/B measurements of compile-time knobs)
+DEFAULT_SO = os.environ.get("SMATRIX_B200_LIB") or os.path.join(HERE, "lib", "libsmatrix_b200.so")
 
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
@@ -58,6 +59,14 @@ PROTOTYPES = {
                                        C.c_uint32, C.c_void_p, C.c_void_p]),
     "smatrix_b200_gen_c2_queries": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t,
                                            C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "smatrix_b200_gen_c3_ops": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_void_p]),
+    "smatrix_b200_gen_c3_queries": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint64,
+                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "smatrix_b200_gen_c4_lens": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.c_uint32,
+                                        C.c_void_p]),
+    "smatrix_b200_gen_c4_ops": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "smatrix_b200_probe_random_read": (C.c_double, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "smatrix_b200_probe_random_atomic": (C.c_double, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "smatrix_b200_partition2": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -70,6 +79,14 @@ PROTOTYPES = {
     "smatrix_b200_ipc_open": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "smatrix_b200_ipc_close": (None, [C.c_void_p, C.c_void_p]),
     "smatrix_b200_gather": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_b200_row_counts_batch": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_b200_scan_counts": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_b200_getrow_fill_at": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "smatrix_b200_route_offsets": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "smatrix_b200_enable_peer": (C.c_int, [C.c_void_p, C.c_int]),
+    "smatrix_b200_is_device_ptr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "smatrix_b200_memcpy_async": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "smatrix_b200_lane_sync": (None, [C.c_void_p, C.c_int]),
     "smatrix_b200_apply_ordered": (None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_size_t]),
     "smatrix_b200_owner": (C.c_uint32, [C.c_uint32, C.c_uint32]),
@@ -77,6 +94,26 @@ PROTOTYPES = {
                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
 }
+
+# include/smatrix_shard.h
+PROTOTYPES.update({
+    "smatrix_b200_shard_open": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "smatrix_b200_shard_close": (None, [C.c_void_p]),
+    "smatrix_b200_shard_local": (C.c_void_p, [C.c_void_p]),
+    "smatrix_b200_shard_rank": (C.c_int, [C.c_void_p]),
+    "smatrix_b200_shard_world": (C.c_int, [C.c_void_p]),
+    "smatrix_b200_shard_reserve": (None, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "smatrix_b200_shard_incr_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "smatrix_b200_shard_decr_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "smatrix_b200_shard_set_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_b200_shard_get_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_b200_shard_rowlen_batch": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_b200_shard_getrow_batch": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                    C.c_uint64]),
+    "smatrix_b200_shard_barrier": (None, [C.c_void_p]),
+    "smatrix_b200_shard_sum": (C.c_uint64, [C.c_void_p, C.c_uint64]),
+    "smatrix_b200_shard_max": (C.c_uint64, [C.c_void_p, C.c_uint64]),
+})
 
 STAT = {"rows": 0, "nnz": 1, "dir_cap": 2, "slab_bytes": 3, "device_bytes": 4, "launches": 5,
         "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9, "ns_partition": 10, "ns_upsert": 11,

@@ -17,8 +17,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SO = os.path.join(LIBDIR, "libsmatrix_b200.so")
-STATIC = os.path.join(LIBDIR, "smatrix-static.a")
+SUFFIX = os.environ.get("SMX_LIB_SUFFIX", "")     # A/B builds of compile-time knobs: lib/libsmatrix_b200<suffix>.so
+SO = os.path.join(LIBDIR, f"libsmatrix_b200{SUFFIX}.so")
+STATIC = os.path.join(LIBDIR, f"smatrix-static{SUFFIX}.a")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = shutil.which("nvcc") or os.path.join(CUDA_HOME, "bin", "nvcc")
 
@@ -38,10 +39,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     cu = os.path.join(CSRC, "smx_kernels.cu")
     hc = os.path.join(CSRC, "smx_host.c")
+    rc = os.path.join(CSRC, "smx_router.c")
     hdrs = [os.path.join(CSRC, "smx_internal.h")] + [
-        os.path.join(HERE, "..", "include", h) for h in ("smatrix.h", "smatrix_batch.h", "smatrix_b200.h")]
-    cu_o = os.path.join(LIBDIR, "smx_kernels.o")
-    hc_o = os.path.join(LIBDIR, "smx_host.o")
+        os.path.join(HERE, "..", "include", h) for h in ("smatrix.h", "smatrix_batch.h", "smatrix_b200.h",
+                                                         "smatrix_shard.h")]
+    cu_o = os.path.join(LIBDIR, f"smx_kernels{SUFFIX}.o")
+    hc_o = os.path.join(LIBDIR, f"smx_host{SUFFIX}.o")
+    rc_o = os.path.join(LIBDIR, f"smx_router{SUFFIX}.o")
     log = []
     if force or _stale(cu_o, [cu] + hdrs):
         r = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", cu, "-o", cu_o], capture_output=True, text=True)
@@ -57,16 +61,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("gcc failed")
-    if force or _stale(SO, [cu_o, hc_o]):
+    if force or _stale(rc_o, [rc] + hdrs):
+        r = subprocess.run(["gcc"] + GCC_FLAGS + ["-c", rc, "-o", rc_o], capture_output=True, text=True)
+        log.append(r.stderr)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed")
+    if force or _stale(SO, [cu_o, hc_o, rc_o]):
         # nvcc links the static CUDA runtime, so the .so only needs libcuda from the driver
-        r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", cu_o, hc_o,
+        r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", cu_o, hc_o, rc_o,
                             "-o", SO, "-Xlinker", "--no-undefined", "-Xlinker", "-Bsymbolic",
-                            "-Xlinker", "--exclude-libs,ALL", "-lpthread"],
+                            "-Xlinker", "--exclude-libs,ALL", "-lpthread", "-lrt"],
                            capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-        subprocess.run(["ar", "crs", STATIC, cu_o, hc_o], check=True)
+        subprocess.run(["ar", "crs", STATIC, cu_o, hc_o, rc_o], check=True)
     if verbose:
         sys.stderr.write("".join(log))
     return SO

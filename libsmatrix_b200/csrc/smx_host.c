@@ -325,15 +325,15 @@ static void ensure_free_stacks(smatrix_t* s) {
     const int32_t have = s->h_ctl->free_cnt[c] > 0 ? s->h_ctl->free_cnt[c] : 0;
     const uint64_t need = (uint64_t)have + incoming;
     if (need <= s->free_cap[c]) continue;
-    uint64_t cap = s->free_cap[c] ? s->free_cap[c] : 256;
-    while (cap < need) cap *= 2;
+    uint64_t cap = s->free_cap[c] ? s->free_cap[c] : 1024;
+    while (cap < need) cap *= 4;
     if (cap > 0x7FFFFFFFull) smx_die("free list of class %u too long", c);
-    unsigned long long* nb = (unsigned long long*)dmalloc(s, (size_t)cap * 8);
+    /* carved from the slab like the buckets themselves (cudaMalloc costs milliseconds on these hosts);
+     * a replaced stack is simply abandoned: x4 growth keeps that below a third of the final one */
+    unsigned long long* nb = (unsigned long long*)slab_reserve(s, (size_t)cap * 8);
     if (have) CK(cudaMemcpyAsync(nb, s->free_ptr[c], (size_t)have * 8, cudaMemcpyDeviceToDevice, s->stream));
-    CK(cudaMemcpyAsync(&s->d_ctl->free_stack[c], &nb, sizeof nb, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream)); /* &nb is a stack variable; the old stack may be freed now */
-    if (s->free_ptr[c]) CK(cudaFree(s->free_ptr[c]));
-    s->free_ptr[c] = nb;
+    s->free_ptr[c] = nb; /* a field of the handle: stays valid while the copy below is in flight */
+    CK(cudaMemcpyAsync(&s->d_ctl->free_stack[c], &s->free_ptr[c], sizeof nb, cudaMemcpyHostToDevice, s->stream));
     s->free_cap[c] = (uint32_t)cap;
   }
 }
@@ -1444,8 +1444,6 @@ void smatrix_close(smatrix_t* s) {
     scratch_free(s, s->lists.grow); scratch_free(s, s->lists.t0rows); scratch_free(s, s->lists.plan);
     scratch_free(s, s->lists.big); scratch_free(s, s->lists.mid);
   }
-  for (uint32_t c = 0; c < SMX_CLASSES; c++)
-    if (s->free_ptr[c]) cudaFree(s->free_ptr[c]);
   scratch_free(s, s->addrs);
   if (s->part_cap)
     for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
@@ -1615,6 +1613,41 @@ void smatrix_b200_gen_c2_queries(smatrix_t* s, uint64_t seed_get, uint64_t seed_
   leave(s);
 }
 
+void smatrix_b200_gen_c3_ops(smatrix_t* s, uint64_t seed, uint64_t first, size_t count,
+                             const uint64_t* d_thr, uint32_t items, uint32_t* d_xs, uint32_t* d_ys) {
+  enter(s);
+  smx_launch_gen_c3_ops(s->stream, seed, first, count, d_thr, items, d_xs, d_ys);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+void smatrix_b200_gen_c3_queries(smatrix_t* s, uint64_t seed_get, uint64_t seed_build, uint64_t first,
+                                 size_t count, uint64_t n_build, const uint64_t* d_thr, uint32_t items,
+                                 uint32_t* d_xs, uint32_t* d_ys) {
+  enter(s);
+  smx_launch_gen_c3_queries(s->stream, seed_get, seed_build, first, count, n_build, d_thr, items, d_xs, d_ys);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+void smatrix_b200_gen_c4_lens(smatrix_t* s, uint64_t seed, uint64_t first, size_t count,
+                              const uint64_t* d_thr, uint32_t kmax, uint32_t* d_lens) {
+  enter(s);
+  smx_launch_gen_c4_lens(s->stream, seed, first, count, d_thr, kmax, d_lens);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+void smatrix_b200_gen_c4_ops(smatrix_t* s, uint64_t seed, uint64_t first, size_t count,
+                             const uint64_t* d_offs, uint32_t rows, uint32_t* d_xs, uint32_t* d_ys,
+                             uint32_t* d_vs) {
+  enter(s);
+  smx_launch_gen_c4_ops(s->stream, seed, first, count, d_offs, rows, d_xs, d_ys, d_vs);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
 double smatrix_b200_probe_random_read(smatrix_t* s, size_t footprint, size_t accesses, int width) {
   if (width != 4 && width != 8 && width != 16 && width != 32) return 0.0;
   enter(s);
@@ -1728,6 +1761,109 @@ void smatrix_b200_gather(smatrix_t* s, uint32_t* d_out, const uint32_t* d_vals, 
   smx_launch_gather(s->stream, d_out, d_vals, d_pos, (uint32_t)n);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+/* ---- device-level getrow pieces for the multi-GPU router (include/smatrix_b200.h) ---- */
+void smatrix_b200_row_counts_batch(smatrix_t* s, const uint32_t* d_xs, size_t n, uint32_t* d_counts) {
+  if (n == 0) return;
+  if (n >= 0xFFFFFFFFull) smx_die("row_counts: batch too large");
+  enter(s);
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, (uint32_t)n, d_counts, NULL, NULL);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+uint64_t smatrix_b200_scan_counts(smatrix_t* s, const uint32_t* d_counts, size_t n, uint64_t* d_offsets) {
+  if (n >= 0xFFFFFFFFull) smx_die("scan_counts: batch too large");
+  enter(s);
+  ensure_tmp(s, 0, ((size_t)smx_scan_scratch_items((uint32_t)n) + 2) * 8);
+  smx_launch_scan(s->stream, d_counts, (uint32_t)n, 0, d_offsets, s->d_tmp64);
+  s->n_launches += 3;
+  CK(cudaMemcpyAsync(&s->h_small[32], d_offsets + n, 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  uint64_t total = 0;
+  memcpy(&total, &s->h_small[32], 8);
+  leave(s);
+  return total;
+}
+
+void smatrix_b200_getrow_fill_at(smatrix_t* s, const uint32_t* d_xs, size_t n, const uint64_t* d_offsets,
+                                 uint32_t* d_pairs) {
+  if (n == 0) return;
+  if (n >= 0xFFFFFFFFull) smx_die("getrow_fill_at: batch too large");
+  enter(s);
+  const uint32_t nn = (uint32_t)n;
+  ensure_tmp(s, (size_t)nn * 4, 0);
+  if ((size_t)nn * 8 + 64 > s->d_big_bytes) {
+    if (s->d_big) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_big); }
+    s->d_big_bytes = (size_t)nn * 8 + 4096;
+    s->d_big = (uint32_t*)dmalloc(s, s->d_big_bytes);
+  }
+  s->d_cursors = s->d_big + nn;
+  CK(cudaMemsetAsync(s->d_cursors, 0, (size_t)nn * 4 + 8, s->stream));
+  uint32_t* d_nbig = s->d_cursors + nn;
+  /* rows with a big bucket are compacted by the whole grid: find them first */
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, nn, s->d_tmp, s->d_big, d_nbig);
+  CK(cudaMemcpyAsync(&s->h_small[34], d_nbig, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, d_offsets, 0, d_pairs, s->d_big, s->h_small[34], s->d_cursors);
+  s->n_launches += 2;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+void smatrix_b200_route_offsets(smatrix_t* s, const uint64_t* d_offsets, const uint32_t* d_pos, size_t n,
+                                uint32_t world, const uint64_t* h_tab) {
+  if (world == 0 || world > 64) smx_die("route: world size must be 1..64");
+  if (n == 0) return;
+  if (n >= 0xFFFFFFFFull) smx_die("route_offsets: batch too large");
+  enter(s);
+  ensure_tmp(s, 0, (2 * 64 + 5 * 64) * 8);
+  unsigned long long* d_tab = (unsigned long long*)s->d_tmp64 + 128;
+  CK(cudaMemcpyAsync(d_tab, h_tab, 2 * (size_t)world * 8, cudaMemcpyHostToDevice, s->stream));
+  smx_launch_route_offsets(s->stream, d_offsets, d_pos, (uint32_t)n, world, d_tab);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+int smatrix_b200_is_device_ptr(smatrix_t* s, const void* p) {
+  enter(s);
+  const int r = is_device_ptr(p);
+  leave(s);
+  return r;
+}
+
+int smatrix_b200_enable_peer(smatrix_t* s, int peer_device) {
+  if (peer_device == s->device) return 0;
+  enter(s);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  (void)cudaGetLastError(); /* "already enabled" is fine */
+  leave(s);
+  return (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) ? 0 : -1;
+}
+
+/* asynchronous copies on one of the side streams (lane 0..2), for callers that overlap uploads and
+ * downloads with work on the main stream; smatrix_b200_lane_sync waits for a lane */
+static cudaStream_t lane_stream(smatrix_t* s, int lane) {
+  return lane == 0 ? s->copy_stream : s->read_stream[(lane - 1) & 1];
+}
+void smatrix_b200_memcpy_async(smatrix_t* s, void* dst, const void* src, size_t bytes, int lane) {
+  if (!bytes) return;
+  enter(s);
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, lane_stream(s, lane)));
+  leave(s);
+}
+void smatrix_b200_lane_sync(smatrix_t* s, int lane) {
+  enter(s);
+  CK(cudaStreamSynchronize(lane_stream(s, lane)));
   CK(cudaGetLastError());
   leave(s);
 }

@@ -174,6 +174,15 @@ void smx_launch_gen_c2_ops(smx_stream_t stream, uint64_t seed, uint64_t first, u
 void smx_launch_gen_c2_queries(smx_stream_t stream, uint64_t seed_get, uint64_t seed_build,
                                uint64_t first, uint64_t count, uint64_t n_build, uint32_t rows,
                                uint32_t ycols, uint32_t* xs, uint32_t* ys);
+void smx_launch_gen_c3_ops(smx_stream_t stream, uint64_t seed, uint64_t first, uint64_t count,
+                           const uint64_t* thr, uint32_t items, uint32_t* xs, uint32_t* ys);
+void smx_launch_gen_c3_queries(smx_stream_t stream, uint64_t seed_get, uint64_t seed_build,
+                               uint64_t first, uint64_t count, uint64_t n_build, const uint64_t* thr,
+                               uint32_t items, uint32_t* xs, uint32_t* ys);
+void smx_launch_gen_c4_lens(smx_stream_t stream, uint64_t seed, uint64_t first, uint64_t count,
+                            const uint64_t* thr, uint32_t kmax, uint32_t* lens);
+void smx_launch_gen_c4_ops(smx_stream_t stream, uint64_t seed, uint64_t first, uint64_t count,
+                           const uint64_t* offs, uint32_t rows, uint32_t* xs, uint32_t* ys, uint32_t* vs);
 void smx_launch_probe_read(smx_stream_t stream, const void* buf, uint64_t n_units, uint64_t accesses,
                            int width, smx_ctl_t* ctl);
 void smx_launch_probe_atomic(smx_stream_t stream, uint32_t* buf, uint64_t n_words, uint64_t accesses);
@@ -196,6 +205,8 @@ void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const
                                   uint32_t src_bias /* added to every osrc value */);
 void smx_launch_gather(smx_stream_t stream, uint32_t* out, const uint32_t* vals, const uint32_t* pos,
                        uint32_t n);
+void smx_launch_route_offsets(smx_stream_t stream, const uint64_t* offs, const uint32_t* pos, uint32_t n,
+                             uint32_t world, const unsigned long long* tab /* device: [2][world] */);
 uint32_t smx_scan_scratch_items(uint32_t n); /* number of uint64 block sums smx_launch_scan needs */
 int smx_grid_blocks(void);                   /* resident grid size used by the streaming kernels */
 

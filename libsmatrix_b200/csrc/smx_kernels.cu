@@ -81,19 +81,33 @@ __host__ __device__ __forceinline__ ull smx_splitmix64(ull z) {
   return z ^ (z >> 31);
 }
 
-/* One 32-byte sector with a single 256-bit load that bypasses L1 (coherent at L2).  L2::64B: a
- * miss fetches 64 bytes from DRAM instead of the whole 128-byte line (SASS LDG.E.ENL2.LTC64B.256);
- * the random-touch rate is the same, the DRAM bytes per probe halve (profiles/r2_summary.md). */
-__device__ __forceinline__ void ld_sector(const void* p, ull c[4]) {
+/* One 32-byte sector with a single 256-bit load that bypasses L1 (coherent at L2).  With the
+ * L2::64B hint a miss fetches 64 bytes from DRAM instead of the whole 128-byte line (SASS
+ * LDG.E.ENL2.LTC64B.256): the random-touch rate is the same, the DRAM bytes per probe halve.
+ * Column buckets use the hint (the next sector in probe order is in the same 64 bytes half of the
+ * time); directory entries do not — an entry is 64 bytes and the probe order visits BOTH entries of
+ * a 128-byte line before moving on, so the full-line fetch makes the second probe free. */
+#ifndef SMX_CELL_FETCH64
+#define SMX_CELL_FETCH64 1
+#endif
+#ifndef SMX_HDR_FETCH64
+#define SMX_HDR_FETCH64 0
+#endif
+template <bool FETCH64>
+__device__ __forceinline__ void ld_sector_t(const void* p, ull c[4]) {
 #ifdef SMX_HOSTSIM
   memcpy(c, p, 32);
 #else
-  asm volatile("ld.global.cg.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3])
-               : "l"(p)
-               : "memory");
+  if (FETCH64)
+    asm volatile("ld.global.cg.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3]) : "l"(p) : "memory");
+  else
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3]) : "l"(p) : "memory");
 #endif
 }
+__device__ __forceinline__ void ld_sector(const void* p, ull c[4]) { ld_sector_t<SMX_CELL_FETCH64 != 0>(p, c); }
+__device__ __forceinline__ void ld_hsector(const void* p, ull c[4]) { ld_sector_t<SMX_HDR_FETCH64 != 0>(p, c); }
 
 struct Hdr {
   uint32_t key, meta;
@@ -102,7 +116,7 @@ struct Hdr {
 };
 __device__ __forceinline__ Hdr ld_hdr(const smx_row_t* e) {
   ull c[4];
-  ld_sector(e, c);
+  ld_hsector(e, c);
   Hdr h;
   h.key = (uint32_t)c[0];
   h.meta = (uint32_t)(c[0] >> 32);
@@ -652,9 +666,9 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_dir_rehash(smx_view_t from, smx_v
        pos += (ull)gridDim.x * blockDim.x) {
     const smx_row_t* o = from.dir + pos;
     ull a[4], b[4];
-    ld_sector(o, a);
+    ld_hsector(o, a);
     if (!((a[0] >> 32) & SMX_META_USED)) continue;
-    ld_sector((const char*)o + 32, b);
+    ld_hsector((const char*)o + 32, b);
     const ull home = smx_mix_row((uint32_t)a[0]) & mask;
     for (ull step = 0;; ++step) { /* same probe order as dir_find */
       const ull q = dir_probe_pos(home, step, mask);
@@ -1206,6 +1220,83 @@ k_gen_c2_queries(ull seed_get, ull seed_build, ull first, ull count, ull n_build
   }
 }
 
+/* ---- C3 (co-occurrence build, examples/cf_recommender.c:35-47) and C4 (Zipf row lengths) --------
+ * Both draw from a discrete distribution by inverse CDF: thr[k] = floor(2^64 * CDF(k+1)), k = 0..m-1,
+ * built once on the host; draw(r) = 1 + #{k : thr[k] < r} — a binary search that the CPU baseline's
+ * generator and the device do on the same table with the same counter-based r, so they see the same
+ * stream. */
+__host__ __device__ __forceinline__ uint32_t smx_draw(const ull* thr, uint32_t m, ull r) {
+  uint32_t lo = 0, hi = m - 1u; /* thr[m-1] = 2^64 - 1: the answer is in [0, m-1] */
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (thr[mid] < r) lo = mid + 1u; else hi = mid;
+  }
+  return lo + 1u;
+}
+/* op i of the C3 stream: basket b = i / 64 holds 8 item ids; op k = i % 64 belongs to n = k / 8:
+ * j = k % 8 == 0 -> (ids[n], 0), else (ids[n], ids[i']) with i' = the (j-1)-th index != n */
+__host__ __device__ __forceinline__ void smx_c3_op(ull seed, ull i, const ull* thr, uint32_t items,
+                                                    uint32_t* x, uint32_t* y) {
+  const ull b = i >> 6;
+  const uint32_t k = (uint32_t)(i & 63ull), n = k >> 3, j = k & 7u;
+  *x = smx_draw(thr, items, smx_splitmix64(seed + b * 8ull + n));
+  if (j == 0u) { *y = 0u; return; }
+  const uint32_t other = (j - 1u < n) ? j - 1u : j;
+  *y = smx_draw(thr, items, smx_splitmix64(seed + b * 8ull + other));
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gen_c3_ops(ull seed, ull first, ull count, const ull* thr, uint32_t items, uint32_t* xs, uint32_t* ys) {
+  for (ull i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (ull)gridDim.x * blockDim.x)
+    smx_c3_op(seed, first + i, thr, items, &xs[i], &ys[i]);
+}
+/* C3 queries: query j re-generates build op k = r % n_build; odd j moves y out of the item range */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gen_c3_queries(ull seed_get, ull seed_build, ull first, ull count, ull n_build, const ull* thr,
+                 uint32_t items, uint32_t* xs, uint32_t* ys) {
+  for (ull i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (ull)gridDim.x * blockDim.x) {
+    const ull j = first + i;
+    uint32_t x, y;
+    smx_c3_op(seed_build, smx_splitmix64(seed_get + j) % n_build, thr, items, &x, &y);
+    if (j & 1ull) y += items + 1u;
+    xs[i] = x;
+    ys[i] = y;
+  }
+}
+/* C4: row r has len[r] = draw(thr, kmax, splitmix64(seed + r)) columns */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gen_c4_lens(ull seed, ull first, ull count, const ull* thr, uint32_t kmax, uint32_t* lens) {
+  for (ull i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (ull)gridDim.x * blockDim.x)
+    lens[i] = smx_draw(thr, kmax, smx_splitmix64(seed + first + i));
+}
+/* murmur3 finaliser: a bijection on uint32 with f(0) = 0, so distinct non-zero inputs give distinct
+ * non-zero columns */
+__host__ __device__ __forceinline__ uint32_t smx_fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+/* op i of the C4 build: row r = the row whose range [offs[r], offs[r+1]) holds i, j = i - offs[r];
+ * x = r * 2654435761, y = fmix32(j + salt_r) (salt_r in [1, 2^32 - 2^21]: j + salt never wraps and
+ * is never 0), v = an odd 32-bit number */
+__host__ __device__ __forceinline__ void smx_c4_op(ull seed, ull i, const ull* offs, uint32_t rows,
+                                                    uint32_t* x, uint32_t* y, uint32_t* v) {
+  uint32_t lo = 0, hi = rows - 1u; /* last r with offs[r] <= i */
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+    if (offs[mid] <= i) lo = mid; else hi = mid - 1u;
+  }
+  const uint32_t j = (uint32_t)(i - offs[lo]);
+  const uint32_t salt = 1u + (uint32_t)(smx_splitmix64((seed ^ 0xC4C4C4C4ull) + lo) % 0xFFE00000ull);
+  *x = lo * 2654435761u;
+  *y = smx_fmix32(j + salt);
+  *v = (uint32_t)(smx_splitmix64(seed + 0x5EED0000ull + i) >> 32) | 1u;
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gen_c4_ops(ull seed, ull first, ull count, const ull* offs, uint32_t rows, uint32_t* xs, uint32_t* ys,
+             uint32_t* vs) {
+  for (ull i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (ull)gridDim.x * blockDim.x)
+    smx_c4_op(seed, first + i, offs, rows, &xs[i], &ys[i], &vs[i]);
+}
+
 /* random reads of `width` bytes at width-aligned addresses; 4 independent loads in flight */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_probe_read(const char* buf, ull n_units, ull accesses, int width, smx_ctl_t* ctl) {
@@ -1217,7 +1308,7 @@ k_probe_read(const char* buf, ull n_units, ull accesses, int width, smx_ctl_t* c
     const char* p = buf + u * (ull)width;
     if (width == 32) {
       ull c[4];
-      ld_sector(p, c);
+      ld_sector_t<false>(p, c);
       acc ^= c[0] ^ c[1] ^ c[2] ^ c[3];
     } else if (width == 16) {
       const ull* q = (const ull*)p;
@@ -1418,6 +1509,22 @@ __global__ void __launch_bounds__(SMX_BLOCK)
 k_gather(uint32_t* out, const uint32_t* vals, const uint32_t* pos, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = vals[pos[i]];
+}
+
+/* getrow across ranks: the requester hands every routed row its output offset.  pos[i] = routed
+ * position of my row i (runs by owner, run o starts at tab[o]); the offset goes to owner o's array
+ * (address tab[world + o], peer memory) at the row's index inside the run. */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_route_offsets(const ull* offs, const uint32_t* pos, uint32_t n, uint32_t world, const ull* tab) {
+  __shared__ ull s_tab[2 * 64];
+  for (uint32_t k = threadIdx.x; k < 2u * world; k += blockDim.x) s_tab[k] = tab[k];
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const ull p = pos[i];
+    uint32_t o = 0;
+    while (o + 1u < world && s_tab[o + 1u] <= p) ++o; /* runs may be empty: take the LAST run starting at or before p */
+    ((ull*)s_tab[world + o])[p - s_tab[o]] = offs[i];
+  }
 }
 
 /* ==========================================================================================
@@ -1654,6 +1761,33 @@ extern "C" void smx_launch_gen_c2_queries(smx_stream_t st, uint64_t seed_get, ui
              (ull)first, (ull)count, (ull)n_build, rows, ycols, xs, ys);
 }
 
+extern "C" void smx_launch_gen_c3_ops(smx_stream_t st, uint64_t seed, uint64_t first, uint64_t count,
+                                      const uint64_t* thr, uint32_t items, uint32_t* xs, uint32_t* ys) {
+  if (!count) return;
+  SMX_LAUNCH(k_gen_c3_ops, grid_for(count), SMX_BLOCK, st, (ull)seed, (ull)first, (ull)count,
+             (const ull*)thr, items, xs, ys);
+}
+extern "C" void smx_launch_gen_c3_queries(smx_stream_t st, uint64_t seed_get, uint64_t seed_build,
+                                          uint64_t first, uint64_t count, uint64_t n_build,
+                                          const uint64_t* thr, uint32_t items, uint32_t* xs, uint32_t* ys) {
+  if (!count) return;
+  SMX_LAUNCH(k_gen_c3_queries, grid_for(count), SMX_BLOCK, st, (ull)seed_get, (ull)seed_build, (ull)first,
+             (ull)count, (ull)n_build, (const ull*)thr, items, xs, ys);
+}
+extern "C" void smx_launch_gen_c4_lens(smx_stream_t st, uint64_t seed, uint64_t first, uint64_t count,
+                                       const uint64_t* thr, uint32_t kmax, uint32_t* lens) {
+  if (!count) return;
+  SMX_LAUNCH(k_gen_c4_lens, grid_for(count), SMX_BLOCK, st, (ull)seed, (ull)first, (ull)count,
+             (const ull*)thr, kmax, lens);
+}
+extern "C" void smx_launch_gen_c4_ops(smx_stream_t st, uint64_t seed, uint64_t first, uint64_t count,
+                                      const uint64_t* offs, uint32_t rows, uint32_t* xs, uint32_t* ys,
+                                      uint32_t* vs) {
+  if (!count) return;
+  SMX_LAUNCH(k_gen_c4_ops, grid_for(count), SMX_BLOCK, st, (ull)seed, (ull)first, (ull)count,
+             (const ull*)offs, rows, xs, ys, vs);
+}
+
 extern "C" void smx_launch_probe_read(smx_stream_t st, const void* buf, uint64_t n_units,
                                       uint64_t accesses, int width, smx_ctl_t* ctl) {
   SMX_LAUNCH(k_probe_read, grid_for(accesses), SMX_BLOCK, st, (const char*)buf, (ull)n_units,
@@ -1695,6 +1829,12 @@ extern "C" void smx_launch_gather(smx_stream_t st, uint32_t* out, const uint32_t
                                   const uint32_t* pos, uint32_t n) {
   if (!n) return;
   SMX_LAUNCH(k_gather, grid_for(n), SMX_BLOCK, st, out, vals, pos, n);
+}
+
+extern "C" void smx_launch_route_offsets(smx_stream_t st, const uint64_t* offs, const uint32_t* pos,
+                                         uint32_t n, uint32_t world, const unsigned long long* tab) {
+  if (!n) return;
+  SMX_LAUNCH(k_route_offsets, grid_for(n), SMX_BLOCK, st, (const ull*)offs, pos, n, world, (const ull*)tab);
 }
 
 extern "C" uint32_t smx_owner_hash(uint32_t x) { return smx_mix_owner(x); }

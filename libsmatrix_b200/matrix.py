@@ -47,6 +47,13 @@ class SparseMatrix:
             # src/smatrix_jni.c:61-62 turns a NULL handle into IllegalArgumentException
             raise ValueError("smatrix_open() failed")
 
+    @classmethod
+    def _borrow(cls, lib, handle):
+        """Wrap a handle somebody else owns (the C router's local shard); close() is the owner's job."""
+        m = cls.__new__(cls)
+        m._lib, m._h, m.filename = lib, handle, None
+        return m
+
     # ---- handle plumbing -------------------------------------------------------------------
     def _handle(self):
         if not self._h:
@@ -269,6 +276,19 @@ class SparseMatrix:
                        d_ys: int):
         self._lib.smatrix_b200_gen_c2_queries(self._handle(), seed_get, seed_build, first, count,
                                               n_build, rows, ycols, d_xs, d_ys)
+
+    def gen_c3_ops(self, seed, first, count, d_thr: int, items: int, d_xs: int, d_ys: int):
+        self._lib.smatrix_b200_gen_c3_ops(self._handle(), seed, first, count, d_thr, items, d_xs, d_ys)
+
+    def gen_c3_queries(self, seed_get, seed_build, first, count, n_build, d_thr: int, items: int, d_xs: int, d_ys: int):
+        self._lib.smatrix_b200_gen_c3_queries(self._handle(), seed_get, seed_build, first, count, n_build, d_thr,
+                                              items, d_xs, d_ys)
+
+    def gen_c4_lens(self, seed, first, count, d_thr: int, kmax: int, d_lens: int):
+        self._lib.smatrix_b200_gen_c4_lens(self._handle(), seed, first, count, d_thr, kmax, d_lens)
+
+    def gen_c4_ops(self, seed, first, count, d_offs: int, rows: int, d_xs: int, d_ys: int, d_vs: int):
+        self._lib.smatrix_b200_gen_c4_ops(self._handle(), seed, first, count, d_offs, rows, d_xs, d_ys, d_vs)
 
     def probe_random_read(self, footprint_bytes: int, accesses: int, width: int = 32) -> float:
         return float(self._lib.smatrix_b200_probe_random_read(self._handle(), footprint_bytes,

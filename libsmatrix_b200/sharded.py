@@ -1,4 +1,17 @@
-"""ShardedSparseMatrix — one matrix row-sharded over the GPUs of one box.
+"""One matrix row-sharded over the GPUs of one box.
+
+Two implementations of the same collective API:
+
+  ShardedSparseMatrix       the product: a thin ctypes wrapper over the C router
+                            (include/smatrix_shard.h, csrc/smx_router.c) — rendezvous through POSIX
+                            shared memory, batches routed by the partition kernel's own stores over
+                            NVLink, no NCCL and no Python on the data path.
+  TorchShardedSparseMatrix  the fallback when peer memory cannot be mapped, and the gloo / CPU test
+                            vehicle: torch.distributed all-to-all-v (described below).
+
+open_sharded() picks the C router and falls back (on every rank alike) when it cannot be set up.
+
+TorchShardedSparseMatrix
 
     owner(x) = mix_owner(x) mod world        (smatrix_b200_owner; independent of the directory hash)
 
@@ -48,7 +61,7 @@ class _PeerBuffers:
     ARRAYS = ("x", "y", "v", "o", "b")
     LOCAL_ONLY = ("p",)  # inverse permutation of my own queries: never touched by a peer
 
-    def __init__(self, sm: "ShardedSparseMatrix", cap_ops: int):
+    def __init__(self, sm: "TorchShardedSparseMatrix", cap_ops: int):
         self.sm, self.cap, self.gen = sm, int(cap_ops), 0
         lib, h = sm._lib, sm.router._handle()
         self.local = {(g, a): int(lib.smatrix_b200_dev_alloc(h, self.cap * 4))
@@ -99,7 +112,7 @@ class _PeerBuffers:
             lib.smatrix_b200_dev_free(h, p)
 
 
-class ShardedSparseMatrix:
+class TorchShardedSparseMatrix:
     def __init__(self, rank: int, world: int, device: int = 0, group=None, _lib_path: str | None = None,
                  p2p: bool | None = None):
         self.rank, self.world, self.group = rank, world, group
@@ -245,16 +258,26 @@ class ShardedSparseMatrix:
             return False
         need = int(nmax * 1.25) + 65536
         if self._peers is None or self._peers.cap < need:
+            peers, err = None, None
             try:
                 if self._peers is not None:
                     self._peers.close()
-                self._peers = _PeerBuffers(self, need)
-            except Exception as e:            # no peer access on this box: stay on the NCCL path
-                ok = torch.tensor([0], device=self.dev)
+                    self._peers = None
+                peers = _PeerBuffers(self, need)
+            except Exception as e:            # no peer access on this box
+                err = e
+            # agree on the outcome: one failed rank and EVERY rank falls back to the NCCL path together
+            # (a rank that stayed on the peer route alone would wait for collectives nobody else calls)
+            ok = torch.tensor([0 if err else 1], device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if peers is not None:
+                    peers.close()
                 self._peers, self._use_p2p = None, False
-                print(f"[smatrix sharded] peer-memory route unavailable ({e}); using NCCL all-to-all",
-                      flush=True)
+                print(f"[smatrix sharded] peer-memory route unavailable ({err or 'a peer failed'}); "
+                      "using NCCL all-to-all", flush=True)
                 return False
+            self._peers = peers
         return True
 
     def reserve_route(self, max_ops_per_rank: int) -> bool:
@@ -489,13 +512,55 @@ class ShardedSparseMatrix:
         back = self._a2a(ans, recv, send)
         return self._unpermute(back, opos)
 
+    def getrow_batch(self, xs):
+        """-> (offsets[n+1] uint64, pairs[total, 2] uint32) host arrays for THIS rank's rows xs, rows
+        in input order, pairs in the owners' table order (src/smatrix.c:189-210 with full buffers).
+        Row ids travel to their owners, each owner answers with the CSR of its run, and the asking
+        rank puts the rows back into input order."""
+        xs_np = xs.cpu().numpy().view(np.uint32) if torch.is_tensor(xs) else np.ascontiguousarray(xs, dtype=np.uint32)
+        n = len(xs_np)
+        dx = self._up("gx", torch.from_numpy(xs_np.view(np.int32).copy())) if n else self._buf(0)
+        send, recv, rx, _, _, opos, _ = self._route(dx, None, None, want_pos=True)
+        if rx.numel():
+            off_l, pairs_l = self.local.getrow_batch(rx.cpu().numpy().view(np.uint32))
+        else:
+            off_l, pairs_l = np.zeros(1, np.uint64), np.zeros((0, 2), np.uint32)
+        cnt_l = np.diff(off_l).astype(np.int64)                       # pairs per received row, inbox order
+        self._sync_torch()
+        back_cnt = self._a2a(torch.from_numpy(cnt_l.astype(np.int32)).to(self.dev), recv, send)
+        edges = np.concatenate([[0], np.cumsum(recv)]).astype(np.int64)
+        pairs_to = [int(cnt_l[edges[r]:edges[r + 1]].sum()) for r in range(self.world)]   # pairs I send to rank r
+        cnt_back = back_cnt.cpu().numpy().astype(np.int64)            # pairs per row, MY routed order
+        sedges = np.concatenate([[0], np.cumsum(send)]).astype(np.int64)
+        pairs_from = [int(cnt_back[sedges[r]:sedges[r + 1]].sum()) for r in range(self.world)]
+        flat = torch.from_numpy(pairs_l.reshape(-1).view(np.int32).copy()).to(self.dev)
+        got = torch.empty(2 * sum(pairs_from), dtype=torch.int32, device=self.dev)
+        dist.all_to_all_single(got, flat, output_split_sizes=[2 * c for c in pairs_from],
+                               input_split_sizes=[2 * c for c in pairs_to], group=self.group)
+        got = got.cpu().numpy().view(np.uint32).reshape(-1, 2)
+        pos = opos.cpu().numpy().astype(np.int64) if n else np.zeros(0, np.int64)
+        roff = np.concatenate([[0], np.cumsum(cnt_back)]).astype(np.int64)   # CSR in routed order
+        lens = cnt_back[pos] if n else np.zeros(0, np.int64)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        total = int(offsets[-1])
+        take = np.repeat(roff[pos] - offsets[:-1].astype(np.int64), lens) + np.arange(total, dtype=np.int64)
+        return offsets, got[take] if total else np.zeros((0, 2), np.uint32)
+
     # ------------------------------------------------------------------ local controls
     def stat(self, name):
         return self.local.stat(name)
 
+    _LOCAL_CONTROLS = frozenset((
+        "timer_start", "timer_stop_ms", "set_kernel_timing", "sync", "gen_c2_ops", "gen_c2_queries",
+        "gen_c3_ops", "gen_c3_queries", "gen_c4_lens", "gen_c4_ops", "probe_random_read",
+        "probe_random_atomic", "dev_alloc", "dev_free", "memcpy", "device", "stream"))
+
     def __getattr__(self, name):
-        # timer_start / timer_stop_ms / set_kernel_timing / gen_c2_* / probe_* / sync: the local shard's
-        return getattr(self.local, name)
+        # only controls of the local shard are forwarded; a data-path call that is not sharded here
+        # (cf_neighbors_batch, *_batch_out, single ops) must not silently run on one shard
+        if name in TorchShardedSparseMatrix._LOCAL_CONTROLS:
+            return getattr(self.local, name)
+        raise AttributeError(f"{type(self).__name__} has no sharded '{name}' (it would only see this rank's rows)")
 
     def close(self):
         if self._pool is not None:
@@ -508,3 +573,145 @@ class ShardedSparseMatrix:
             self._peers = None
         self.router.close()
         self.local.close()
+
+
+# ====================================================================================================
+# the product: the C router (include/smatrix_shard.h) behind the same collective API
+# ====================================================================================================
+_seq = [0]
+
+
+def default_name() -> str:
+    """A rendezvous name every rank of one launch derives alike: the launcher's pid (torchrun agent /
+    the test that spawned the ranks), the rendezvous port, and how many sharded matrices this process
+    has opened so far (every rank opens them in the same order)."""
+    _seq[0] += 1
+    return f"smx_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}_{_seq[0]}"
+
+
+class ShardedSparseMatrix:
+    """ctypes wrapper of smatrix_b200_shard_* — no computation and no routing logic here."""
+
+    def __init__(self, rank: int, world: int, device: int = 0, name: str | None = None,
+                 _lib_path: str | None = None):
+        from . import binding
+        self._lib = binding.load(_lib_path)
+        self.rank, self.world = rank, world
+        self._name = name or default_name()
+        self._h = self._lib.smatrix_b200_shard_open(self._name.encode(), rank, world, int(device))
+        if not self._h:
+            raise RuntimeError("smatrix_b200_shard_open failed (no CUDA device or no peer access)")
+        self.local = SparseMatrix._borrow(self._lib, self._lib.smatrix_b200_shard_local(self._h))
+        self._cuda = _lib_path is None
+
+    def _handle(self):
+        if not self._h:
+            raise ValueError("sharded matrix is closed")
+        return self._h
+
+    @staticmethod
+    def _n(a) -> int:
+        return 0 if a is None else (a.numel() if torch.is_tensor(a) else len(a))
+
+    def _write(self, fn, xs, ys, vals, *extra):
+        keep: list = []
+        A = SparseMatrix._arg
+        px, py, pv = A(xs, keep), A(ys, keep), A(vals, keep)
+        if torch.is_tensor(xs) and xs.is_cuda:
+            torch.cuda.current_stream(xs.device).synchronize()   # inputs may still be in flight on torch's stream
+        fn(self._handle(), px, py, pv, self._n(xs), *extra)
+
+    def incr_batch(self, xs, ys, vals=None, ordered: bool = True):
+        self._write(self._lib.smatrix_b200_shard_incr_batch, xs, ys, vals, 1 if ordered else 0)
+
+    def decr_batch(self, xs, ys, vals=None, ordered: bool = True):
+        self._write(self._lib.smatrix_b200_shard_decr_batch, xs, ys, vals, 1 if ordered else 0)
+
+    def set_batch(self, xs, ys, vals=None):
+        self._write(self._lib.smatrix_b200_shard_set_batch, xs, ys, vals)
+
+    def _out_like(self, xs, out):
+        n = self._n(xs)
+        if out is not None:
+            return out
+        if torch.is_tensor(xs):
+            return torch.empty(n, dtype=torch.int32, device=xs.device)
+        return np.empty(n, dtype=np.uint32)
+
+    def get_batch(self, xs, ys, out=None):
+        keep: list = []
+        A = SparseMatrix._arg
+        out = self._out_like(xs, out)
+        if torch.is_tensor(xs) and xs.is_cuda:
+            torch.cuda.current_stream(xs.device).synchronize()
+        self._lib.smatrix_b200_shard_get_batch(self._handle(), A(xs, keep), A(ys, keep), self._n(xs),
+                                               out.data_ptr() if torch.is_tensor(out) else out.ctypes.data)
+        return out
+
+    def rowlen_batch(self, xs, out=None):
+        keep: list = []
+        out = self._out_like(xs, out)
+        if torch.is_tensor(xs) and xs.is_cuda:
+            torch.cuda.current_stream(xs.device).synchronize()
+        self._lib.smatrix_b200_shard_rowlen_batch(self._handle(), SparseMatrix._arg(xs, keep), self._n(xs),
+                                                  out.data_ptr() if torch.is_tensor(out) else out.ctypes.data)
+        return out
+
+    def getrow_batch(self, xs):
+        """-> (offsets[n+1] uint64, pairs[total, 2] uint32) host arrays (rows in input order)."""
+        xs = xs.cpu().numpy().view(np.uint32) if torch.is_tensor(xs) else np.ascontiguousarray(xs, dtype=np.uint32)
+        n = len(xs)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        h = self._handle()
+        total = int(self._lib.smatrix_b200_shard_getrow_batch(h, xs.ctypes.data, n, offsets.ctypes.data, None, 0))
+        # the fill is collective too: every rank makes the second call, with room for its own total
+        pairs = np.zeros((max(total, 1), 2), dtype=np.uint32)
+        got = int(self._lib.smatrix_b200_shard_getrow_batch(h, xs.ctypes.data, n, offsets.ctypes.data,
+                                                            pairs.ctypes.data, max(total, 1)))
+        assert got == total
+        return offsets, pairs[:total]
+
+    def getrow_batch_into(self, d_xs, n: int, d_offsets: int, d_pairs: int, pairs_cap: int) -> int:
+        """The raw collective call on device (or host) pointers; returns the total number of pairs."""
+        return int(self._lib.smatrix_b200_shard_getrow_batch(self._handle(), d_xs, n, d_offsets, d_pairs, pairs_cap))
+
+    def reserve_route(self, max_ops_per_rank: int, max_pairs_per_rank: int = 0) -> bool:
+        self._lib.smatrix_b200_shard_reserve(self._handle(), int(max_ops_per_rank), int(max_pairs_per_rank))
+        return True
+
+    def barrier(self):
+        self._lib.smatrix_b200_shard_barrier(self._handle())
+
+    def sum(self, v: int) -> int:
+        return int(self._lib.smatrix_b200_shard_sum(self._handle(), int(v)))
+
+    def max(self, v: int) -> int:
+        return int(self._lib.smatrix_b200_shard_max(self._handle(), int(v)))
+
+    def stat(self, name):
+        return self.local.stat(name)
+
+    def __getattr__(self, name):
+        if name in TorchShardedSparseMatrix._LOCAL_CONTROLS:
+            return getattr(self.local, name)
+        raise AttributeError(f"{type(self).__name__} has no sharded '{name}' (it would only see this rank's rows)")
+
+    def close(self):
+        if self._h:
+            self.local._h = None          # borrowed: the router closes it
+            self._lib.smatrix_b200_shard_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        pass   # closing is collective: never from a finalizer
+
+
+def open_sharded(rank: int, world: int, device: int = 0, group=None, name: str | None = None):
+    """The C router when it can be set up, else (every rank alike — shard_open agrees on the outcome
+    before anyone returns) the torch.distributed fallback.  $SMX_ROUTER=torch forces the fallback."""
+    if os.environ.get("SMX_ROUTER", "c") != "torch":
+        try:
+            return ShardedSparseMatrix(rank, world, device, name=name)
+        except RuntimeError as e:
+            print(f"[smatrix sharded] rank {rank}: C router unavailable ({e}); using torch.distributed", flush=True)
+    return TorchShardedSparseMatrix(rank, world, device, group=group)

@@ -63,6 +63,17 @@ def driver():
                                      _u32p, _u32p]
         d.drv_gen_c2_queries.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t,
                                          C.c_uint64, C.c_uint32, C.c_uint32, _u32p, _u32p]
+        d.drv_gen_c3_ops.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, _u64p, C.c_uint32, _u32p, _u32p]
+        d.drv_gen_c3_queries.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint64, _u64p,
+                                         C.c_uint32, _u32p, _u32p]
+        d.drv_gen_c4_lens.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, _u64p, C.c_uint32, _u32p]
+        d.drv_gen_c4_ops.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, _u64p, C.c_uint32, _u32p, _u32p, _u32p]
+        d.drv_bench_apply.restype = C.c_double
+        d.drv_bench_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _u32p, _u32p, _u32p, C.c_size_t]
+        d.drv_bench_get.restype = C.c_double
+        d.drv_bench_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _u32p, _u32p, C.c_size_t]
+        d.drv_bench_getrow.restype = C.c_double
+        d.drv_bench_getrow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _u32p, C.c_size_t, _u64p]
         _driver = d
     return _driver
 
@@ -182,6 +193,25 @@ class CpuMatrix:
         return driver().drv_bench_c2_get(self.fnptr("get"), self.h, threads, seed_get, seed_build,
                                          first, count, n_build, rows, ycols)
 
+    # the same harness over pre-generated arrays (any workload)
+    def bench_apply(self, op: str, threads: int, xs, ys, vs=None) -> float:
+        xs, ys = _u32(xs), _u32(ys)
+        vs = _u32(vs) if vs is not None else None
+        return driver().drv_bench_apply(self.fnptr(op), self.h, threads, _ptr(xs), _ptr(ys),
+                                        _ptr(vs) if vs is not None else None, len(xs))
+
+    def bench_get(self, threads: int, xs, ys) -> float:
+        xs, ys = _u32(xs), _u32(ys)
+        return driver().drv_bench_get(self.fnptr("get"), self.h, threads, _ptr(xs), _ptr(ys), len(xs))
+
+    def bench_getrow(self, threads: int, xs):
+        """rowlen + getrow (full-size buffers) of every row in xs -> (seconds, pairs returned)"""
+        xs = _u32(xs)
+        pairs = C.c_uint64(0)
+        secs = driver().drv_bench_getrow(self.fnptr("rowlen"), self.fnptr("getrow"), self.h, threads,
+                                         _ptr(xs), len(xs), C.byref(pairs))
+        return secs, int(pairs.value)
+
     def close(self):
         if self.h:
             self._f["close"](self.h)
@@ -218,3 +248,47 @@ def gen_c2_queries(seed_get, seed_build, first, count, n_build, rows, ycols):
     driver().drv_gen_c2_queries(seed_get, seed_build, first, count, n_build, rows, ycols,
                                 _ptr(xs), _ptr(ys))
     return xs, ys
+
+
+# ---- C3 / C4 streams: inverse-CDF thresholds + the generators of smx_driver.c -------
+def zipf_thresholds(m: int, s: float) -> np.ndarray:
+    """thr[k] = floor(2^64 * CDF(k+1)) for P(k) ~ k^-s, k = 1..m (uint64, last = 2^64 - 1).  Built
+    once per process and handed to BOTH the device generator and this module's, so both draw
+    from the same table."""
+    w = np.arange(1, m + 1, dtype=np.float64) ** (-float(s))
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    thr = np.minimum(cdf * 18446744073709551616.0, 18446744073709549568.0).astype(np.uint64)
+    thr[-1] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    return thr
+
+
+def gen_c3_ops(seed, first, count, thr):
+    xs = np.empty(count, dtype=np.uint32)
+    ys = np.empty(count, dtype=np.uint32)
+    driver().drv_gen_c3_ops(seed, first, count, _ptr(thr, _u64p), len(thr), _ptr(xs), _ptr(ys))
+    return xs, ys
+
+
+def gen_c3_queries(seed_get, seed_build, first, count, n_build, thr):
+    xs = np.empty(count, dtype=np.uint32)
+    ys = np.empty(count, dtype=np.uint32)
+    driver().drv_gen_c3_queries(seed_get, seed_build, first, count, n_build, _ptr(thr, _u64p), len(thr),
+                                _ptr(xs), _ptr(ys))
+    return xs, ys
+
+
+def gen_c4_lens(seed, first, count, thr):
+    lens = np.empty(count, dtype=np.uint32)
+    driver().drv_gen_c4_lens(seed, first, count, _ptr(thr, _u64p), len(thr), _ptr(lens))
+    return lens
+
+
+def gen_c4_ops(seed, first, count, offs):
+    """offs: exclusive prefix of the row lengths, rows + 1 entries (uint64)"""
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    xs = np.empty(count, dtype=np.uint32)
+    ys = np.empty(count, dtype=np.uint32)
+    vs = np.empty(count, dtype=np.uint32)
+    driver().drv_gen_c4_ops(seed, first, count, _ptr(offs, _u64p), len(offs) - 1, _ptr(xs), _ptr(ys), _ptr(vs))
+    return xs, ys, vs

@@ -97,6 +97,63 @@ void drv_gen_c2_queries(uint64_t seed_get, uint64_t seed_build, uint64_t first, 
     c2_query(seed_get, seed_build, first + i, n_build, rows, ycols, &xs[i], &ys[i]);
 }
 
+/* ---- C3 / C4 streams: the same definitions as the device generators (csrc/smx_kernels.cu) ---- */
+static inline uint32_t draw(const uint64_t* thr, uint32_t m, uint64_t r) {
+  uint32_t lo = 0, hi = m - 1u;
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (thr[mid] < r) lo = mid + 1u; else hi = mid;
+  }
+  return lo + 1u;
+}
+/* examples/cf_recommender.c:35-47: per basket of 8 ids, for n: incr(ids[n],0,1); for i != n:
+ * incr(ids[n], ids[i], 1) — op k = i % 64 of basket i / 64 */
+static inline void c3_op(uint64_t seed, uint64_t i, const uint64_t* thr, uint32_t items, uint32_t* x,
+                         uint32_t* y) {
+  uint64_t b = i >> 6;
+  uint32_t k = (uint32_t)(i & 63u), n = k >> 3, j = k & 7u;
+  *x = draw(thr, items, splitmix64(seed + b * 8u + n));
+  if (j == 0) { *y = 0; return; }
+  uint32_t other = (j - 1u < n) ? j - 1u : j;
+  *y = draw(thr, items, splitmix64(seed + b * 8u + other));
+}
+void drv_gen_c3_ops(uint64_t seed, uint64_t first, size_t count, const uint64_t* thr, uint32_t items,
+                    uint32_t* xs, uint32_t* ys) {
+  for (size_t i = 0; i < count; i++) c3_op(seed, first + i, thr, items, &xs[i], &ys[i]);
+}
+void drv_gen_c3_queries(uint64_t seed_get, uint64_t seed_build, uint64_t first, size_t count,
+                        uint64_t n_build, const uint64_t* thr, uint32_t items, uint32_t* xs, uint32_t* ys) {
+  for (size_t i = 0; i < count; i++) {
+    uint64_t j = first + i;
+    c3_op(seed_build, splitmix64(seed_get + j) % n_build, thr, items, &xs[i], &ys[i]);
+    if (j & 1) ys[i] += items + 1u;
+  }
+}
+void drv_gen_c4_lens(uint64_t seed, uint64_t first, size_t count, const uint64_t* thr, uint32_t kmax,
+                     uint32_t* lens) {
+  for (size_t i = 0; i < count; i++) lens[i] = draw(thr, kmax, splitmix64(seed + first + i));
+}
+static inline uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+void drv_gen_c4_ops(uint64_t seed, uint64_t first, size_t count, const uint64_t* offs, uint32_t rows,
+                    uint32_t* xs, uint32_t* ys, uint32_t* vs) {
+  for (size_t q = 0; q < count; q++) {
+    uint64_t i = first + q;
+    uint32_t lo = 0, hi = rows - 1u;
+    while (lo < hi) {
+      uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+      if (offs[mid] <= i) lo = mid; else hi = mid - 1u;
+    }
+    uint32_t j = (uint32_t)(i - offs[lo]);
+    uint32_t salt = 1u + (uint32_t)(splitmix64((seed ^ 0xC4C4C4C4ull) + lo) % 0xFFE00000ull);
+    xs[q] = lo * 2654435761u;
+    ys[q] = fmix32(j + salt);
+    vs[q] = (uint32_t)(splitmix64(seed + 0x5EED0000ull + i) >> 32) | 1u;
+  }
+}
+
 /* ---------------------------------------------------------------- pthread harness */
 
 typedef struct {
@@ -181,6 +238,81 @@ double drv_bench_c2_get(void* get, void* h, int threads, uint64_t seed_get, uint
   p.rows = rows;
   p.ycols = ycols;
   return run_threads(p, threads);
+}
+
+/* ---- the same harness over PRE-GENERATED arrays (any workload): thread t applies the ops
+ * [t*n/T, (t+1)*n/T) in order; vs == NULL means every value is 1.  Returns wall seconds. */
+typedef struct {
+  int kind; /* 0 = write op (incr/set/decr), 1 = get, 2 = rowlen + getrow of whole rows */
+  void *fn, *fn2, *h;
+  const uint32_t *xs, *ys, *vs;
+  size_t first, count;
+  uint64_t sink;
+} ajob_t;
+static void* aworker(void* arg) {
+  ajob_t* j = (ajob_t*)arg;
+  uint64_t acc = 0;
+  if (j->kind == 0) {
+    fn_xyv op = (fn_xyv)j->fn;
+    for (size_t i = j->first; i < j->first + j->count; i++) acc += op(j->h, j->xs[i], j->ys[i], j->vs ? j->vs[i] : 1u);
+  } else if (j->kind == 1) {
+    fn_xy get = (fn_xy)j->fn;
+    for (size_t i = j->first; i < j->first + j->count; i++) acc += get(j->h, j->xs[i], j->ys[i]);
+  } else {
+    fn_x rowlen = (fn_x)j->fn;
+    fn_row getrow = (fn_row)j->fn2;
+    size_t cap = 1024;
+    uint32_t* buf = malloc(cap * 8);
+    for (size_t i = j->first; i < j->first + j->count; i++) {
+      uint64_t len = rowlen(j->h, j->xs[i]);
+      if (len + 2 > cap) { cap = (len + 2) * 2; buf = realloc(buf, cap * 8); }
+      acc += getrow(j->h, j->xs[i], buf, (size_t)(len + 2) * 8); /* pairs returned */
+    }
+    free(buf);
+  }
+  j->sink = acc;
+  return NULL;
+}
+static double run_athreads(ajob_t proto, size_t n, int threads, uint64_t* sink) {
+  pthread_t* tid = malloc(sizeof(pthread_t) * (size_t)threads);
+  ajob_t* jobs = malloc(sizeof(ajob_t) * (size_t)threads);
+  struct timespec t0, t1;
+  size_t per = n / (size_t)threads;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < threads; t++) {
+    jobs[t] = proto;
+    jobs[t].first = per * (size_t)t;
+    jobs[t].count = (t == threads - 1) ? n - per * (size_t)t : per;
+    pthread_create(&tid[t], NULL, aworker, &jobs[t]);
+  }
+  uint64_t acc = 0;
+  for (int t = 0; t < threads; t++) { pthread_join(tid[t], NULL); acc += jobs[t].sink; }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (sink) *sink = acc;
+  free(tid);
+  free(jobs);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+double drv_bench_apply(void* op, void* h, int threads, const uint32_t* xs, const uint32_t* ys,
+                       const uint32_t* vs, size_t n) {
+  ajob_t p;
+  memset(&p, 0, sizeof p);
+  p.kind = 0; p.fn = op; p.h = h; p.xs = xs; p.ys = ys; p.vs = vs;
+  return run_athreads(p, n, threads, NULL);
+}
+double drv_bench_get(void* get, void* h, int threads, const uint32_t* xs, const uint32_t* ys, size_t n) {
+  ajob_t p;
+  memset(&p, 0, sizeof p);
+  p.kind = 1; p.fn = get; p.h = h; p.xs = xs; p.ys = ys;
+  return run_athreads(p, n, threads, NULL);
+}
+/* rowlen + getrow (full-size buffer) of n rows; *pairs_out = pairs returned in total */
+double drv_bench_getrow(void* rowlen, void* getrow, void* h, int threads, const uint32_t* xs, size_t n,
+                        uint64_t* pairs_out) {
+  ajob_t p;
+  memset(&p, 0, sizeof p);
+  p.kind = 2; p.fn = rowlen; p.fn2 = getrow; p.h = h; p.xs = xs;
+  return run_athreads(p, n, threads, pairs_out);
 }
 
 /* ---------------------------------------------------------------- full-scale parity digests */

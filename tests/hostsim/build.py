@@ -12,7 +12,7 @@ SO = os.path.join(HERE, "libsmatrix_hostsim.so")
 
 def build() -> str:
     srcs = [os.path.join(CSRC, "smx_kernels.cu"), os.path.join(CSRC, "smx_host.c"),
-            os.path.join(HERE, "fake_runtime.cpp"), os.path.join(HERE, "hostsim.h"),
+            os.path.join(HERE, "fake_runtime.cpp"), os.path.join(CSRC, "smx_router.c"), os.path.join(HERE, "hostsim.h"),
             os.path.join(CSRC, "smx_internal.h")]
     if os.path.exists(SO) and all(os.path.getmtime(s) < os.path.getmtime(SO) for s in srcs):
         return SO
@@ -21,13 +21,14 @@ def build() -> str:
     objs = []
     for src, cc, extra in ((srcs[0], "g++", ["-x", "c++", "-std=c++17"]),
                            (srcs[1], "gcc", ["-std=gnu11"]),
-                           (srcs[2], "g++", ["-std=c++17"])):
+                           (srcs[2], "g++", ["-std=c++17"]),
+                           (srcs[3], "gcc", ["-std=gnu11"])):
         o = os.path.join(HERE, os.path.basename(src) + ".o")
         subprocess.run([cc] + common + extra + ["-c", src, "-o", o], check=True)
         objs.append(o)
     # -Bsymbolic: the fake cuda* symbols must bind inside this library even when a real
     # libcudart is already loaded in the process (torch)
-    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", SO] + objs + ["-lpthread"], check=True)
+    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", SO] + objs + ["-lpthread", "-lrt"], check=True)
     return SO
 
 

@@ -65,9 +65,11 @@ cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes* a, const void
   }
   return 0;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return 1; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return 1; }
+// "IPC" inside one process: the handle carries the raw pointer (ranks are threads in the CPU tests)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return 0; }
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return *p ? 0 : 1; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
 cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *t = (size_t)8 << 30; *f = *t - g_dev_bytes; return 0; }
 cudaError_t cudaGetLastError(void) { return 0; }
 cudaError_t cudaDeviceSynchronize(void) { return 0; }

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from libsmatrix_b200.sharded import ShardedSparseMatrix  # noqa: E402
+from libsmatrix_b200.sharded import ShardedSparseMatrix, TorchShardedSparseMatrix  # noqa: E402
 from oracle import cpu  # noqa: E402
 
 U32 = np.uint32
@@ -22,8 +22,12 @@ def main():
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    p2p = os.environ.get("SMX_P2P", "1") == "1"       # fused peer-memory route vs NCCL all-to-all
-    m = ShardedSparseMatrix(rank, world, rank, p2p=p2p)
+    kind = os.environ.get("SMX_ROUTER_KIND", "c")     # c = the C router (product); torch-p2p / torch-nccl = fallback
+    p2p = kind != "torch-nccl"
+    if kind == "c":
+        m = ShardedSparseMatrix(rank, world, rank)
+    else:
+        m = TorchShardedSparseMatrix(rank, world, rank, p2p=p2p)
     ref = cpu.CpuMatrix("reference" if cpu.have_reference() else "port")
     rng = np.random.default_rng(321)                  # the same global stream on every rank
     n = 400_000
@@ -42,7 +46,8 @@ def main():
     nz = ys != 0
     ref.apply("incr", xs[nz], ys[nz], np.ones(int(nz.sum()), U32))
     k = int(nz.sum())
-    m.PIPELINE_MIN, m.PIPELINE_PIECE = 50_000, 40_000                      # force the overlapped pieces
+    if kind != "c":
+        m.PIPELINE_MIN, m.PIPELINE_PIECE = 50_000, 40_000                  # force the overlapped pieces
     m.incr_batch(t(xs[nz][sl(k)]), t(ys[nz][sl(k)]), None, ordered=False)  # order-free stream
     allx = np.concatenate([xs, gx]); ally = np.concatenate([ys, gy])
     qx = np.concatenate([allx[rank::7], rng.integers(0, 2**32, 1000, dtype=np.uint64).astype(U32)])
@@ -53,15 +58,24 @@ def main():
     rows = np.unique(allx)[rank::world]
     got = m.rowlen_batch(t(rows)).cpu().numpy().view(U32)
     assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
+    # getrow across ranks (src/smatrix.c:189-210): overlapping requests, rows nobody has, an empty request
+    grows = np.concatenate([np.unique(allx)[rank::3], np.array([3, 5], U32)])
+    o1, p1 = m.getrow_batch(grows)
+    o2, p2 = ref.getrow_many(grows)
+    assert (o1 == o2).all(), f"rank {rank}: sharded getrow offsets mismatch"
+    assert (cpu.sort_rows(o1, p1) == cpu.sort_rows(o2, p2)).all(), f"rank {rank}: sharded getrow pairs mismatch"
+    o0, p0 = m.getrow_batch(np.zeros(0, U32))
+    assert len(o0) == 1 and len(p0) == 0
     tot = torch.tensor([m.stat("rows"), m.stat("nnz")], device=dev)
     dist.all_reduce(tot)
     o, p = ref.getrow_many(np.unique(allx))
     assert int(tot[0]) == len(np.unique(allx)) and int(tot[1]) == len(p)
-    assert (m._peers is not None) == p2p, "peer-memory route was expected to be active"
+    if kind != "c":
+        assert (m._peers is not None) == p2p, "peer-memory route was expected to be active"
     m.close(); ref.close()
     dist.barrier()
     dist.destroy_process_group()
-    print(f"rank {rank} ok (p2p={p2p}, peers={'yes' if p2p else 'n/a'})")
+    print(f"rank {rank} ok (router={kind})")
 
 
 if __name__ == "__main__":

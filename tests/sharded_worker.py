@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from libsmatrix_b200.sharded import ShardedSparseMatrix  # noqa: E402
+from libsmatrix_b200.sharded import TorchShardedSparseMatrix as ShardedSparseMatrix  # noqa: E402
 from oracle import cpu  # noqa: E402
 
 
@@ -66,6 +66,16 @@ def main():
     rows = np.unique(xs)[rank::2]
     got = m.rowlen_batch(t(rows)).numpy().view(np.uint32)
     assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
+    # getrow across ranks: rows come back in input order, pairs compared sorted by column
+    rows = np.concatenate([np.unique(xs)[rank::3], np.array([11, 12], np.uint32)])
+    o1, p1 = m.getrow_batch(rows)
+    o2, p2 = ref.getrow_many(rows)
+    assert (o1 == o2).all() and (cpu.sort_rows(o1, p1) == cpu.sort_rows(o2, p2)).all(), f"rank {rank}: sharded getrow mismatch"
+    try:
+        m.cf_neighbors_batch
+        raise SystemExit("data-path calls that are not sharded must be refused")
+    except AttributeError:
+        pass
     # the shard holds exactly the rows this rank owns
     owned = np.array([x for x in np.unique(xs) if m._lib.smatrix_b200_owner(int(x), world) == rank], np.uint32)
     assert m.stat("rows") == len(owned)

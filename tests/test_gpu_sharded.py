@@ -1,6 +1,8 @@
 """Multi-GPU parity (BASELINE config 5 shape at test scale): rows hash-partitioned over the GPUs of
-one box, ops routed by NCCL all-to-all, every rank updating only its own shard — bit-exact against
-the reference fed the whole stream.  Needs >= 2 GPUs (`gpurun --gpus 2`)."""
+one box, ops routed to their owners — by the C router (peer-memory stores from the partition kernel,
+shared-memory rendezvous; the product) and by the torch.distributed fallback — every rank updating
+only its own shard, bit-exact against the reference fed the whole stream, incl. getrow across ranks.
+Needs >= 2 GPUs (`gpurun --gpus 2`)."""
 import os
 import subprocess
 import sys
@@ -19,13 +21,14 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("p2p", [1, 0], ids=["peer-memory", "nccl-a2a"])
+@pytest.mark.parametrize("kind", ["c", "torch-p2p", "torch-nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_row_sharding_nccl(world, p2p):
+def test_row_sharding(world, kind):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + world + 10 * p2p),
-               WORLD_SIZE=str(world), SMX_P2P=str(p2p))
+    port = 29600 + world + 10 * ["c", "torch-p2p", "torch-nccl"].index(kind)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+               WORLD_SIZE=str(world), SMX_ROUTER_KIND=kind)
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "sharded_gpu_worker.py")],
                               env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True) for r in range(world)]
