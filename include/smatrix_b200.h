@@ -52,7 +52,9 @@ enum {
   SMX_STAT_VALUE_SUM = 16,  /* sum of every stored value mod 2^64 (scans the whole table) */
   SMX_STAT_LIVE_BUCKET_BYTES = 17, /* bytes of slab buckets rows own right now (scans the directory) */
   SMX_STAT_FREE_BYTES = 18, /* bytes of vacated buckets waiting on the free lists              */
-  SMX_STAT_RECYCLED = 19    /* row growths served from the free lists so far                   */
+  SMX_STAT_RECYCLED = 19,   /* row growths served from the free lists so far                   */
+  SMX_STAT_H2D_BYTES = 20,  /* bytes copied host -> device by this handle so far (batches, tables) */
+  SMX_STAT_D2H_BYTES = 21   /* bytes copied device -> host (answers, control-block reads)      */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 

@@ -73,6 +73,14 @@ void smatrix_b200_shard_rowlen_batch(smatrix_shard_t* self, const uint32_t* xs, 
 uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* self, const uint32_t* xs, size_t n,
                                          uint64_t* offsets, uint32_t* pairs, uint64_t pairs_cap);
 
+/* Host wall-clock accounting of this rank since the last reset (not collective): time spent routing
+ * (count, count exchange, scatter over NVLink, arrival barrier), time spent applying the inbox,
+ * number of routes, bytes this rank stored into OTHER ranks' inboxes. */
+enum { SMX_SHARD_STAT_ROUTE_NS = 0, SMX_SHARD_STAT_APPLY_NS = 1, SMX_SHARD_STAT_ROUTES = 2,
+       SMX_SHARD_STAT_REMOTE_BYTES = 3 };
+uint64_t smatrix_b200_shard_stat(smatrix_shard_t* self, int which);
+void smatrix_b200_shard_stat_reset(smatrix_shard_t* self);
+
 /* collective helpers (shared-memory barrier / sum over ranks), for hosts without another transport */
 void smatrix_b200_shard_barrier(smatrix_shard_t* self);
 uint64_t smatrix_b200_shard_sum(smatrix_shard_t* self, uint64_t v);

@@ -117,6 +117,7 @@ struct smatrix_s {
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
+  uint64_t h2d_bytes, d2h_bytes; /* bytes this handle copied between host and device (SMX_STAT_*_BYTES) */
   double phase_ns[8];
   int timing;
   cudaEvent_t ev0, ev1, t_start, t_stop;
@@ -157,6 +158,16 @@ static void* dmalloc(smatrix_t* s, size_t bytes) {
   return p;
 }
 
+/* host <-> device copies, counted (the end-to-end accounting of bench.py reads the counters) */
+static inline void copy_h2d(smatrix_t* s, void* d, const void* h, size_t bytes, cudaStream_t st) {
+  CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+  s->h2d_bytes += bytes;
+}
+static inline void copy_d2h(smatrix_t* s, void* h, const void* d, size_t bytes, cudaStream_t st) {
+  CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+  s->d2h_bytes += bytes;
+}
+
 static uint32_t log2_u64(uint64_t v) {
   uint32_t l = 0;
   while ((1ull << l) < v) l++;
@@ -190,7 +201,7 @@ static inline double now_ns(void) {
 }
 
 static void read_ctl(smatrix_t* s) {
-  CK(cudaMemcpyAsync(s->h_ctl, s->d_ctl, sizeof(smx_ctl_t), cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, s->h_ctl, s->d_ctl, sizeof(smx_ctl_t), s->stream);
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
   unsigned long long used = 0;
@@ -333,7 +344,7 @@ static void ensure_free_stacks(smatrix_t* s) {
     unsigned long long* nb = (unsigned long long*)slab_reserve(s, (size_t)cap * 8);
     if (have) CK(cudaMemcpyAsync(nb, s->free_ptr[c], (size_t)have * 8, cudaMemcpyDeviceToDevice, s->stream));
     s->free_ptr[c] = nb; /* a field of the handle: stays valid while the copy below is in flight */
-    CK(cudaMemcpyAsync(&s->d_ctl->free_stack[c], &s->free_ptr[c], sizeof nb, cudaMemcpyHostToDevice, s->stream));
+    copy_h2d(s, &s->d_ctl->free_stack[c], &s->free_ptr[c], sizeof nb, s->stream);
     s->free_cap[c] = (uint32_t)cap;
   }
 }
@@ -521,7 +532,7 @@ static int partition_chunk(smatrix_t* s, smx_ops_t* ops, int api_op, uint32_t* n
   double t0 = now_ns();
   CK(cudaMemsetAsync(d_counts, 0, parts * 8, s->stream));
   smx_launch_partition_count(s->stream, ops->xs, ops->ys, n, parts, (uint32_t)(s->dir_cap - 1), shift, slices, d_counts);
-  CK(cudaMemcpyAsync(h, d_counts, parts * 8, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, h, d_counts, parts * 8, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   unsigned long long at = 0;
   for (uint32_t p = 0; p < parts; p++) {
@@ -530,7 +541,7 @@ static int partition_chunk(smatrix_t* s, smx_ops_t* ops, int api_op, uint32_t* n
     at += h[p];
   }
   const int want_idx = api_op == 2 || *n_main != n || ops->idx != NULL;
-  CK(cudaMemcpyAsync(d_cursors, cur, parts * 8, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, d_cursors, cur, parts * 8, s->stream);
   smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, (uint32_t)(s->dir_cap - 1),
                                shift, slices, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
                                want_idx ? s->part[3] : NULL, ops->idx, NULL, NULL, 0);
@@ -655,7 +666,7 @@ static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint
     uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
     const uint32_t* src[3] = {xs, ys, vs};
     for (int a = 0; a < 3; a++)
-      if (src[a]) CK(cudaMemcpyAsync(s->stage[b][a], src[a] + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->copy_stream));
+      if (src[a]) copy_h2d(s, s->stage[b][a], src[a] + off, (size_t)len * 4, s->copy_stream);
     CK(cudaEventRecord(s->stage_ready[b], s->copy_stream));
     while (off < n) {
       const size_t next = off + len;
@@ -663,7 +674,7 @@ static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint
       if (next < n) { /* start uploading the next chunk into the other buffer */
         next_len = (uint32_t)((n - next < step) ? n - next : step);
         for (int a = 0; a < 3; a++)
-          if (src[a]) CK(cudaMemcpyAsync(s->stage[b ^ 1][a], src[a] + next, (size_t)next_len * 4, cudaMemcpyHostToDevice, s->copy_stream));
+          if (src[a]) copy_h2d(s, s->stage[b ^ 1][a], src[a] + next, (size_t)next_len * 4, s->copy_stream);
         CK(cudaEventRecord(s->stage_ready[b ^ 1], s->copy_stream));
       }
       CK(cudaStreamWaitEvent(s->stream, s->stage_ready[b], 0));
@@ -746,9 +757,9 @@ static void write_batch_out(smatrix_t* s, int api_op, const uint32_t* xs, const 
     for (size_t off = 0; off < n; off += step) {
       const uint32_t len = (uint32_t)((n - off < step) ? n - off : step);
       for (int a = 0; a < 3; a++)
-        if (src[a]) CK(cudaMemcpyAsync(s->stage[0][a], src[a] + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
+        if (src[a]) copy_h2d(s, s->stage[0][a], src[a] + off, (size_t)len * 4, s->stream);
       chunk_out(s, api_op, s->stage[0][0], s->stage[0][1], vs ? s->stage[0][2] : NULL, len, s->bo_out);
-      CK(cudaMemcpyAsync(out + off, s->bo_out, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+      copy_d2h(s, out + off, s->bo_out, (size_t)len * 4, s->stream);
       CK(cudaStreamSynchronize(s->stream));
     }
   }
@@ -787,7 +798,7 @@ void smatrix_b200_apply_ordered(smatrix_t* s, int op, const uint32_t* d_xs, cons
     for (int a = 0; a < 4; a++) {
       if (!src[a]) continue;
       tmp[a] = (uint32_t*)dmalloc(s, n * 4);
-      CK(cudaMemcpyAsync(tmp[a], src[a], n * 4, cudaMemcpyHostToDevice, s->stream));
+      copy_h2d(s, tmp[a], src[a], n * 4, s->stream);
     }
     process_chunk_ordered(s, op, tmp[0], tmp[1], tmp[2], tmp[3], (uint32_t)n);
     CK(cudaStreamSynchronize(s->stream));
@@ -835,11 +846,11 @@ void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, siz
       cudaStream_t st = sts[q];
       uint32_t* const* buf = s->stage[q >> 1];
       const size_t half = (size_t)(q & 1u) * step;
-      CK(cudaMemcpyAsync(buf[0] + half, xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(buf[1] + half, ys + off, (size_t)len * 4, cudaMemcpyHostToDevice, st));
+      copy_h2d(s, buf[0] + half, xs + off, (size_t)len * 4, st);
+      copy_h2d(s, buf[1] + half, ys + off, (size_t)len * 4, st);
       smx_launch_get(st, view_of(s), buf[0] + half, buf[1] + half, len, buf[2] + half);
       s->n_launches++;
-      CK(cudaMemcpyAsync(out + off, buf[2] + half, (size_t)len * 4, cudaMemcpyDeviceToHost, st));
+      copy_d2h(s, out + off, buf[2] + half, (size_t)len * 4, st);
     }
     CK(cudaStreamSynchronize(s->read_stream[0]));
     CK(cudaStreamSynchronize(s->read_stream[1]));
@@ -861,9 +872,9 @@ void smatrix_rowlen_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint32_t* 
       smx_launch_rowlen(s->stream, view_of(s), xs + off, len, out + off);
     } else {
       ensure_tmp(s, (size_t)len * 8, 0);
-      CK(cudaMemcpyAsync(s->d_tmp, xs + off, (size_t)len * 4, cudaMemcpyHostToDevice, s->stream));
+      copy_h2d(s, s->d_tmp, xs + off, (size_t)len * 4, s->stream);
       smx_launch_rowlen(s->stream, view_of(s), s->d_tmp, len, s->d_tmp + len);
-      CK(cudaMemcpyAsync(out + off, s->d_tmp + len, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
+      copy_d2h(s, out + off, s->d_tmp + len, (size_t)len * 4, s->stream);
     }
     s->n_launches++;
     CK(cudaStreamSynchronize(s->stream));
@@ -889,8 +900,8 @@ static uint64_t plan_rows(smatrix_t* s, const uint32_t* d_xs, uint32_t n, uint32
   (void)tiles;
   s->n_launches += 4;
   uint64_t total = 0;
-  CK(cudaMemcpyAsync(&s->h_small[32], s->d_tmp64 + n, 8, cudaMemcpyDeviceToHost, s->stream));
-  CK(cudaMemcpyAsync(&s->h_small[34], d_nbig, 4, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, &s->h_small[32], s->d_tmp64 + n, 8, s->stream);
+  copy_d2h(s, &s->h_small[34], d_nbig, 4, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   memcpy(&total, &s->h_small[32], 8);
   s->n_big_rows = s->h_small[34];
@@ -917,15 +928,21 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
   const uint32_t* d_xs = xs;
   uint32_t* d_counts = s->d_tmp + nn;
   if (!dev) {
-    CK(cudaMemcpyAsync(s->d_tmp, xs, (size_t)nn * 4, cudaMemcpyHostToDevice, s->stream));
+    copy_h2d(s, s->d_tmp, xs, (size_t)nn * 4, s->stream);
     d_xs = s->d_tmp;
   }
   const uint64_t total = plan_rows(s, d_xs, nn, d_counts);
-  if (offsets)
+  if (offsets) {
     CK(cudaMemcpyAsync(offsets, s->d_tmp64, ((size_t)nn + 1) * 8, cudaMemcpyDefault, s->stream));
+    if (!is_device_ptr(offsets)) s->d2h_bytes += ((size_t)nn + 1) * 8;
+  }
+  int filled = 0;
   if (pairs && total <= pairs_cap && total > 0) {
+    filled = 1;
     if (is_device_ptr(pairs)) {
+      timed_begin(s);
       smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, pairs, s->d_big, s->n_big_rows, s->d_cursors);
+      timed_end(s);
       s->n_launches++;
     } else {
       if (total * 8 > s->d_rowbuf_bytes) {
@@ -933,12 +950,15 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
         s->d_rowbuf_bytes = (size_t)total * 8;
         s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
       }
+      timed_begin(s);
       smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
+      timed_end(s);
       s->n_launches++;
-      CK(cudaMemcpyAsync(pairs, s->d_rowbuf, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
+      copy_d2h(s, pairs, s->d_rowbuf, (size_t)total * 8, s->stream);
     }
   }
   CK(cudaStreamSynchronize(s->stream));
+  if (filled) timed_collect(s);
   CK(cudaGetLastError());
   leave(s);
   return total;
@@ -959,7 +979,7 @@ uint64_t smatrix_cf_neighbors_batch(smatrix_t* s, const uint32_t* items, size_t 
   ensure_tmp(s, (size_t)nn * 8, ((size_t)nn + 1 + tiles) * 8);
   const uint32_t* d_items = items;
   if (!dev) {
-    CK(cudaMemcpyAsync(s->d_tmp, items, (size_t)nn * 4, cudaMemcpyHostToDevice, s->stream));
+    copy_h2d(s, s->d_tmp, items, (size_t)nn * 4, s->stream);
     d_items = s->d_tmp;
   }
   const uint64_t total = plan_rows(s, d_items, nn, s->d_tmp + nn);
@@ -984,8 +1004,8 @@ uint64_t smatrix_cf_neighbors_batch(smatrix_t* s, const uint32_t* items, size_t 
     smx_launch_cf_scores(s->stream, view_of(s), d_items, nn, s->d_tmp64, s->d_rowbuf, d_ids, d_scores);
     s->n_launches += 2;
     if (!out_dev) {
-      CK(cudaMemcpyAsync(ids, d_ids, (size_t)total * 4, cudaMemcpyDeviceToHost, s->stream));
-      CK(cudaMemcpyAsync(scores, d_scores, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
+      copy_d2h(s, ids, d_ids, (size_t)total * 4, s->stream);
+      copy_d2h(s, scores, d_scores, (size_t)total * 8, s->stream);
       CK(cudaStreamSynchronize(s->stream));
       CK(cudaFree(tmp));
     }
@@ -1000,11 +1020,11 @@ uint64_t smatrix_cf_neighbors_batch(smatrix_t* s, const uint32_t* items, size_t 
 static uint32_t single_write(smatrix_t* s, int api_op, uint32_t x, uint32_t y, uint32_t v) {
   enter(s);
   s->h_small[0] = x; s->h_small[1] = y; s->h_small[2] = v;
-  CK(cudaMemcpyAsync(s->d_small, s->h_small, 12, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, s->d_small, s->h_small, 12, s->stream);
   process_chunk(s, api_op, s->d_small, s->d_small + 1, s->d_small + 2, 1);
   smx_launch_get(s->stream, view_of(s), s->d_small, s->d_small + 1, 1, s->d_small + 3);
   s->n_launches++;
-  CK(cudaMemcpyAsync(&s->h_small[3], s->d_small + 3, 4, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, &s->h_small[3], s->d_small + 3, 4, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   const uint32_t r = s->h_small[3];
   leave(s);
@@ -1024,10 +1044,10 @@ uint32_t smatrix_decr(smatrix_t* self, uint32_t x, uint32_t y, uint32_t value) {
 uint32_t smatrix_get(smatrix_t* s, uint32_t x, uint32_t y) {
   enter(s);
   s->h_small[0] = x; s->h_small[1] = y;
-  CK(cudaMemcpyAsync(s->d_small, s->h_small, 8, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, s->d_small, s->h_small, 8, s->stream);
   smx_launch_get(s->stream, view_of(s), s->d_small, s->d_small + 1, 1, s->d_small + 3);
   s->n_launches++;
-  CK(cudaMemcpyAsync(&s->h_small[3], s->d_small + 3, 4, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, &s->h_small[3], s->d_small + 3, 4, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   const uint32_t r = s->h_small[3];
   leave(s);
@@ -1037,10 +1057,10 @@ uint32_t smatrix_get(smatrix_t* s, uint32_t x, uint32_t y) {
 uint32_t smatrix_rowlen(smatrix_t* s, uint32_t x) {
   enter(s);
   s->h_small[0] = x;
-  CK(cudaMemcpyAsync(s->d_small, s->h_small, 4, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, s->d_small, s->h_small, 4, s->stream);
   smx_launch_rowlen(s->stream, view_of(s), s->d_small, 1, s->d_small + 3);
   s->n_launches++;
-  CK(cudaMemcpyAsync(&s->h_small[3], s->d_small + 3, 4, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, &s->h_small[3], s->d_small + 3, 4, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   const uint32_t r = s->h_small[3];
   leave(s);
@@ -1050,7 +1070,7 @@ uint32_t smatrix_rowlen(smatrix_t* s, uint32_t x) {
 uint32_t smatrix_getrow(smatrix_t* s, uint32_t x, uint32_t* ret, size_t ret_len) {
   enter(s);
   s->h_small[0] = x;
-  CK(cudaMemcpyAsync(s->d_small, s->h_small, 4, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, s->d_small, s->h_small, 4, s->stream);
   ensure_tmp(s, 64, (2 + smx_scan_scratch_items(1)) * 8);
   const uint64_t total = plan_rows(s, s->d_small, 1, s->d_small + 4);
   /* reference loop (src/smatrix.c:196-205): emit, then stop once num*8 >= ret_len */
@@ -1179,10 +1199,10 @@ static int snapshot_save(smatrix_t* s) {
       h_pairs = (uint32_t*)malloc(h_pairs_cap * 4);
       if (!h_pairs) smx_die("out of host memory");
     }
-    CK(cudaMemcpyAsync(h_keys, d_xs, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(h_slog, d_slog, (size_t)len * 4, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(h_off, s->d_tmp64, ((size_t)len + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
-    if (total) CK(cudaMemcpyAsync(h_pairs, s->d_rowbuf, (size_t)total * 8, cudaMemcpyDeviceToHost, s->stream));
+    copy_d2h(s, h_keys, d_xs, (size_t)len * 4, s->stream);
+    copy_d2h(s, h_slog, d_slog, (size_t)len * 4, s->stream);
+    copy_d2h(s, h_off, s->d_tmp64, ((size_t)len + 1) * 8, s->stream);
+    if (total) copy_d2h(s, h_pairs, s->d_rowbuf, (size_t)total * 8, s->stream);
     CK(cudaStreamSynchronize(s->stream));
     /* lay the chunk's row blocks out in one buffer, then one write */
     size_t need = 0;
@@ -1279,8 +1299,8 @@ static int snapshot_load(smatrix_t* s, int fd) {
 #define FLUSH_OPS()  do { if (n) { smatrix_set_batch(s, xs, ys, vs, n); n = 0; } } while (0)
 #define FLUSH_ROWS() do { FLUSH_OPS(); if (nr) {                                                     \
       enter(s); ensure_tmp(s, nr * 8, 0);                                                             \
-      CK(cudaMemcpyAsync(s->d_tmp, rk, nr * 4, cudaMemcpyHostToDevice, s->stream));                   \
-      CK(cudaMemcpyAsync(s->d_tmp + nr, rs, nr * 4, cudaMemcpyHostToDevice, s->stream));              \
+      copy_h2d(s, s->d_tmp, rk, nr * 4, s->stream);                   \
+      copy_h2d(s, s->d_tmp + nr, rs, nr * 4, s->stream);              \
       smx_launch_load_fixup(s->stream, view_of(s), s->d_tmp, s->d_tmp + nr, (uint32_t)nr);            \
       CK(cudaStreamSynchronize(s->stream)); leave(s); nr = 0; } } while (0)
   while (bpos && rc == 0) {
@@ -1543,6 +1563,8 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
         if (s->h_ctl->free_cnt[c] > 0) r += (uint64_t)s->h_ctl->free_cnt[c] * (8ull << c);
       break;
     case SMX_STAT_RECYCLED: r = s->n_recycled; break;
+    case SMX_STAT_H2D_BYTES: r = s->h2d_bytes; break;
+    case SMX_STAT_D2H_BYTES: r = s->d2h_bytes; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;
     case SMX_STAT_SLAB_BYTES: r = s->slab_bytes; break;
     case SMX_STAT_DEVICE_BYTES:
@@ -1589,6 +1611,8 @@ void smatrix_b200_dev_free(smatrix_t* s, void* p) {
 }
 void smatrix_b200_memcpy(smatrix_t* s, void* dst, const void* src, size_t bytes) {
   enter(s);
+  if (!is_device_ptr(src)) { if (is_device_ptr(dst)) s->h2d_bytes += bytes; }
+  else if (!is_device_ptr(dst)) s->d2h_bytes += bytes;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   leave(s);
@@ -1721,7 +1745,7 @@ void smatrix_b200_partition_count(smatrix_t* s, const uint32_t* d_xs, size_t n, 
   unsigned long long h[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
   smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, 0, d_counts);
-  CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, h, d_counts, world * 8, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   for (uint32_t r = 0; r < world; r++) h_counts[r] = h[r];
   s->n_launches++;
@@ -1742,7 +1766,7 @@ void smatrix_b200_route_p2p(smatrix_t* s, const uint32_t* d_xs, const uint32_t* 
   unsigned long long* d_cursors = (unsigned long long*)s->d_tmp64 + 64;
   unsigned long long* d_tab = (unsigned long long*)s->d_tmp64 + 128;
   CK(cudaMemsetAsync(d_cursors, 0, 64 * 8, s->stream));
-  CK(cudaMemcpyAsync(d_tab, h_dst, 5 * (size_t)world * 8, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, d_tab, h_dst, 5 * (size_t)world * 8, s->stream);
   smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER, 0,
                                d_cursors, NULL, NULL, NULL, NULL, NULL, d_out_pos, d_tab, src_bias);
   s->n_launches++;
@@ -1783,7 +1807,7 @@ uint64_t smatrix_b200_scan_counts(smatrix_t* s, const uint32_t* d_counts, size_t
   ensure_tmp(s, 0, ((size_t)smx_scan_scratch_items((uint32_t)n) + 2) * 8);
   smx_launch_scan(s->stream, d_counts, (uint32_t)n, 0, d_offsets, s->d_tmp64);
   s->n_launches += 3;
-  CK(cudaMemcpyAsync(&s->h_small[32], d_offsets + n, 8, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, &s->h_small[32], d_offsets + n, 8, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
   uint64_t total = 0;
@@ -1809,11 +1833,14 @@ void smatrix_b200_getrow_fill_at(smatrix_t* s, const uint32_t* d_xs, size_t n, c
   uint32_t* d_nbig = s->d_cursors + nn;
   /* rows with a big bucket are compacted by the whole grid: find them first */
   smx_launch_row_counts(s->stream, view_of(s), d_xs, nn, s->d_tmp, s->d_big, d_nbig);
-  CK(cudaMemcpyAsync(&s->h_small[34], d_nbig, 4, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, &s->h_small[34], d_nbig, 4, s->stream);
   CK(cudaStreamSynchronize(s->stream));
+  timed_begin(s);
   smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, d_offsets, 0, d_pairs, s->d_big, s->h_small[34], s->d_cursors);
+  timed_end(s);
   s->n_launches += 2;
   CK(cudaStreamSynchronize(s->stream));
+  timed_collect(s);
   CK(cudaGetLastError());
   leave(s);
 }
@@ -1826,7 +1853,7 @@ void smatrix_b200_route_offsets(smatrix_t* s, const uint64_t* d_offsets, const u
   enter(s);
   ensure_tmp(s, 0, (2 * 64 + 5 * 64) * 8);
   unsigned long long* d_tab = (unsigned long long*)s->d_tmp64 + 128;
-  CK(cudaMemcpyAsync(d_tab, h_tab, 2 * (size_t)world * 8, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, d_tab, h_tab, 2 * (size_t)world * 8, s->stream);
   smx_launch_route_offsets(s->stream, d_offsets, d_pos, (uint32_t)n, world, d_tab);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
@@ -1858,6 +1885,8 @@ static cudaStream_t lane_stream(smatrix_t* s, int lane) {
 void smatrix_b200_memcpy_async(smatrix_t* s, void* dst, const void* src, size_t bytes, int lane) {
   if (!bytes) return;
   enter(s);
+  if (!is_device_ptr(src)) s->h2d_bytes += bytes;
+  else if (!is_device_ptr(dst)) s->d2h_bytes += bytes;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, lane_stream(s, lane)));
   leave(s);
 }
@@ -1889,7 +1918,7 @@ void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t*
   unsigned long long h[64], cur[64];
   CK(cudaMemsetAsync(d_counts, 0, 64 * 8, s->stream));
   smx_launch_partition_count(s->stream, d_xs, NULL, (uint32_t)n, world, 0, SMX_PART_OWNER, 0, d_counts);
-  CK(cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s->stream));
+  copy_d2h(s, h, d_counts, world * 8, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   unsigned long long at = 0;
   for (uint32_t r = 0; r < world; r++) {
@@ -1897,7 +1926,7 @@ void smatrix_b200_partition2(smatrix_t* s, const uint32_t* d_xs, const uint32_t*
     at += h[r];
     h_counts[r] = h[r];
   }
-  CK(cudaMemcpyAsync(d_cursors, cur, world * 8, cudaMemcpyHostToDevice, s->stream));
+  copy_h2d(s, d_cursors, cur, world * 8, s->stream);
   smx_launch_partition_scatter(s->stream, d_xs, d_ys, d_vals, (uint32_t)n, world, 0, SMX_PART_OWNER, 0,
                                d_cursors, d_out_xs, d_out_ys, d_out_vals, d_out_src, NULL, d_out_pos, NULL, 0);
   s->n_launches += 2;

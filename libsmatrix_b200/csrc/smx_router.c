@@ -83,6 +83,7 @@ struct smatrix_shard_s {
   uint32_t* stage[2][4];
   size_t stage_cap;
   uint32_t piece;
+  uint64_t stat[8]; /* SMX_SHARD_STAT_* */
 };
 
 /* inbox layout for capacity `cap` ops (cap is a multiple of 256): shared arrays first, then the
@@ -339,6 +340,10 @@ void smatrix_b200_shard_close(smatrix_shard_t* sh) {
   free(sh);
 }
 
+uint64_t smatrix_b200_shard_stat(smatrix_shard_t* sh, int which) {
+  return (which >= 0 && which < 8) ? sh->stat[which] : 0;
+}
+void smatrix_b200_shard_stat_reset(smatrix_shard_t* sh) { memset(sh->stat, 0, sizeof sh->stat); }
 smatrix_t* smatrix_b200_shard_local(smatrix_shard_t* sh) { return sh->local; }
 int smatrix_b200_shard_rank(smatrix_shard_t* sh) { return sh->rank; }
 int smatrix_b200_shard_world(smatrix_shard_t* sh) { return sh->world; }
@@ -376,6 +381,7 @@ static uint64_t rt_in_base(const rt_route_t* R, int s, int o) {
 static void rt_route(smatrix_shard_t* sh, const uint32_t* d_xs, const uint32_t* d_ys, const uint32_t* d_vs,
                      size_t n, int want_ord, int want_pos, rt_route_t* R) {
   const int W = sh->world, me = sh->rank;
+  const double t_begin = rt_now();
   uint64_t mine[RT_MAXW];
   memset(mine, 0, sizeof mine);
   if (n) smatrix_b200_partition_count(sh->local, d_xs, n, (uint32_t)W, mine);
@@ -420,6 +426,10 @@ static void rt_route(smatrix_shard_t* sh, const uint32_t* d_xs, const uint32_t* 
     smatrix_b200_route_p2p(sh->local, d_xs, d_ys, d_vs, n, (uint32_t)W, tab, (uint32_t)R->bias,
                            want_pos ? (uint32_t*)(sh->inbox + OFF_POS(cap)) : NULL);
   rt_barrier(sh); /* every rank's runs have landed (route_p2p returns after its kernel completed) */
+  sh->stat[SMX_SHARD_STAT_ROUTE_NS] += (uint64_t)((rt_now() - t_begin) * 1e9);
+  sh->stat[SMX_SHARD_STAT_ROUTES]++;
+  sh->stat[SMX_SHARD_STAT_REMOTE_BYTES] +=
+      (uint64_t)(n - R->cnt[me][me]) * 4u * (1u + (d_ys != NULL) + (d_vs != NULL) + (want_ord != 0));
 }
 
 /* ------------------------------------------------------------------------------ staging of host arrays */
@@ -440,6 +450,7 @@ static int rt_is_dev(smatrix_shard_t* sh, const void* p) { return p ? smatrix_b2
 static void rt_apply(smatrix_shard_t* sh, int op, int ordered, int has_vals, const rt_route_t* R) {
   if (!R->n_recv) return;
   const uint64_t cap = sh->cap;
+  const double t_begin = rt_now();
   const uint32_t* x = (const uint32_t*)(sh->inbox + OFF_X(cap));
   const uint32_t* y = (const uint32_t*)(sh->inbox + OFF_Y(cap));
   const uint32_t* v = has_vals ? (const uint32_t*)(sh->inbox + OFF_V(cap)) : NULL;
@@ -450,6 +461,7 @@ static void rt_apply(smatrix_shard_t* sh, int op, int ordered, int has_vals, con
   } else {
     smatrix_decr_batch(sh->local, x, y, v, (size_t)R->n_recv);
   }
+  sh->stat[SMX_SHARD_STAT_APPLY_NS] += (uint64_t)((rt_now() - t_begin) * 1e9);
 }
 
 static void rt_write(smatrix_shard_t* sh, int op, const uint32_t* xs, const uint32_t* ys, const uint32_t* vals,

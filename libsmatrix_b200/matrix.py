@@ -132,10 +132,44 @@ class SparseMatrix:
         keep.append(a)
         return a.ctypes.data
 
+    @staticmethod
+    def _len(a) -> int:
+        return a.n if isinstance(a, DevPtr) else (a.numel() if _is_torch(a) else len(a))
+
+    @staticmethod
+    def _on_device(a) -> bool:
+        return isinstance(a, DevPtr) or (_is_torch(a) and a.is_cuda)
+
+    @classmethod
+    def _check_same(cls, arrays):
+        """All batch arrays: the same length and all host or all device — the C side reads n entries from
+        each raw pointer and abort()s the process on mixed placement, so refuse here instead."""
+        arrays = [a for a in arrays if a is not None]
+        n = cls._len(arrays[0])
+        if any(cls._len(a) != n for a in arrays):
+            raise ValueError("batch arrays must have the same length: " + ", ".join(str(cls._len(a)) for a in arrays))
+        if len({cls._on_device(a) for a in arrays}) > 1:
+            raise ValueError("batch arrays must be all host or all device arrays")
+        return n
+
+    @classmethod
+    def _check_out(cls, out, n: int, like):
+        if cls._len(out) < n:
+            raise ValueError(f"out holds {cls._len(out)} entries, the batch has {n}")
+        if cls._on_device(out) != cls._on_device(like):
+            raise ValueError("out must live where the batch arrays live (host or device)")
+        if _is_torch(out):
+            import torch
+            if out.dtype not in (torch.int32, torch.uint32) or not out.is_contiguous():
+                raise TypeError("out must be a contiguous int32 / uint32 tensor")
+        elif isinstance(out, np.ndarray):
+            if out.dtype != np.uint32 or not out.flags.c_contiguous or not out.flags.writeable:
+                raise TypeError("out must be a writable C-contiguous uint32 array")
+
     def _write(self, fn, xs, ys, vals):
         keep: list = []
         px, py, pv = self._arg(xs, keep), self._arg(ys, keep), self._arg(vals, keep)
-        n = keep[0].numel() if _is_torch(keep[0]) else len(keep[0])
+        n = self._check_same(keep)
         fn(self._handle(), px, py, pv, n)
 
     def incr_batch(self, xs, ys, vals=None):
@@ -151,6 +185,7 @@ class SparseMatrix:
         """-> out[i] = what the single-op call i would have returned (input order)."""
         keep: list = []
         px, py, pv = self._arg(xs, keep), self._arg(ys, keep), self._arg(vals, keep)
+        self._check_same(keep)
         if _is_torch(keep[0]):
             import torch
             n = keep[0].numel()
@@ -174,8 +209,9 @@ class SparseMatrix:
     def get_batch(self, xs, ys, out=None):
         keep: list = []
         px, py = self._arg(xs, keep), self._arg(ys, keep)
+        self._check_same(keep)
         if isinstance(keep[0], DevPtr):
-            assert isinstance(out, DevPtr)
+            assert isinstance(out, DevPtr) and out.n >= keep[0].n
             self._lib.smatrix_get_batch(self._handle(), px, py, keep[0].n, out.ptr)
             return out
         if _is_torch(keep[0]):
@@ -183,11 +219,13 @@ class SparseMatrix:
             n = keep[0].numel()
             if out is None:
                 out = torch.empty(n, dtype=torch.int32, device=keep[0].device)
+            self._check_out(out, n, keep[0])
             po = out.data_ptr()
         else:
             n = len(keep[0])
             if out is None:
                 out = np.empty(n, dtype=np.uint32)
+            self._check_out(out, n, keep[0])
             po = out.ctypes.data
         self._lib.smatrix_get_batch(self._handle(), px, py, n, po)
         return out
@@ -201,10 +239,14 @@ class SparseMatrix:
             return out
         if _is_torch(keep[0]):
             import torch
-            out = torch.empty(keep[0].numel(), dtype=torch.int32, device=keep[0].device)
+            if out is None:
+                out = torch.empty(keep[0].numel(), dtype=torch.int32, device=keep[0].device)
+            self._check_out(out, keep[0].numel(), keep[0])
             self._lib.smatrix_rowlen_batch(self._handle(), px, keep[0].numel(), out.data_ptr())
             return out
-        out = np.empty(len(keep[0]), dtype=np.uint32)
+        if out is None:
+            out = np.empty(len(keep[0]), dtype=np.uint32)
+        self._check_out(out, len(keep[0]), keep[0])
         self._lib.smatrix_rowlen_batch(self._handle(), px, len(keep[0]), out.ctypes.data)
         return out
 

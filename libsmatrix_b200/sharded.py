@@ -679,6 +679,13 @@ class ShardedSparseMatrix:
         self._lib.smatrix_b200_shard_reserve(self._handle(), int(max_ops_per_rank), int(max_pairs_per_rank))
         return True
 
+    def route_stats(self, reset: bool = False) -> dict:
+        g = lambda k: int(self._lib.smatrix_b200_shard_stat(self._handle(), k))
+        d = {"route_ms": g(0) / 1e6, "apply_ms": g(1) / 1e6, "routes": g(2), "remote_bytes": g(3)}
+        if reset:
+            self._lib.smatrix_b200_shard_stat_reset(self._handle())
+        return d
+
     def barrier(self):
         self._lib.smatrix_b200_shard_barrier(self._handle())
 

@@ -251,16 +251,7 @@ def gen_c2_queries(seed_get, seed_build, first, count, n_build, rows, ycols):
 
 
 # ---- C3 / C4 streams: inverse-CDF thresholds + the generators of smx_driver.c -------
-def zipf_thresholds(m: int, s: float) -> np.ndarray:
-    """thr[k] = floor(2^64 * CDF(k+1)) for P(k) ~ k^-s, k = 1..m (uint64, last = 2^64 - 1).  Built
-    once per process and handed to BOTH the device generator and this module's, so both draw
-    from the same table."""
-    w = np.arange(1, m + 1, dtype=np.float64) ** (-float(s))
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
-    thr = np.minimum(cdf * 18446744073709551616.0, 18446744073709549568.0).astype(np.uint64)
-    thr[-1] = np.uint64(0xFFFFFFFFFFFFFFFF)
-    return thr
+from libsmatrix_b200.workloads import zipf_thresholds  # noqa: E402,F401 - ONE definition for host and device
 
 
 def gen_c3_ops(seed, first, count, thr):
