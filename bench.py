@@ -522,8 +522,8 @@ def run_write_workload(job: Job, name: str):
     nnz_local, rows_local = m.stat("nnz"), m.stat("rows")
     vsum_local = m.stat("value_sum")     # every op added 1: the table-wide sum must equal the op count
     stats = {k: m.stat(k) for k in ("dir_cap", "slab_bytes", "device_bytes", "row_grows", "dir_grows", "recycled",
-                                    "live_bucket_bytes", "free_bytes")}
-    stats["slab_over_live"] = round(stats["slab_bytes"] / max(1, stats["live_bucket_bytes"]), 3)
+                                    "bucket_bytes", "live_bucket_bytes", "free_bytes")}
+    stats["buckets_over_live"] = round(stats["bucket_bytes"] / max(1, stats["live_bucket_bytes"]), 3)
 
     # ---- timed gets (50 % hits): all queries resident first
     G = wl.gets
@@ -830,8 +830,8 @@ def run_c4(job: Job):
     del bx, by, bv
     nnz_local, rows_local = m.stat("nnz"), m.stat("rows")
     stats = {k: m.stat(k) for k in ("dir_cap", "slab_bytes", "device_bytes", "row_grows", "recycled",
-                                    "live_bucket_bytes", "free_bytes")}
-    stats["slab_over_live"] = round(stats["slab_bytes"] / max(1, stats["live_bucket_bytes"]), 3)
+                                    "bucket_bytes", "live_bucket_bytes", "free_bytes")}
+    stats["buckets_over_live"] = round(stats["bucket_bytes"] / max(1, stats["live_bucket_bytes"]), 3)
 
     # ---- steps: this rank asks for ITS 1/world of the rows (ids interleaved), 1/K of them per step
     K = a.steps or 13

@@ -114,9 +114,11 @@ struct smatrix_s {
   unsigned long long* free_ptr[SMX_CLASSES]; /* device stacks of vacated buckets, per size class */
   uint32_t free_cap[SMX_CLASSES];
   int recycle;                               /* SMATRIX_RECYCLE (default 1) */
+  uint64_t last_chunk_new, last_chunk_ops;   /* rows created by / ops of the previous chunk (presize_dir) */
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
+  uint64_t bucket_bytes;         /* slab bytes handed out for column buckets (fresh, not recycled) */
   uint64_t h2d_bytes, d2h_bytes; /* bytes this handle copied between host and device (SMX_STAT_*_BYTES) */
   double phase_ns[8];
   int timing;
@@ -359,6 +361,7 @@ static void grow_rows(smatrix_t* s, uint32_t n_grow) {
   const size_t bytes = (size_t)s->h_ctl->plan_bytes;
   const uint32_t n_big = s->h_ctl->n_big, n_mid = s->h_ctl->n_mid;
   char* region = bytes ? slab_reserve(s, bytes) : NULL;
+  s->bucket_bytes += bytes;
   if (s->recycle) {
     ensure_free_stacks(s);
     smx_launch_free_push(s->stream, v, s->lists, n_grow);
@@ -397,7 +400,9 @@ static void presize_dir(smatrix_t* s, const smx_ops_t* ops) {
   const uint64_t n = ops->n, used = s->h_ctl->dir_used;
   if (n < s->part_min || !s->presize) return;      /* small batches: the grow loop is cheap        */
   if (used + n <= s->dir_cap / 4) return;          /* fits even if every op creates a row           */
-  if (4 * used >= n) return;                       /* mostly existing rows: let the grow loop decide */
+  /* worth a pass over the chunk only while chunks still bring many new rows: the table is empty, or
+   * the previous chunk created a row with at least every 16th op */
+  if (used && s->last_chunk_new * 16 < s->last_chunk_ops) return;
   const uint64_t m = 1ull << SMX_SKETCH_BITS_LOG;
   ensure_tmp(s, (size_t)(m / 8), 0);
   CK(cudaMemsetAsync(s->d_tmp, 0, (size_t)(m / 8), s->stream));
@@ -580,6 +585,7 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = d_ords; ops.v_const = 1u; ops.n = n;
 
   presize_dir(s, &ops);
+  const uint64_t rows_before = s->h_ctl->dir_used;
   uint32_t n_main = n;
   const int parted = (n >= s->part_min) ? partition_chunk(s, &ops, api_op, &n_main) : 0;
   /* partitioned: [0, n_main) = ops on columns != 0, [n_main, n) = ops on column 0 (dense ranges);
@@ -612,6 +618,8 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
     smx_launch_finalize_t0(s->stream, view_of(s), s->lists.t0rows, n_t0);
     s->n_launches++;
   }
+  s->last_chunk_new = s->h_ctl->dir_used > rows_before ? s->h_ctl->dir_used - rows_before : 0;
+  s->last_chunk_ops = n;
   maybe_shrink_dir(s);
 }
 
@@ -1543,13 +1551,22 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
       read_ctl(s);
       r = s->h_ctl->scratch;
       break;
-    case SMX_STAT_VALUE_SUM:
+    case SMX_STAT_VALUE_SUM: {
+      read_ctl(s);
+      const size_t rows = (size_t)s->h_ctl->dir_used;
+      ensure_tmp(s, (rows + 2) * 4, 0); /* list of the rows with a big bucket + its counter */
+      uint32_t* d_cnt = s->d_tmp + rows + 1;
       CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
-      smx_launch_sum_values(s->stream, view_of(s));
-      s->n_launches++;
+      CK(cudaMemsetAsync(d_cnt, 0, 4, s->stream));
+      smx_launch_sum_values(s->stream, view_of(s), s->d_tmp, d_cnt);
+      copy_d2h(s, &s->h_small[36], d_cnt, 4, s->stream);
+      CK(cudaStreamSynchronize(s->stream));
+      smx_launch_sum_values_big(s->stream, view_of(s), s->d_tmp, s->h_small[36]);
+      s->n_launches += 2;
       read_ctl(s);
       r = s->h_ctl->scratch;
       break;
+    }
     case SMX_STAT_LIVE_BUCKET_BYTES:
       CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
       smx_launch_live_bytes(s->stream, view_of(s));
@@ -1563,6 +1580,7 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
         if (s->h_ctl->free_cnt[c] > 0) r += (uint64_t)s->h_ctl->free_cnt[c] * (8ull << c);
       break;
     case SMX_STAT_RECYCLED: r = s->n_recycled; break;
+    case SMX_STAT_BUCKET_BYTES: r = s->bucket_bytes; break;
     case SMX_STAT_H2D_BYTES: r = s->h2d_bytes; break;
     case SMX_STAT_D2H_BYTES: r = s->d2h_bytes; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;

@@ -162,7 +162,8 @@ void smx_launch_getrow_fill(smx_stream_t stream, smx_view_t v, const uint32_t* x
                             const uint64_t* offsets, uint64_t offset_bias, uint32_t* pairs,
                             const uint32_t* big_list, uint32_t n_big, uint32_t* cursors /* [n], zeroed */);
 void smx_launch_count_nnz(smx_stream_t stream, smx_view_t v);
-void smx_launch_sum_values(smx_stream_t stream, smx_view_t v);
+void smx_launch_sum_values(smx_stream_t stream, smx_view_t v, uint32_t* big_list /* [rows] */, uint32_t* big_counter /* zeroed */);
+void smx_launch_sum_values_big(smx_stream_t stream, smx_view_t v, const uint32_t* big_list, uint32_t n_big);
 void smx_launch_cf_scores(smx_stream_t stream, smx_view_t v, const uint32_t* items, uint32_t n,
                           const uint64_t* offsets, const uint32_t* pairs, uint32_t* ids, double* scores);
 void smx_launch_list_rows(smx_stream_t stream, smx_view_t v, uint32_t* keys, uint32_t* counter /* zeroed */);

@@ -1123,7 +1123,7 @@ k_load_fixup(smx_view_t V, const uint32_t* xs, const uint32_t* slogs, uint32_t n
 /* sum of every stored value (all cells + column 0) mod 2^64 -> ctl->scratch: one warp per
  * directory entry walks that row's bucket.  For an incr-only build this must equal the sum of all
  * increments — the size-independent invariant bench.py checks at full scale. */
-__global__ void __launch_bounds__(SMX_BLOCK) k_sum_values(smx_view_t V) {
+__global__ void __launch_bounds__(SMX_BLOCK) k_sum_values(smx_view_t V, uint32_t* big_list, uint32_t* big_counter) {
   const uint32_t lane = lane_id();
   const ull warp = (blockIdx.x * (ull)blockDim.x + threadIdx.x) / SMX_WARP;
   const ull nwarps = (ull)gridDim.x * blockDim.x / SMX_WARP;
@@ -1134,12 +1134,26 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_sum_values(smx_view_t V) {
     if (!(h.meta & SMX_META_USED)) continue;
     if (lane == 0) acc += h.c0;
     const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+    if (caplog >= SMX_BIG_LOG) { /* a bucket of megabytes is not one warp's job: k_sum_values_big */
+      if (lane == 0) big_list[atomicAdd(big_counter, 1u)] = (uint32_t)pos;
+      continue;
+    }
     const ull* base = (caplog == SMX_INLINE_LOG) ? (const ull*)e->inl : (const ull*)h.slots;
     const ull cap = 1ull << caplog;
     for (ull c = lane; c < cap; c += SMX_WARP) acc += base[c] >> 32;
   }
   for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(SMX_FULL, acc, d);
   if (lane == 0 && acc) atomicAdd(&V.ctl->scratch, acc);
+}
+/* big rows: the grid (x) strides over the bucket of one row (y) */
+__global__ void __launch_bounds__(SMX_BLOCK) k_sum_values_big(smx_view_t V, const uint32_t* big_list, uint32_t first) {
+  const Hdr h = ld_hdr(V.dir + big_list[first + blockIdx.y]);
+  const ull* base = (const ull*)h.slots;
+  const ull cap = 1ull << (h.meta & SMX_META_CAPLOG);
+  ull acc = 0;
+  for (ull c = blockIdx.x * (ull)blockDim.x + threadIdx.x; c < cap; c += (ull)gridDim.x * blockDim.x) acc += base[c] >> 32;
+  for (uint32_t d = SMX_WARP / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(SMX_FULL, acc, d);
+  if (lane_id() == 0 && acc) atomicAdd(&V.ctl->scratch, acc);
 }
 
 /* nnz = sum over rows of live + (c0 != 0) -> ctl->scratch */
@@ -1740,8 +1754,15 @@ extern "C" void smx_launch_cf_scores(smx_stream_t st, smx_view_t v, const uint32
   SMX_LAUNCH(k_cf_scores, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, items, n, (const ull*)offsets,
              pairs, ids, scores);
 }
-extern "C" void smx_launch_sum_values(smx_stream_t st, smx_view_t v) {
-  SMX_LAUNCH(k_sum_values, grid_for(v.dir_cap * SMX_WARP), SMX_BLOCK, st, v);
+extern "C" void smx_launch_sum_values(smx_stream_t st, smx_view_t v, uint32_t* big_list, uint32_t* big_counter) {
+  SMX_LAUNCH(k_sum_values, grid_for(v.dir_cap * SMX_WARP), SMX_BLOCK, st, v, big_list, big_counter);
+}
+extern "C" void smx_launch_sum_values_big(smx_stream_t st, smx_view_t v, const uint32_t* big_list, uint32_t n_big) {
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? 32u : 2u, cnt, 1u);
+    SMX_LAUNCH(k_sum_values_big, grid, SMX_BLOCK, st, v, big_list, first);
+  }
 }
 extern "C" void smx_launch_count_nnz(smx_stream_t st, smx_view_t v) {
   SMX_LAUNCH(k_count_nnz, grid_for(v.dir_cap), SMX_BLOCK, st, v);

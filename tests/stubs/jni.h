@@ -1,6 +1,7 @@
 /* tests/stubs/jni.h — TEST SCAFFOLDING: the slice of the JNI C interface that the reference's
- * src/smatrix_jni.c uses, enough to COMPILE AND LINK that file unchanged against include/smatrix.h
- * and our library (no JDK in this image).  Not a working JVM interface. */
+ * src/smatrix_jni.c and examples/jni/smatrix_jni_batch.c use, enough to COMPILE AND LINK them against
+ * include/smatrix.h and our library (no JDK in this image), and — with
+ * tests/stubs/fake_jvm.c, a toy implementation of this table — to EXECUTE them.  Not a JVM. */
 #ifndef SMX_STUB_JNI_H
 #define SMX_STUB_JNI_H
 #include <stdint.h>
@@ -14,6 +15,11 @@ typedef jobject jstring;
 typedef void* jfieldID;
 typedef void* jmethodID;
 typedef unsigned char jboolean;
+typedef jint jsize;
+typedef jobject jarray;
+typedef jarray jintArray;
+typedef jarray jlongArray;
+#define JNI_ABORT 2
 struct JNINativeInterface_;
 typedef const struct JNINativeInterface_* JNIEnv;
 struct JNINativeInterface_ {
@@ -27,5 +33,14 @@ struct JNINativeInterface_ {
   jclass (*GetObjectClass)(JNIEnv*, jobject);
   jmethodID (*GetMethodID)(JNIEnv*, jclass, const char*, const char*);
   void (*CallVoidMethod)(JNIEnv*, jobject, jmethodID, ...);
+  /* primitive arrays (examples/jni/smatrix_jni_batch.c) */
+  jsize (*GetArrayLength)(JNIEnv*, jarray);
+  void* (*GetPrimitiveArrayCritical)(JNIEnv*, jarray, jboolean*);
+  void (*ReleasePrimitiveArrayCritical)(JNIEnv*, jarray, void*, jint);
+  jintArray (*NewIntArray)(JNIEnv*, jsize);
+  jint* (*GetIntArrayElements)(JNIEnv*, jintArray, jboolean*);
+  void (*ReleaseIntArrayElements)(JNIEnv*, jintArray, jint*, jint);
+  jlong* (*GetLongArrayElements)(JNIEnv*, jlongArray, jboolean*);
+  void (*ReleaseLongArrayElements)(JNIEnv*, jlongArray, jlong*, jint);
 };
 #endif
