@@ -106,6 +106,7 @@ struct smatrix_s {
   uint32_t* bo_out;
   void* bo_sort;
   size_t bo_sort_bytes;
+  uint64_t* d_info;     /* getrow: per-row directory index | caplog << 32 (k_row_counts) */
   uint32_t* d_big;      /* getrow: indices of big rows in the current query + per-row output cursors */
   uint32_t* d_cursors;
   size_t d_big_bytes;
@@ -659,9 +660,12 @@ static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint
   if (is_device_ptr(ys) != dev || (vs && is_device_ptr(vs) != dev))
     smx_die("batch arrays must be all host or all device pointers");
   if (dev) {
-    for (size_t off = 0; off < n; off += s->chunk_max) {
-      const uint32_t len = (uint32_t)((n - off < s->chunk_max) ? n - off : s->chunk_max);
-      process_chunk(s, api_op, xs + off, ys + off, vs ? vs + off : NULL, len);
+    /* equal chunks: a batch a little over k * chunk_max must not end in a sliver that pays a whole
+     * chunk's launches and round trips (the multi-GPU inbox holds 2^26 +- a few thousand ops) */
+    const size_t pieces = (n + s->chunk_max - 1) / s->chunk_max;
+    for (size_t k = 0; k < pieces; k++) {
+      const size_t off = n * k / pieces, end = n * (k + 1) / pieces;
+      process_chunk(s, api_op, xs + off, ys + off, vs ? vs + off : NULL, (uint32_t)(end - off));
     }
     CK(cudaStreamSynchronize(s->stream));
   } else {
@@ -893,19 +897,24 @@ void smatrix_rowlen_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint32_t* 
 
 /* counts + scan for rows xs[0..n) (device array); leaves offsets in d_tmp64[0..n], the list of
  * big rows in s->d_big[0..s->n_big) and zeroed per-row cursors in s->d_cursors; returns total */
-static uint64_t plan_rows(smatrix_t* s, const uint32_t* d_xs, uint32_t n, uint32_t* d_counts) {
-  const uint32_t tiles = smx_scan_scratch_items(n);
-  if ((size_t)n * 8 + 64 > s->d_big_bytes) {
-    if (s->d_big) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_big); }
-    s->d_big_bytes = (size_t)n * 8 + 4096;
-    s->d_big = (uint32_t*)dmalloc(s, s->d_big_bytes);
+/* scratch of the getrow plan for n rows: info (u64), list of big rows (u32), output cursors (u32) + counter */
+static uint32_t* ensure_rowplan(smatrix_t* s, uint32_t n) {
+  const size_t need = (size_t)n * 16 + 64;
+  if (need > s->d_big_bytes) {
+    if (s->d_info) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_info); }
+    s->d_big_bytes = need + need / 4 + 4096;
+    s->d_info = (uint64_t*)dmalloc(s, s->d_big_bytes);
   }
+  s->d_big = (uint32_t*)(s->d_info + n);
   s->d_cursors = s->d_big + n;
   CK(cudaMemsetAsync(s->d_cursors, 0, (size_t)n * 4 + 8, s->stream));
-  uint32_t* d_nbig = s->d_cursors + n; /* one counter word after the cursors */
-  smx_launch_row_counts(s->stream, view_of(s), d_xs, n, d_counts, s->d_big, d_nbig);
+  return s->d_cursors + n; /* one counter word after the cursors */
+}
+
+static uint64_t plan_rows(smatrix_t* s, const uint32_t* d_xs, uint32_t n, uint32_t* d_counts) {
+  uint32_t* d_nbig = ensure_rowplan(s, n);
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, n, d_counts, s->d_info, s->d_big, d_nbig);
   smx_launch_scan(s->stream, d_counts, n, 0, s->d_tmp64, s->d_tmp64 + (size_t)n + 1);
-  (void)tiles;
   s->n_launches += 4;
   uint64_t total = 0;
   copy_d2h(s, &s->h_small[32], s->d_tmp64 + n, 8, s->stream);
@@ -949,7 +958,7 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
     filled = 1;
     if (is_device_ptr(pairs)) {
       timed_begin(s);
-      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, pairs, s->d_big, s->n_big_rows, s->d_cursors);
+      smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, nn, s->d_tmp64, 0, pairs, s->d_big, s->n_big_rows, s->d_cursors);
       timed_end(s);
       s->n_launches++;
     } else {
@@ -959,7 +968,7 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
         s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
       }
       timed_begin(s);
-      smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
+      smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
       timed_end(s);
       s->n_launches++;
       copy_d2h(s, pairs, s->d_rowbuf, (size_t)total * 8, s->stream);
@@ -998,7 +1007,7 @@ uint64_t smatrix_cf_neighbors_batch(smatrix_t* s, const uint32_t* items, size_t 
       s->d_rowbuf_bytes = (size_t)total * 8;
       s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
     }
-    smx_launch_getrow_fill(s->stream, view_of(s), d_items, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
+    smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, nn, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
     const int out_dev = is_device_ptr(ids);
     if (is_device_ptr(scores) != out_dev) smx_die("batch arrays must be all host or all device pointers");
     uint32_t* d_ids = ids;
@@ -1091,7 +1100,7 @@ uint32_t smatrix_getrow(smatrix_t* s, uint32_t x, uint32_t* ret, size_t ret_len)
       s->d_rowbuf_bytes = (size_t)total * 8;
       s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
     }
-    smx_launch_getrow_fill(s->stream, view_of(s), s->d_small, 1, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
+    smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, 1, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
     s->n_launches++;
     CK(cudaMemcpyAsync(ret, s->d_rowbuf, (size_t)n * 8, cudaMemcpyDefault, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -1200,7 +1209,7 @@ static int snapshot_save(smatrix_t* s) {
       s->d_rowbuf_bytes = (size_t)total * 8 + 4096;
       s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
     }
-    if (total) smx_launch_getrow_fill(s->stream, view_of(s), d_xs, len, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
+    if (total) smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, len, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
     if (total * 2 > h_pairs_cap) {
       free(h_pairs);
       h_pairs_cap = (size_t)total * 2 + 1024;
@@ -1481,7 +1490,7 @@ void smatrix_close(smatrix_t* s) {
   if (s->d_tmp) cudaFree(s->d_tmp);
   if (s->d_tmp64) cudaFree(s->d_tmp64);
   if (s->d_rowbuf) cudaFree(s->d_rowbuf);
-  if (s->d_big) cudaFree(s->d_big);
+  if (s->d_info) cudaFree(s->d_info);
   if (s->bo_cap) {
     cudaFree(s->bo_addr[0]); cudaFree(s->bo_addr[1]); cudaFree(s->bo_idx[0]); cudaFree(s->bo_idx[1]);
     cudaFree(s->bo_seg); cudaFree(s->bo_tiles); cudaFree(s->bo_out); cudaFree(s->bo_sort);
@@ -1812,7 +1821,7 @@ void smatrix_b200_row_counts_batch(smatrix_t* s, const uint32_t* d_xs, size_t n,
   if (n == 0) return;
   if (n >= 0xFFFFFFFFull) smx_die("row_counts: batch too large");
   enter(s);
-  smx_launch_row_counts(s->stream, view_of(s), d_xs, (uint32_t)n, d_counts, NULL, NULL);
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, (uint32_t)n, d_counts, NULL, NULL, NULL);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());
@@ -1841,20 +1850,13 @@ void smatrix_b200_getrow_fill_at(smatrix_t* s, const uint32_t* d_xs, size_t n, c
   enter(s);
   const uint32_t nn = (uint32_t)n;
   ensure_tmp(s, (size_t)nn * 4, 0);
-  if ((size_t)nn * 8 + 64 > s->d_big_bytes) {
-    if (s->d_big) { CK(cudaStreamSynchronize(s->stream)); cudaFree(s->d_big); }
-    s->d_big_bytes = (size_t)nn * 8 + 4096;
-    s->d_big = (uint32_t*)dmalloc(s, s->d_big_bytes);
-  }
-  s->d_cursors = s->d_big + nn;
-  CK(cudaMemsetAsync(s->d_cursors, 0, (size_t)nn * 4 + 8, s->stream));
-  uint32_t* d_nbig = s->d_cursors + nn;
-  /* rows with a big bucket are compacted by the whole grid: find them first */
-  smx_launch_row_counts(s->stream, view_of(s), d_xs, nn, s->d_tmp, s->d_big, d_nbig);
+  uint32_t* d_nbig = ensure_rowplan(s, nn);
+  /* resolve the rows (directory index, bucket size) and find the ones the whole grid compacts */
+  smx_launch_row_counts(s->stream, view_of(s), d_xs, nn, s->d_tmp, s->d_info, s->d_big, d_nbig);
   copy_d2h(s, &s->h_small[34], d_nbig, 4, s->stream);
   CK(cudaStreamSynchronize(s->stream));
   timed_begin(s);
-  smx_launch_getrow_fill(s->stream, view_of(s), d_xs, nn, d_offsets, 0, d_pairs, s->d_big, s->h_small[34], s->d_cursors);
+  smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, nn, d_offsets, 0, d_pairs, s->d_big, s->h_small[34], s->d_cursors);
   timed_end(s);
   s->n_launches += 2;
   CK(cudaStreamSynchronize(s->stream));

@@ -155,10 +155,11 @@ void smx_launch_get(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const
 void smx_launch_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
                        uint32_t* out);
 void smx_launch_row_counts(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
-                           uint32_t* counts, uint32_t* big_list /* nullable */, uint32_t* big_counter);
+                           uint32_t* counts, uint64_t* info /* nullable: directory index | caplog << 32 per row */,
+                           uint32_t* big_list /* nullable */, uint32_t* big_counter);
 void smx_launch_scan(smx_stream_t stream, const uint32_t* counts, uint32_t n, uint64_t base,
                      uint64_t* offsets /* n+1 */, uint64_t* block_sums /* scratch */);
-void smx_launch_getrow_fill(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,
+void smx_launch_getrow_fill(smx_stream_t stream, smx_view_t v, const uint64_t* info, uint32_t n,
                             const uint64_t* offsets, uint64_t offset_bias, uint32_t* pairs,
                             const uint32_t* big_list, uint32_t n_big, uint32_t* cursors /* [n], zeroed */);
 void smx_launch_count_nnz(smx_stream_t stream, smx_view_t v);

@@ -886,69 +886,94 @@ k_rowlen(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* out) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * K6: getrow for a batch of rows -> CSR
+ * K6: getrow for a batch of rows -> CSR (replaces smatrix_getrow, src/smatrix.c:189-210, for whole
+ * batches).  k_row_counts resolves every row ONCE (directory probe) and leaves, besides the pair
+ * count, an `info` word per row (directory index | log2 capacity << 32, ~0 = no such row) that the
+ * compaction kernels start from; the exclusive scan of the counts gives the CSR offsets; then three
+ * compaction kernels, by bucket size:
+ *   k_getrow_inline  rows that never left their directory entry (<= 4 cells): one THREAD per row
+ *   k_getrow_fill    16 .. 1024 cells: one WARP per row, 16-byte loads, the live cells of a 64-cell
+ *                    step are compacted with a warp prefix-sum, staged in shared memory and written
+ *                    out as one contiguous run
+ *   k_getrow_chunks  >= 2048 cells: the bucket is cut into 2048-cell chunks that all blocks of the
+ *                    grid share; a chunk is compacted in shared memory (block prefix-sum), reserves
+ *                    its output range with one atomic on the row's cursor and streams out
  * ---------------------------------------------------------------------------------------- */
+#define SMX_GETROW_BIG_LOG 11u
+#define SMX_NO_ROW 0xFFFFFFFFFFFFFFFFull
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_row_counts(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* counts, uint32_t* big_list,
+k_row_counts(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* counts, ull* info, uint32_t* big_list,
              uint32_t* big_counter) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     smx_row_t* e;
     Hdr h;
     uint32_t c = 0u;
+    ull inf = SMX_NO_ROW;
     if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) {
       c = h.live + (h.c0 != 0u ? 1u : 0u);
-      /* rows with a big bucket are compacted by the whole grid (k_getrow_big), not by one warp */
-      if (big_list && (h.meta & SMX_META_CAPLOG) >= SMX_BIG_LOG) big_list[agg_inc(big_counter)] = i;
+      const uint32_t caplog = h.meta & SMX_META_CAPLOG;
+      inf = (ull)(e - V.dir) | ((ull)caplog << 32);
+      if (big_list && caplog >= SMX_GETROW_BIG_LOG) big_list[agg_inc(big_counter)] = i;
     }
     counts[i] = c;
+    if (info) info[i] = inf;
   }
 }
 
+/* exclusive scan of one value per thread over the block (warp shuffles + one shared-memory hop);
+ * returns the exclusive prefix, *total = the block's sum */
+__device__ __forceinline__ ull block_exclusive_scan(ull v, ull* total) {
+  __shared__ ull s_warp[SMX_BLOCK / SMX_WARP + 1];
+  const uint32_t lane = lane_id(), wib = threadIdx.x / SMX_WARP;
+  ull incl = v;
+  for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+    const ull t = __shfl_up_sync(SMX_FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  __syncthreads(); /* s_warp may still be read from a previous call */
+  if (lane == SMX_WARP - 1) s_warp[wib] = incl;
+  __syncthreads();
+  if (wib == 0) {
+    const uint32_t nw = blockDim.x / SMX_WARP;
+    ull w = lane < nw ? s_warp[lane] : 0ull, wi = w;
+    for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+      const ull t = __shfl_up_sync(SMX_FULL, wi, d);
+      if (lane >= d) wi += t;
+    }
+    if (lane < nw) s_warp[lane] = wi - w;
+    if (lane == nw - 1) s_warp[nw] = wi;
+  }
+  __syncthreads();
+  *total = s_warp[blockDim.x / SMX_WARP];
+  return s_warp[wib] + incl - v;
+}
 
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_scan_tile_sums(const uint32_t* counts, uint32_t n, ull* tile_sums) {
-  __shared__ ull sh[SMX_BLOCK];
   const ull first = (ull)blockIdx.x * SCAN_TILE + (ull)threadIdx.x * SCAN_PER_THREAD;
   ull s = 0;
   for (int k = 0; k < SCAN_PER_THREAD; ++k)
     if (first + k < n) s += counts[first + k];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ull t = 0;
-    for (uint32_t k = 0; k < blockDim.x; ++k) t += sh[k];
-    tile_sums[blockIdx.x] = t;
-  }
+  ull total;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 /* one block: exclusive scan of the tile sums, total goes to offsets[n] */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_scan_tiles(ull* tile_sums, uint32_t n_tiles, ull base, ull* offsets, uint32_t n) {
-  __shared__ ull sh[SMX_BLOCK];
-  __shared__ ull carry;
-  if (threadIdx.x == 0) carry = base;
-  __syncthreads();
+  ull carry = base;
   for (uint32_t t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
     const uint32_t t = t0 + threadIdx.x;
-    sh[threadIdx.x] = (t < n_tiles) ? tile_sums[t] : 0ull;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      ull run = carry;
-      for (uint32_t k = 0; k < blockDim.x; ++k) {
-        ull v = sh[k];
-        sh[k] = run;
-        run += v;
-      }
-      carry = run;
-    }
-    __syncthreads();
-    if (t < n_tiles) tile_sums[t] = sh[threadIdx.x];
-    __syncthreads();
+    const ull v = (t < n_tiles) ? tile_sums[t] : 0ull;
+    ull total;
+    const ull excl = block_exclusive_scan(v, &total);
+    if (t < n_tiles) tile_sums[t] = carry + excl;
+    carry += total;
   }
   if (threadIdx.x == 0) offsets[n] = carry;
 }
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_scan_apply(const uint32_t* counts, uint32_t n, const ull* tile_sums, ull* offsets) {
-  __shared__ ull sh[SMX_BLOCK];
   const ull first = (ull)blockIdx.x * SCAN_TILE + (ull)threadIdx.x * SCAN_PER_THREAD;
   uint32_t c[SCAN_PER_THREAD];
   ull s = 0;
@@ -956,52 +981,69 @@ k_scan_apply(const uint32_t* counts, uint32_t n, const ull* tile_sums, ull* offs
     c[k] = (first + k < n) ? counts[first + k] : 0u;
     s += c[k];
   }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ull run = tile_sums[blockIdx.x];
-    for (uint32_t k = 0; k < blockDim.x; ++k) {
-      ull v = sh[k];
-      sh[k] = run;
-      run += v;
-    }
-  }
-  __syncthreads();
-  ull run = sh[threadIdx.x];
+  ull total;
+  ull run = tile_sums[blockIdx.x] + block_exclusive_scan(s, &total);
   for (int k = 0; k < SCAN_PER_THREAD; ++k) {
     if (first + k < n) offsets[first + k] = run;
     run += c[k];
   }
 }
 
-/* one warp per row: 16-byte loads, ballot-free warp prefix over per-lane live counts */
+/* 16-byte load of two adjacent cells */
+__device__ __forceinline__ void ld_cells2(const ull* p, ull* a, ull* b) {
+#ifdef SMX_HOSTSIM
+  *a = p[0]; *b = p[1];
+#else
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+  *a = v.x; *b = v.y;
+#endif
+}
+
+/* rows that live in their directory entry: one thread per row */
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, ull bias,
-              uint32_t* pairs, int skip_big) {
-  const uint32_t lane = lane_id();
+k_getrow_inline(smx_view_t V, const ull* info, uint32_t n, const ull* offsets, ull bias, uint32_t* pairs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const ull inf = info[i];
+    if (inf == SMX_NO_ROW || (uint32_t)(inf >> 32) != SMX_INLINE_LOG) continue;
+    const smx_row_t* e = V.dir + (uint32_t)inf;
+    ull hdr[4], c[4];
+    ld_hsector(e, hdr);
+    ld_hsector((const char*)e + 32, c);
+    ull* out = (ull*)pairs + (offsets[i] - bias);
+    const uint32_t c0 = (uint32_t)(hdr[2] >> 32);
+    if (c0 != 0u) *out++ = (ull)c0 << 32; /* (column 0, c0) */
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c[k] != 0ull) *out++ = c[k];
+  }
+}
+
+/* one warp per row, buckets of 16 .. 2^(SMX_GETROW_BIG_LOG-1) cells */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_getrow_fill(smx_view_t V, const ull* info, uint32_t n, const ull* offsets, ull bias, uint32_t* pairs) {
+  __shared__ ull s_out[SMX_BLOCK / SMX_WARP][2 * SMX_WARP];
+  const uint32_t lane = lane_id(), wib = threadIdx.x / SMX_WARP;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
   const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
+  ull* stage = s_out[wib];
   for (uint32_t i = warp; i < n; i += nwarps) {
-    smx_row_t* e;
-    Hdr h;
-    if (dir_find(V, xs[i], false, &e, &h) != DIR_FOUND) continue;
-    if (skip_big && (h.meta & SMX_META_CAPLOG) >= SMX_BIG_LOG) continue;
+    const ull inf = info[i];
+    const uint32_t caplog = (uint32_t)(inf >> 32);
+    if (inf == SMX_NO_ROW || caplog == SMX_INLINE_LOG || caplog >= SMX_GETROW_BIG_LOG) continue;
+    const smx_row_t* e = V.dir + (uint32_t)inf;
+    const Hdr h = ld_hdr(e);
     ull* out = (ull*)pairs + (offsets[i] - bias);
     ull pos = 0;
     if (h.c0 != 0u) {
       if (lane == 0) out[0] = (ull)h.c0 << 32; /* (column 0, c0) */
       pos = 1;
     }
-    const uint32_t caplog = h.meta & SMX_META_CAPLOG;
-    const ull* base = (caplog == SMX_INLINE_LOG) ? (const ull*)e->inl : (const ull*)h.slots;
+    const ull* base = (const ull*)h.slots;
     const ull cap = 1ull << caplog;
     for (ull s0 = 0; s0 < cap; s0 += 2ull * SMX_WARP) {
       const ull s = s0 + 2ull * lane;
       ull a = 0, b = 0;
-      if (s < cap) { /* cap is a multiple of 4, s is even: both cells are in range */
-        a = base[s];
-        b = base[s + 1];
-      }
+      if (s < cap) ld_cells2(base + s, &a, &b); /* cap is a multiple of 4, s is even: both cells are in range */
       const uint32_t mine = (a != 0ull) + (b != 0ull);
       uint32_t incl = mine;
       for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
@@ -1009,46 +1051,55 @@ k_getrow_fill(smx_view_t V, const uint32_t* xs, uint32_t n, const ull* offsets, 
         if (lane >= d) incl += t;
       }
       const uint32_t total = __shfl_sync(SMX_FULL, incl, SMX_WARP - 1);
-      ull w = pos + incl - mine;
-      if (a != 0ull) out[w++] = a;
-      if (b != 0ull) out[w] = b;
+      uint32_t w = incl - mine; /* compact into shared memory, then one contiguous run goes out */
+      if (a != 0ull) stage[w++] = a;
+      if (b != 0ull) stage[w] = b;
+      __syncwarp();
+      for (uint32_t k = lane; k < total; k += SMX_WARP) out[pos + k] = stage[k];
+      __syncwarp();
       pos += total;
     }
   }
 }
 
-/* big rows: every warp of the grid (x) takes 64-cell pieces of one row's bucket (y) and reserves
- * its output range with one atomic on the row's cursor; pair order inside the row is arbitrary */
+/* big rows (>= 2^SMX_GETROW_BIG_LOG cells), cut into chunks of GETROW_CHUNK cells that the blocks of a
+ * persistent grid share; pair order inside a row is arbitrary (the contract compares sorted) */
+#define GETROW_CHUNK_LOG 11u
+#define GETROW_CHUNK (1u << GETROW_CHUNK_LOG)
+#define GETROW_PER_THREAD (GETROW_CHUNK / SMX_BLOCK) /* 8 cells = 4 x 16-byte loads per thread */
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_getrow_big(smx_view_t V, const uint32_t* xs, const uint32_t* big_list, uint32_t big_first,
-             const ull* offsets, ull bias, uint32_t* pairs, uint32_t* cursors) {
-  const uint32_t lane = lane_id();
-  const uint32_t i = big_list[big_first + blockIdx.y];
-  smx_row_t* e;
-  Hdr h;
-  if (dir_find(V, xs[i], false, &e, &h) != DIR_FOUND) return;
-  ull* out = (ull*)pairs + (offsets[i] - bias);
-  const ull* base = (const ull*)h.slots;
-  const ull cap = 1ull << (h.meta & SMX_META_CAPLOG);
-  const ull warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
-  const ull nwarps = (ull)gridDim.x * blockDim.x / SMX_WARP;
-  if (warp == 0 && lane == 0 && h.c0 != 0u) out[atomicAdd(&cursors[i], 1u)] = (ull)h.c0 << 32;
-  for (ull s0 = warp * 2ull * SMX_WARP; s0 < cap; s0 += nwarps * 2ull * SMX_WARP) {
-    const ull s = s0 + 2ull * lane;
-    const ull a = base[s], b = base[s + 1]; /* cap is a multiple of 2 * SMX_WARP here */
-    const uint32_t mine = (a != 0ull) + (b != 0ull);
-    uint32_t incl = mine;
-    for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
-      uint32_t t = __shfl_up_sync(SMX_FULL, incl, d);
-      if (lane >= d) incl += t;
+k_getrow_chunks(smx_view_t V, const ull* info, const uint32_t* big_list, uint32_t n_big, const ull* offsets,
+                ull bias, uint32_t* pairs, uint32_t* cursors) {
+  __shared__ ull s_stage[GETROW_CHUNK + 1];
+  __shared__ uint32_t s_base;
+  for (uint32_t b = 0; b < n_big; ++b) {
+    const uint32_t i = big_list[b];
+    const ull inf = info[i];
+    const ull nchunks = (1ull << (uint32_t)(inf >> 32)) >> GETROW_CHUNK_LOG;
+    /* rotate the first block of every row so that short rows do not all land on blocks 0, 1, ... */
+    for (ull c = (blockIdx.x + gridDim.x - (b * 61u) % gridDim.x) % gridDim.x; c < nchunks; c += gridDim.x) {
+      const smx_row_t* e = V.dir + (uint32_t)inf;
+      const Hdr h = ld_hdr(e);
+      const ull* base = (const ull*)h.slots + (c << GETROW_CHUNK_LOG) + (ull)threadIdx.x * GETROW_PER_THREAD;
+      ull cell[GETROW_PER_THREAD];
+#pragma unroll
+      for (int k = 0; k < (int)GETROW_PER_THREAD; k += 2) ld_cells2(base + k, &cell[k], &cell[k + 1]);
+      uint32_t mine = 0;
+#pragma unroll
+      for (int k = 0; k < (int)GETROW_PER_THREAD; ++k) mine += cell[k] != 0ull;
+      const bool with_c0 = (c == 0 && threadIdx.x == 0 && h.c0 != 0u);
+      ull total;
+      uint32_t w = (uint32_t)block_exclusive_scan((ull)mine + (with_c0 ? 1u : 0u), &total);
+      if (with_c0) s_stage[w++] = (ull)h.c0 << 32;
+#pragma unroll
+      for (int k = 0; k < (int)GETROW_PER_THREAD; ++k)
+        if (cell[k] != 0ull) s_stage[w++] = cell[k];
+      if (threadIdx.x == 0) s_base = total ? atomicAdd(&cursors[i], (uint32_t)total) : 0u;
+      __syncthreads();
+      ull* out = (ull*)pairs + (offsets[i] - bias) + s_base;
+      for (uint32_t k = threadIdx.x; k < (uint32_t)total; k += blockDim.x) out[k] = s_stage[k];
+      __syncthreads(); /* before the next chunk reuses the staging buffer */
     }
-    const uint32_t total = __shfl_sync(SMX_FULL, incl, SMX_WARP - 1);
-    uint32_t start = 0;
-    if (lane == 0 && total) start = atomicAdd(&cursors[i], total);
-    start = __shfl_sync(SMX_FULL, start, 0);
-    ull w = (ull)start + incl - mine;
-    if (a != 0ull) out[w++] = a;
-    if (b != 0ull) out[w] = b;
   }
 }
 
@@ -1705,9 +1756,9 @@ extern "C" void smx_launch_rowlen(smx_stream_t st, smx_view_t v, const uint32_t*
   SMX_LAUNCH(k_rowlen, grid_for(n), SMX_BLOCK, st, v, xs, n, out);
 }
 extern "C" void smx_launch_row_counts(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
-                                      uint32_t* counts, uint32_t* big_list, uint32_t* big_counter) {
+                                      uint32_t* counts, uint64_t* info, uint32_t* big_list, uint32_t* big_counter) {
   if (!n) return;
-  SMX_LAUNCH(k_row_counts, grid_for(n), SMX_BLOCK, st, v, xs, n, counts, big_list, big_counter);
+  SMX_LAUNCH(k_row_counts, grid_for(n), SMX_BLOCK, st, v, xs, n, counts, (ull*)info, big_list, big_counter);
 }
 
 extern "C" uint32_t smx_scan_scratch_items(uint32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
@@ -1720,18 +1771,16 @@ extern "C" void smx_launch_scan(smx_stream_t st, const uint32_t* counts, uint32_
   if (tiles) SMX_LAUNCH(k_scan_apply, tiles, SMX_BLOCK, st, counts, n, (const ull*)tile_sums, (ull*)offsets);
 }
 
-extern "C" void smx_launch_getrow_fill(smx_stream_t st, smx_view_t v, const uint32_t* xs, uint32_t n,
+extern "C" void smx_launch_getrow_fill(smx_stream_t st, smx_view_t v, const uint64_t* info, uint32_t n,
                                        const uint64_t* offsets, uint64_t bias, uint32_t* pairs,
                                        const uint32_t* big_list, uint32_t n_big, uint32_t* cursors) {
   if (!n) return;
-  SMX_LAUNCH(k_getrow_fill, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, xs, n,
-             (const ull*)offsets, (ull)bias, pairs, n_big ? 1 : 0);
-  for (uint32_t first = 0; first < n_big; first += 32768u) {
-    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
-    dim3 grid(SMX_WARP > 1 ? 128u : 2u, cnt, 1u);
-    SMX_LAUNCH(k_getrow_big, grid, SMX_BLOCK, st, v, xs, big_list, first, (const ull*)offsets, (ull)bias,
-               pairs, cursors);
-  }
+  SMX_LAUNCH(k_getrow_inline, grid_for(n), SMX_BLOCK, st, v, (const ull*)info, n, (const ull*)offsets, (ull)bias, pairs);
+  SMX_LAUNCH(k_getrow_fill, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, (const ull*)info, n,
+             (const ull*)offsets, (ull)bias, pairs);
+  if (n_big)
+    SMX_LAUNCH(k_getrow_chunks, (uint32_t)smx_grid_blocks(), SMX_BLOCK, st, v, (const ull*)info, big_list, n_big,
+               (const ull*)offsets, (ull)bias, pairs, cursors);
 }
 
 extern "C" void smx_launch_list_rows(smx_stream_t st, smx_view_t v, uint32_t* keys, uint32_t* counter) {

@@ -348,10 +348,12 @@ smatrix_t* smatrix_b200_shard_local(smatrix_shard_t* sh) { return sh->local; }
 int smatrix_b200_shard_rank(smatrix_shard_t* sh) { return sh->rank; }
 int smatrix_b200_shard_world(smatrix_shard_t* sh) { return sh->world; }
 
+static void rt_need_stage(smatrix_shard_t* sh, size_t ops);
 void smatrix_b200_shard_reserve(smatrix_shard_t* sh, size_t max_ops, size_t max_pairs) {
   const uint64_t ops = smatrix_b200_shard_max(sh, max_ops), pairs = smatrix_b200_shard_max(sh, max_pairs);
   rt_need_inbox(sh, ops);
   if (pairs) rt_need_rowbuf(sh, pairs);
+  rt_need_stage(sh, (size_t)(ops < sh->piece ? ops : sh->piece) + 1); /* staging of host-array pieces */
 }
 
 /* ------------------------------------------------------------------------------ the route */
