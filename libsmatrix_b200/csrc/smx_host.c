@@ -1126,17 +1126,7 @@ uint32_t smatrix_getrow(smatrix_t* s, uint32_t x, uint32_t* ret, size_t ret_len)
 #define SMX_F_DIR_HEAD 16ull
 #define SMX_F_DIR_SLOT 12ull
 #define SMX_F_ROW_HEAD 16ull
-#define SMX_SNAPSHOT_ROWS (1u << 20)
-
-static void ref_place(uint32_t* cells, uint64_t size, uint32_t key, uint32_t val) {
-  uint64_t at = key % size;
-  for (;;) {
-    if (key == 0 ? cells[2 * at] == 0 : (cells[2 * at] == 0 && cells[2 * at + 1] == 0)) break;
-    at = (at + 1) % size;
-  }
-  cells[2 * at] = key;
-  cells[2 * at + 1] = val;
-}
+#define SMX_SNAPSHOT_ROWS (1u << 18)
 
 static int write_all(int fd, const void* buf, size_t bytes, uint64_t at) {
   const char* p = (const char*)buf;
@@ -1182,81 +1172,56 @@ static int snapshot_save(smatrix_t* s) {
   uint32_t* d_keys = NULL;
   unsigned char* dir_entries = (unsigned char*)calloc(n_rows ? n_rows : 1, SMX_F_DIR_SLOT);
   uint32_t* h_keys = (uint32_t*)malloc(SMX_SNAPSHOT_ROWS * 4);
-  uint32_t* h_slog = (uint32_t*)malloc(SMX_SNAPSHOT_ROWS * 4);
   uint64_t* h_off = (uint64_t*)malloc(((size_t)SMX_SNAPSHOT_ROWS + 1) * 8);
-  uint32_t* h_pairs = NULL;
-  size_t h_pairs_cap = 0;
-  unsigned char* out = NULL;
+  unsigned char* out = NULL; /* pinned: the row blocks come down at PCIe speed */
   size_t out_cap = 0;
-  if (!dir_entries || !h_keys || !h_slog || !h_off) smx_die("out of host memory");
+  if (!dir_entries || !h_keys || !h_off) smx_die("out of host memory");
   if (n_rows) {
     d_keys = (uint32_t*)dmalloc(s, n_rows * 4);
     CK(cudaMemsetAsync(&s->d_ctl->scratch, 0, 8, s->stream));
     smx_launch_list_rows(s->stream, view_of(s), d_keys, (uint32_t*)&s->d_ctl->scratch);
     CK(cudaStreamSynchronize(s->stream));
   }
+  /* K9: every chunk of rows is laid out ON THE DEVICE in the reference's row-block format (sizes ->
+   * scan -> k_snap_rows / k_snap_big place every cell by column % size); the host only moves bytes */
   for (uint64_t first = 0; first < n_rows && rc == 0; first += SMX_SNAPSHOT_ROWS) {
     const uint32_t len = (uint32_t)((n_rows - first < SMX_SNAPSHOT_ROWS) ? n_rows - first : SMX_SNAPSHOT_ROWS);
     const uint32_t* d_xs = d_keys + first;
     const uint32_t tiles = smx_scan_scratch_items(len);
-    ensure_tmp(s, (size_t)len * 8, ((size_t)len + 1 + tiles) * 8);
+    ensure_tmp(s, (size_t)len * 12, ((size_t)len + 2 + tiles) * 8);
     uint32_t* d_counts = s->d_tmp;
     uint32_t* d_slog = s->d_tmp + len;
-    const uint64_t total = plan_rows(s, d_xs, len, d_counts);
+    uint32_t* d_units = s->d_tmp + 2 * (size_t)len;
+    uint32_t* d_nbig = ensure_rowplan(s, len);
+    smx_launch_row_counts(s->stream, view_of(s), d_xs, len, d_counts, s->d_info, s->d_big, d_nbig);
     smx_launch_row_slog(s->stream, view_of(s), d_xs, len, d_slog);
-    if (total * 8 > s->d_rowbuf_bytes) {
+    smx_launch_snap_units(s->stream, d_counts, d_slog, len, d_units);
+    smx_launch_scan(s->stream, d_units, len, 0, s->d_tmp64, s->d_tmp64 + (size_t)len + 1);
+    copy_d2h(s, h_off, s->d_tmp64, ((size_t)len + 1) * 8, s->stream);
+    copy_d2h(s, h_keys, d_xs, (size_t)len * 4, s->stream);
+    copy_d2h(s, &s->h_small[34], d_nbig, 4, s->stream);
+    CK(cudaStreamSynchronize(s->stream));
+    const size_t need = (size_t)h_off[len] * 8;
+    if (need > s->d_rowbuf_bytes) {
       if (s->d_rowbuf) cudaFree(s->d_rowbuf);
-      s->d_rowbuf_bytes = (size_t)total * 8 + 4096;
+      s->d_rowbuf_bytes = need + need / 8 + 4096;
       s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
     }
-    if (total) smx_launch_getrow_fill(s->stream, view_of(s), s->d_info, len, s->d_tmp64, 0, s->d_rowbuf, s->d_big, s->n_big_rows, s->d_cursors);
-    if (total * 2 > h_pairs_cap) {
-      free(h_pairs);
-      h_pairs_cap = (size_t)total * 2 + 1024;
-      h_pairs = (uint32_t*)malloc(h_pairs_cap * 4);
-      if (!h_pairs) smx_die("out of host memory");
-    }
-    copy_d2h(s, h_keys, d_xs, (size_t)len * 4, s->stream);
-    copy_d2h(s, h_slog, d_slog, (size_t)len * 4, s->stream);
-    copy_d2h(s, h_off, s->d_tmp64, ((size_t)len + 1) * 8, s->stream);
-    if (total) copy_d2h(s, h_pairs, s->d_rowbuf, (size_t)total * 8, s->stream);
-    CK(cudaStreamSynchronize(s->stream));
-    /* lay the chunk's row blocks out in one buffer, then one write */
-    size_t need = 0;
-    for (uint32_t i = 0; i < len; i++) {
-      const uint64_t c = h_off[i + 1] - h_off[i];
-      uint64_t size = 1ull << (h_slog[i] < 4 ? 4 : h_slog[i]);
-      while (c > size / 2) size *= 2;
-      need += SMX_F_ROW_HEAD + size * 8;
-    }
     if (need > out_cap) {
-      free(out);
-      out_cap = need + 4096;
-      out = (unsigned char*)malloc(out_cap);
-      if (!out) smx_die("out of host memory");
+      if (out) cudaFreeHost(out);
+      out_cap = need + need / 8 + 4096;
+      CK(cudaHostAlloc((void**)&out, out_cap, cudaHostAllocDefault));
     }
-    memset(out, 0, need);
-    size_t at = 0;
+    CK(cudaMemsetAsync(s->d_rowbuf, 0, need, s->stream));
+    smx_launch_snap_rows(s->stream, view_of(s), s->d_info, len, s->d_tmp64, (uint64_t*)s->d_rowbuf, s->d_big, s->h_small[34]);
+    s->n_launches += 8;
+    copy_d2h(s, out, s->d_rowbuf, need, s->stream);
+    CK(cudaStreamSynchronize(s->stream));
     for (uint32_t i = 0; i < len; i++) {
-      const uint32_t* pr = h_pairs + 2 * h_off[i];
-      const uint64_t c = h_off[i + 1] - h_off[i];
-      uint64_t size = 1ull << (h_slog[i] < 4 ? 4 : h_slog[i]);
-      while (c > size / 2) size *= 2;
-      unsigned char* blk = out + at;
-      memset(blk, 0x23, 8);
-      memcpy(blk + 8, &size, 8);
-      uint32_t* cells = (uint32_t*)(blk + SMX_F_ROW_HEAD);
-      for (uint64_t k = 0; k < c; k++) /* non-zero values of real columns first */
-        if (pr[2 * k] != 0 && pr[2 * k + 1] != 0) ref_place(cells, size, pr[2 * k], pr[2 * k + 1]);
-      for (uint64_t k = 0; k < c; k++) /* column 0 goes to the first cell whose column is 0 */
-        if (pr[2 * k] == 0) ref_place(cells, size, 0, pr[2 * k + 1]);
-      for (uint64_t k = 0; k < c; k++) /* zero-valued cells last (both loaders drop them) */
-        if (pr[2 * k] != 0 && pr[2 * k + 1] == 0) ref_place(cells, size, pr[2 * k], 0);
       unsigned char* de = dir_entries + (first + i) * SMX_F_DIR_SLOT;
-      const uint64_t row_fpos = fpos + at;
+      const uint64_t row_fpos = fpos + h_off[i] * 8;
       memcpy(de, &h_keys[i], 4);
       memcpy(de + 4, &row_fpos, 8);
-      at += SMX_F_ROW_HEAD + size * 8;
     }
     if (write_all(fd, out, need, fpos)) rc = -1;
     fpos += need;
@@ -1282,7 +1247,8 @@ static int snapshot_save(smatrix_t* s) {
     unlink(tmp); /* the previous snapshot, if any, is still intact */
   }
   if (d_keys) cudaFree(d_keys);
-  free(dir_entries); free(h_keys); free(h_slog); free(h_off); free(h_pairs); free(out); free(tmp);
+  if (out) cudaFreeHost(out);
+  free(dir_entries); free(h_keys); free(h_off); free(tmp);
   return rc;
 }
 

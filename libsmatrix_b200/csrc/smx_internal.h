@@ -169,6 +169,11 @@ void smx_launch_cf_scores(smx_stream_t stream, smx_view_t v, const uint32_t* ite
                           const uint64_t* offsets, const uint32_t* pairs, uint32_t* ids, double* scores);
 void smx_launch_list_rows(smx_stream_t stream, smx_view_t v, uint32_t* keys, uint32_t* counter /* zeroed */);
 void smx_launch_row_slog(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n, uint32_t* out);
+void smx_launch_snap_units(smx_stream_t stream, const uint32_t* counts, const uint32_t* slogs, uint32_t n,
+                           uint32_t* units /* 2 + reference row size, in 8-byte units */);
+void smx_launch_snap_rows(smx_stream_t stream, smx_view_t v, const uint64_t* info, uint32_t n,
+                          const uint64_t* offsets /* n+1, 8-byte units */, uint64_t* out /* zeroed */,
+                          const uint32_t* big_list, uint32_t n_big);
 void smx_launch_load_fixup(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* slogs,
                            uint32_t n);
 void smx_launch_gen_c2_ops(smx_stream_t stream, uint64_t seed, uint64_t first, uint64_t count,

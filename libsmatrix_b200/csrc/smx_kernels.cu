@@ -1067,39 +1067,39 @@ k_getrow_fill(smx_view_t V, const ull* info, uint32_t n, const ull* offsets, ull
 #define GETROW_CHUNK_LOG 11u
 #define GETROW_CHUNK (1u << GETROW_CHUNK_LOG)
 #define GETROW_PER_THREAD (GETROW_CHUNK / SMX_BLOCK) /* 8 cells = 4 x 16-byte loads per thread */
+#define GETROW_BLOCKS_PER_ROW 32u /* grid.x: blocks that share one big row's chunks (grid.y = rows) */
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_getrow_chunks(smx_view_t V, const ull* info, const uint32_t* big_list, uint32_t n_big, const ull* offsets,
+k_getrow_chunks(smx_view_t V, const ull* info, const uint32_t* big_list, uint32_t big_first, const ull* offsets,
                 ull bias, uint32_t* pairs, uint32_t* cursors) {
   __shared__ ull s_stage[GETROW_CHUNK + 1];
   __shared__ uint32_t s_base;
-  for (uint32_t b = 0; b < n_big; ++b) {
-    const uint32_t i = big_list[b];
-    const ull inf = info[i];
-    const ull nchunks = (1ull << (uint32_t)(inf >> 32)) >> GETROW_CHUNK_LOG;
-    /* rotate the first block of every row so that short rows do not all land on blocks 0, 1, ... */
-    for (ull c = (blockIdx.x + gridDim.x - (b * 61u) % gridDim.x) % gridDim.x; c < nchunks; c += gridDim.x) {
-      const smx_row_t* e = V.dir + (uint32_t)inf;
-      const Hdr h = ld_hdr(e);
-      const ull* base = (const ull*)h.slots + (c << GETROW_CHUNK_LOG) + (ull)threadIdx.x * GETROW_PER_THREAD;
-      ull cell[GETROW_PER_THREAD];
+  const uint32_t i = big_list[big_first + blockIdx.y];
+  const ull inf = info[i];
+  const ull nchunks = (1ull << (uint32_t)(inf >> 32)) >> GETROW_CHUNK_LOG;
+  if (blockIdx.x >= nchunks) return;
+  const smx_row_t* e = V.dir + (uint32_t)inf;
+  const Hdr h = ld_hdr(e);
+  ull* const out_row = (ull*)pairs + (offsets[i] - bias);
+  for (ull c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const ull* base = (const ull*)h.slots + (c << GETROW_CHUNK_LOG) + (ull)threadIdx.x * GETROW_PER_THREAD;
+    ull cell[GETROW_PER_THREAD];
 #pragma unroll
-      for (int k = 0; k < (int)GETROW_PER_THREAD; k += 2) ld_cells2(base + k, &cell[k], &cell[k + 1]);
-      uint32_t mine = 0;
+    for (int k = 0; k < (int)GETROW_PER_THREAD; k += 2) ld_cells2(base + k, &cell[k], &cell[k + 1]);
+    uint32_t mine = 0;
 #pragma unroll
-      for (int k = 0; k < (int)GETROW_PER_THREAD; ++k) mine += cell[k] != 0ull;
-      const bool with_c0 = (c == 0 && threadIdx.x == 0 && h.c0 != 0u);
-      ull total;
-      uint32_t w = (uint32_t)block_exclusive_scan((ull)mine + (with_c0 ? 1u : 0u), &total);
-      if (with_c0) s_stage[w++] = (ull)h.c0 << 32;
+    for (int k = 0; k < (int)GETROW_PER_THREAD; ++k) mine += cell[k] != 0ull;
+    const bool with_c0 = (c == 0 && threadIdx.x == 0 && h.c0 != 0u);
+    ull total;
+    uint32_t w = (uint32_t)block_exclusive_scan((ull)mine + (with_c0 ? 1u : 0u), &total);
+    if (with_c0) s_stage[w++] = (ull)h.c0 << 32;
 #pragma unroll
-      for (int k = 0; k < (int)GETROW_PER_THREAD; ++k)
-        if (cell[k] != 0ull) s_stage[w++] = cell[k];
-      if (threadIdx.x == 0) s_base = total ? atomicAdd(&cursors[i], (uint32_t)total) : 0u;
-      __syncthreads();
-      ull* out = (ull*)pairs + (offsets[i] - bias) + s_base;
-      for (uint32_t k = threadIdx.x; k < (uint32_t)total; k += blockDim.x) out[k] = s_stage[k];
-      __syncthreads(); /* before the next chunk reuses the staging buffer */
-    }
+    for (int k = 0; k < (int)GETROW_PER_THREAD; ++k)
+      if (cell[k] != 0ull) s_stage[w++] = cell[k];
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(&cursors[i], (uint32_t)total) : 0u;
+    __syncthreads();
+    ull* out = out_row + s_base;
+    for (uint32_t k = threadIdx.x; k < (uint32_t)total; k += blockDim.x) out[k] = s_stage[k];
+    __syncthreads(); /* before the next chunk reuses the staging buffer */
   }
 }
 
@@ -1155,6 +1155,93 @@ k_row_slog(smx_view_t V, const uint32_t* xs, uint32_t n, uint32_t* out) {
     out[i] = slog;
   }
 }
+/* ---- K9: the row blocks of a snapshot, built on the device in the REFERENCE's layout ------------
+ * A row block is 8 x 0x23, u64 size, then `size` cells placed where the reference's loader and its
+ * rmap_probe expect them: position = column % size, linear probing (src/smatrix.c:363-380, :499-545).
+ * Three phases keep every probe chain intact when the loader later drops zero-valued cells
+ * (src/smatrix.c:533-540): (1) cells with a non-zero value, in any order (unique keys: any insertion
+ * order gives a valid table), (2) column 0 into the first cell whose column is 0, (3) zero-valued
+ * cells last.  units[i] = 2 + size_i (in 8-byte units) is scanned into the block offsets. */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_snap_units(const uint32_t* counts, const uint32_t* slogs, uint32_t n, uint32_t* units) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    ull size = 1ull << (slogs[i] < 4u ? 4u : slogs[i]);
+    while ((ull)counts[i] > size / 2) size *= 2; /* never fuller than the reference lets a row get */
+    units[i] = (uint32_t)(size + 2ull);
+  }
+}
+__device__ __forceinline__ void snap_place(ull* cells, ull size, ull cell) {
+  ull at = (ull)(uint32_t)cell % size;
+  for (;;) {
+    if (cells[at] == 0ull && atomicCAS(&cells[at], 0ull, cell) == 0ull) return;
+    at = at + 1 == size ? 0 : at + 1;
+  }
+}
+__device__ __forceinline__ void snap_place_c0(ull* cells, ull size, uint32_t c0) {
+  for (ull at = 0; at < size; ++at) /* the reference probes column 0 from position 0 % size = 0 */
+    if ((uint32_t)__ldcg(&cells[at]) == 0u && atomicCAS(&cells[at], 0ull, (ull)c0 << 32) == 0ull) return;
+}
+/* phase selector: 1 = cells with value != 0, 3 = cells with value == 0 */
+__device__ __forceinline__ bool snap_takes(ull cell, int phase) {
+  return cell != 0ull && (((cell >> 32) != 0ull) == (phase == 1));
+}
+/* rows below 2^SMX_GETROW_BIG_LOG cells: one warp per row, all three phases */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_snap_rows(smx_view_t V, const ull* info, uint32_t n, const ull* offsets, ull* out) {
+  const uint32_t lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
+  const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
+  for (uint32_t i = warp; i < n; i += nwarps) {
+    const ull inf = info[i];
+    const uint32_t caplog = (uint32_t)(inf >> 32);
+    ull* blk = out + offsets[i];
+    const ull size = offsets[i + 1] - offsets[i] - 2ull;
+    if (lane == 0) { blk[0] = 0x2323232323232323ull; blk[1] = size; }
+    if (inf == SMX_NO_ROW || caplog >= SMX_GETROW_BIG_LOG) continue;
+    const smx_row_t* e = V.dir + (uint32_t)inf;
+    const Hdr h = ld_hdr(e);
+    const ull* base = (caplog == SMX_INLINE_LOG) ? (const ull*)e->inl : (const ull*)h.slots;
+    const uint32_t cap = 1u << caplog;
+    for (int phase = 1; phase <= 3; ++phase) {
+      if (phase == 2) {
+        if (lane == 0 && h.c0 != 0u) snap_place_c0(blk + 2, size, h.c0);
+      } else {
+        for (uint32_t c = lane; c < cap; c += SMX_WARP) {
+          const ull cell = base[c];
+          if (snap_takes(cell, phase)) snap_place(blk + 2, size, cell);
+        }
+      }
+      __syncwarp();
+#ifndef SMX_HOSTSIM
+      __threadfence_block();
+#endif
+    }
+  }
+}
+/* big rows: the grid strides over the bucket of one row (y); one launch per phase (1 or 3); phase 2
+ * (column 0) is done by the first thread of the phase-3 launch BEFORE any zero-valued cell is placed
+ * — so phase 3 is launched twice: c0_only = 1, then c0_only = 0 */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_snap_big(smx_view_t V, const ull* info, const uint32_t* big_list, uint32_t first, const ull* offsets, ull* out,
+           int phase, int c0_only) {
+  const uint32_t i = big_list[first + blockIdx.y];
+  const ull inf = info[i];
+  const smx_row_t* e = V.dir + (uint32_t)inf;
+  const Hdr h = ld_hdr(e);
+  ull* blk = out + offsets[i];
+  const ull size = offsets[i + 1] - offsets[i] - 2ull;
+  if (c0_only) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && h.c0 != 0u) snap_place_c0(blk + 2, size, h.c0);
+    return;
+  }
+  const ull* base = (const ull*)h.slots;
+  const ull cap = 1ull << (uint32_t)(inf >> 32);
+  for (ull c = blockIdx.x * (ull)blockDim.x + threadIdx.x; c < cap; c += (ull)gridDim.x * blockDim.x) {
+    const ull cell = base[c];
+    if (snap_takes(cell, phase)) snap_place(blk + 2, size, cell);
+  }
+}
+
 /* after a load: the reference recounts `used` from the file (src/smatrix.c:533-540), i.e. the row
  * size is the file's and column 0 is counted iff it is non-zero */
 __global__ void __launch_bounds__(SMX_BLOCK)
@@ -1778,9 +1865,12 @@ extern "C" void smx_launch_getrow_fill(smx_stream_t st, smx_view_t v, const uint
   SMX_LAUNCH(k_getrow_inline, grid_for(n), SMX_BLOCK, st, v, (const ull*)info, n, (const ull*)offsets, (ull)bias, pairs);
   SMX_LAUNCH(k_getrow_fill, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, (const ull*)info, n,
              (const ull*)offsets, (ull)bias, pairs);
-  if (n_big)
-    SMX_LAUNCH(k_getrow_chunks, (uint32_t)smx_grid_blocks(), SMX_BLOCK, st, v, (const ull*)info, big_list, n_big,
-               (const ull*)offsets, (ull)bias, pairs, cursors);
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? GETROW_BLOCKS_PER_ROW : 2u, cnt, 1u);
+    SMX_LAUNCH(k_getrow_chunks, grid, SMX_BLOCK, st, v, (const ull*)info, big_list, first, (const ull*)offsets,
+               (ull)bias, pairs, cursors);
+  }
 }
 
 extern "C" void smx_launch_list_rows(smx_stream_t st, smx_view_t v, uint32_t* keys, uint32_t* counter) {
@@ -1790,6 +1880,24 @@ extern "C" void smx_launch_row_slog(smx_stream_t st, smx_view_t v, const uint32_
                                     uint32_t* out) {
   if (!n) return;
   SMX_LAUNCH(k_row_slog, grid_for(n), SMX_BLOCK, st, v, xs, n, out);
+}
+extern "C" void smx_launch_snap_units(smx_stream_t st, const uint32_t* counts, const uint32_t* slogs, uint32_t n,
+                                      uint32_t* units) {
+  if (!n) return;
+  SMX_LAUNCH(k_snap_units, grid_for(n), SMX_BLOCK, st, counts, slogs, n, units);
+}
+/* out must be zeroed; offsets in 8-byte units (n + 1 entries) */
+extern "C" void smx_launch_snap_rows(smx_stream_t st, smx_view_t v, const uint64_t* info, uint32_t n,
+                                     const uint64_t* offsets, uint64_t* out, const uint32_t* big_list, uint32_t n_big) {
+  if (!n) return;
+  SMX_LAUNCH(k_snap_rows, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, (const ull*)info, n, (const ull*)offsets, (ull*)out);
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? 32u : 2u, cnt, 1u);
+    SMX_LAUNCH(k_snap_big, grid, SMX_BLOCK, st, v, (const ull*)info, big_list, first, (const ull*)offsets, (ull*)out, 1, 0);
+    SMX_LAUNCH(k_snap_big, grid, SMX_BLOCK, st, v, (const ull*)info, big_list, first, (const ull*)offsets, (ull*)out, 3, 1);
+    SMX_LAUNCH(k_snap_big, grid, SMX_BLOCK, st, v, (const ull*)info, big_list, first, (const ull*)offsets, (ull*)out, 3, 0);
+  }
 }
 extern "C" void smx_launch_load_fixup(smx_stream_t st, smx_view_t v, const uint32_t* xs,
                                       const uint32_t* slogs, uint32_t n) {
