@@ -719,11 +719,23 @@ def run_e2e_writes(job: Job, wl: WriteWorkload, mk):
     gh2d, gd2h = job.sum_over_ranks(m.stat("h2d_bytes") - h2d1, m.stat("d2h_bytes") - d2h1)
     gsteps = -(-G // B)
     m.close()
+    # the box's own ceiling for this step's upload: every rank copies its pinned batch (x, y) host -> device at the
+    # same time, nothing else running — what e2e could reach if routing and updating were free
+    job.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        dx.copy_(hx, non_blocking=True); dy.copy_(hy, non_blocking=True)
+    job.torch.cuda.synchronize()
+    ceil_s = job.max_over_ranks(time.perf_counter() - t0) / 4
+    ceiling_mops = B * world / ceil_s / 1e6
     return {"value": incr, "unit": "Mops/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
             "ms_per_step": secs / K * 1e3, "step_ms": series,
             "get_mops": G * world / gsecs / 1e6, "get_h2d_bytes_per_step": gh2d // gsteps,
             "get_d2h_bytes_per_step": gd2h // gsteps,
             "pcie_frac": (h2d / K / world) / (secs / K) / 55e9,
+            "h2d_ceiling": {"mops": ceiling_mops, "gbs_per_gpu": 8 * B / ceil_s / 1e9, "ms_per_step": ceil_s * 1e3,
+                            "frac": incr / ceiling_mops,
+                            "note": "all ranks uploading one step's pinned (x, y) arrays concurrently, nothing else running"},
             "note": "pinned host arrays through incr_batch / get_batch (N = 1: the C-ABI smatrix_incr_batch / smatrix_get_batch "
                     "with host pointers; N > 1: smatrix_b200_shard_* stage each rank's slice piece by piece, then route); barrier, "
                     "wall clock around the call, max over ranks; bytes = the library's copy counters, summed over ranks; "

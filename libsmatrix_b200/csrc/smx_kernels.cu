@@ -83,15 +83,17 @@ __host__ __device__ __forceinline__ ull smx_splitmix64(ull z) {
 
 /* One 32-byte sector with a single 256-bit load that bypasses L1 (coherent at L2).  With the
  * L2::64B hint a miss fetches 64 bytes from DRAM instead of the whole 128-byte line (SASS
- * LDG.E.ENL2.LTC64B.256): the random-touch rate is the same, the DRAM bytes per probe halve.
- * Column buckets use the hint (the next sector in probe order is in the same 64 bytes half of the
- * time); directory entries do not — an entry is 64 bytes and the probe order visits BOTH entries of
- * a 128-byte line before moving on, so the full-line fetch makes the second probe free. */
+ * LDG.E.ENL2.LTC64B.256).  Measured on the full config-2 table (profiles/r2_summary.md): the speed is
+ * the same with 64- and 128-byte fetches — the path is bound by the number of random DRAM touches,
+ * not by their width — but the DRAM bytes per op drop (k_upsert 233 -> 173, k_get 322 -> 238 with the
+ * hint on the buckets alone), so both the buckets and the 64-byte directory entries use it.  The
+ * directory's probe order still visits both entries of a 128-byte line before moving on: the second
+ * one is then a hit in the same DRAM page. */
 #ifndef SMX_CELL_FETCH64
 #define SMX_CELL_FETCH64 1
 #endif
 #ifndef SMX_HDR_FETCH64
-#define SMX_HDR_FETCH64 0
+#define SMX_HDR_FETCH64 1
 #endif
 template <bool FETCH64>
 __device__ __forceinline__ void ld_sector_t(const void* p, ull c[4]) {
