@@ -648,7 +648,7 @@ def run_write_workload(job: Job, name: str):
                    "l2": "inputs larger than L2 (512 MiB of keys per step, table >> 126 MB)",
                    "arena_gib": wl.arena, "arena_note": "slab arena reserved by smatrix_open (outside the timed region); "
                    "on-demand cudaMalloc is the fallback and costs 0.3-8 ms/step on this pool",
-                   "chunk_ops": int(os.environ.get("SMATRIX_CHUNK", 1 << 25)),
+                   "chunk_ops": int(os.environ.get("SMATRIX_CHUNK", 1 << 26)),
                    "parallelism": f"row-hash shard x{world}, C router over peer memory" if world > 1 else "single GPU"},
         "get_mops": get_mops, "get_ms": ms_get, "get_hit_fraction": hits / G,
         "nnz": nnz_total, "rows_present": rows_seen, "prefill_s": t_prefill,

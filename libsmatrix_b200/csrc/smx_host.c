@@ -36,7 +36,7 @@
 #include "smx_internal.h"
 
 #define SMX_DIR_LOG_DEFAULT 20u
-#define SMX_CHUNK_DEFAULT (1u << 25) /* measured sweet spot on B200 */
+#define SMX_CHUNK_DEFAULT (1u << 26) /* measured on B200: 5.17 vs 5.50 ms per 2^26 ops with 2^25 (profiles/r2_summary.md) */
 #define SMX_STAGE_MAX (1u << 23) /* host-pointer batches: piece size with the best copy/update overlap (measured) */
 #define SMX_SEG_MIN ((size_t)64 << 20)
 #define SMX_SEG_MAX ((size_t)16 << 30)
@@ -115,7 +115,6 @@ struct smatrix_s {
   unsigned long long* free_ptr[SMX_CLASSES]; /* device stacks of vacated buckets, per size class */
   uint32_t free_cap[SMX_CLASSES];
   int recycle;                               /* SMATRIX_RECYCLE (default 1) */
-  uint64_t last_chunk_new, last_chunk_ops;   /* rows created by / ops of the previous chunk (presize_dir) */
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
@@ -401,9 +400,10 @@ static void presize_dir(smatrix_t* s, const smx_ops_t* ops) {
   const uint64_t n = ops->n, used = s->h_ctl->dir_used;
   if (n < s->part_min || !s->presize) return;      /* small batches: the grow loop is cheap        */
   if (used + n <= s->dir_cap / 4) return;          /* fits even if every op creates a row           */
-  /* worth a pass over the chunk only while chunks still bring many new rows: the table is empty, or
-   * the previous chunk created a row with at least every 16th op */
-  if (used && s->last_chunk_new * 16 < s->last_chunk_ops) return;
+  /* only for an EMPTY table: there every distinct row of the chunk is a new row.  Later chunks mix new
+   * and existing rows (the sketch cannot tell them apart and would over-size the directory — measured:
+   * 2^27 instead of 2^26 entries for config 2, +2 % per step); the grow loop handles those */
+  if (used) return;
   const uint64_t m = 1ull << SMX_SKETCH_BITS_LOG;
   ensure_tmp(s, (size_t)(m / 8), 0);
   CK(cudaMemsetAsync(s->d_tmp, 0, (size_t)(m / 8), s->stream));
@@ -586,7 +586,6 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
   ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vs; ops.idx = d_ords; ops.v_const = 1u; ops.n = n;
 
   presize_dir(s, &ops);
-  const uint64_t rows_before = s->h_ctl->dir_used;
   uint32_t n_main = n;
   const int parted = (n >= s->part_min) ? partition_chunk(s, &ops, api_op, &n_main) : 0;
   /* partitioned: [0, n_main) = ops on columns != 0, [n_main, n) = ops on column 0 (dense ranges);
@@ -619,8 +618,6 @@ static void process_chunk_ordered(smatrix_t* s, int api_op, const uint32_t* d_xs
     smx_launch_finalize_t0(s->stream, view_of(s), s->lists.t0rows, n_t0);
     s->n_launches++;
   }
-  s->last_chunk_new = s->h_ctl->dir_used > rows_before ? s->h_ctl->dir_used - rows_before : 0;
-  s->last_chunk_ops = n;
   maybe_shrink_dir(s);
 }
 
