@@ -72,6 +72,7 @@ void  smatrix_b200_host_free(void* p);
 void* smatrix_b200_dev_alloc(smatrix_t* self, size_t bytes);
 void  smatrix_b200_dev_free(smatrix_t* self, void* p);
 void  smatrix_b200_memcpy(smatrix_t* self, void* dst, const void* src, size_t bytes); /* any direction, synchronous */
+void  smatrix_b200_memset0(smatrix_t* self, void* d_dst, size_t bytes);                /* zero device memory */
 
 /* Synthetic streams of SURVEY.md 8(d), generated on the device (r = splitmix64(seed + i)):
  * C2 build ops [first, first+count) and C2 queries (odd j -> guaranteed miss). Device arrays. */
@@ -155,6 +156,12 @@ void     smatrix_b200_getrow_fill_at(smatrix_t* self, const uint32_t* d_xs, size
                                      const uint64_t* d_offsets, uint32_t* d_pairs);
 void     smatrix_b200_route_offsets(smatrix_t* self, const uint64_t* d_offsets, const uint32_t* d_pos,
                                     size_t n, uint32_t world, const uint64_t* h_tab);
+/* CF read side when the totals live on other shards: columns of a pairs array, and the scores of
+ * smatrix_cf_neighbors_batch from pre-fetched totals (a_tot per item, b_tot per pair) */
+void smatrix_b200_pair_cols(smatrix_t* self, const uint32_t* d_pairs, uint64_t total, uint32_t* d_cols);
+void smatrix_b200_cf_scores_totals(smatrix_t* self, size_t n, const uint64_t* d_offsets, const uint32_t* d_pairs,
+                                   const uint32_t* d_a_tot, const uint32_t* d_b_tot, uint32_t* d_ids,
+                                   double* d_scores);
 int  smatrix_b200_is_device_ptr(smatrix_t* self, const void* p);   /* device (or managed) memory? */
 /* peers in the SAME process (one thread per GPU) need no IPC: enable direct access to `peer_device` */
 int  smatrix_b200_enable_peer(smatrix_t* self, int peer_device);

@@ -73,6 +73,13 @@ void smatrix_b200_shard_rowlen_batch(smatrix_shard_t* self, const uint32_t* xs, 
 uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* self, const uint32_t* xs, size_t n,
                                          uint64_t* offsets, uint32_t* pairs, uint64_t pairs_cap);
 
+/* The read side of the co-occurrence recommender across ranks (examples/cf_recommender.c:50-86): same
+ * contract as smatrix_cf_neighbors_batch (offsets[0..n], ids / scores with capacity `cap`, size query
+ * with ids == NULL).  Rows come through the getrow route, the totals at column 0 through two sharded
+ * gets, scores are bit-exact doubles. */
+uint64_t smatrix_b200_shard_cf_neighbors_batch(smatrix_shard_t* self, const uint32_t* items, size_t n,
+                                               uint64_t* offsets, uint32_t* ids, double* scores, uint64_t cap);
+
 /* Host wall-clock accounting of this rank since the last reset (not collective): time spent routing
  * (count, count exchange, scatter over NVLink, arrival barrier), time spent applying the inbox,
  * number of routes, bytes this rank stored into OTHER ranks' inboxes. */

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "smatrix_b200_dev_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
     "smatrix_b200_dev_free": (None, [C.c_void_p, C.c_void_p]),
     "smatrix_b200_memcpy": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "smatrix_b200_memset0": (None, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "smatrix_b200_gen_c2_ops": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint32,
                                        C.c_uint32, C.c_void_p, C.c_void_p]),
     "smatrix_b200_gen_c2_queries": (None, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t,
@@ -83,6 +84,9 @@ PROTOTYPES = {
     "smatrix_b200_scan_counts": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "smatrix_b200_getrow_fill_at": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "smatrix_b200_route_offsets": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "smatrix_b200_pair_cols": (None, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "smatrix_b200_cf_scores_totals": (None, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
     "smatrix_b200_enable_peer": (C.c_int, [C.c_void_p, C.c_int]),
     "smatrix_b200_is_device_ptr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "smatrix_b200_memcpy_async": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
@@ -108,6 +112,8 @@ PROTOTYPES.update({
     "smatrix_b200_shard_set_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "smatrix_b200_shard_get_batch": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "smatrix_b200_shard_rowlen_batch": (None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "smatrix_b200_shard_cf_neighbors_batch": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                          C.c_void_p, C.c_uint64]),
     "smatrix_b200_shard_getrow_batch": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                     C.c_uint64]),
     "smatrix_b200_shard_stat": (C.c_uint64, [C.c_void_p, C.c_int]),

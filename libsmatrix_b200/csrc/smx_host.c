@@ -1608,6 +1608,14 @@ void smatrix_b200_memcpy(smatrix_t* s, void* dst, const void* src, size_t bytes)
   leave(s);
 }
 
+void smatrix_b200_memset0(smatrix_t* s, void* d_dst, size_t bytes) {
+  if (!bytes) return;
+  enter(s);
+  CK(cudaMemsetAsync(d_dst, 0, bytes, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  leave(s);
+}
+
 void smatrix_b200_gen_c2_ops(smatrix_t* s, uint64_t seed, uint64_t first, size_t count,
                              uint32_t rows, uint32_t ycols, uint32_t* d_xs, uint32_t* d_ys) {
   enter(s);
@@ -1838,6 +1846,27 @@ void smatrix_b200_route_offsets(smatrix_t* s, const uint64_t* d_offsets, const u
   unsigned long long* d_tab = (unsigned long long*)s->d_tmp64 + 128;
   copy_h2d(s, d_tab, h_tab, 2 * (size_t)world * 8, s->stream);
   smx_launch_route_offsets(s->stream, d_offsets, d_pos, (uint32_t)n, world, d_tab);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
+/* device-level pieces of the CF read side for the multi-GPU router (all arrays on the device) */
+void smatrix_b200_pair_cols(smatrix_t* s, const uint32_t* d_pairs, uint64_t total, uint32_t* d_cols) {
+  if (!total) return;
+  enter(s);
+  smx_launch_pair_cols(s->stream, d_pairs, total, d_cols);
+  s->n_launches++;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+void smatrix_b200_cf_scores_totals(smatrix_t* s, size_t n, const uint64_t* d_offsets, const uint32_t* d_pairs,
+                                   const uint32_t* d_a_tot, const uint32_t* d_b_tot, uint32_t* d_ids, double* d_scores) {
+  if (!n) return;
+  enter(s);
+  smx_launch_cf_scores_totals(s->stream, (uint32_t)n, d_offsets, d_pairs, d_a_tot, d_b_tot, d_ids, d_scores);
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
   CK(cudaGetLastError());

@@ -167,6 +167,9 @@ void smx_launch_sum_values(smx_stream_t stream, smx_view_t v, uint32_t* big_list
 void smx_launch_sum_values_big(smx_stream_t stream, smx_view_t v, const uint32_t* big_list, uint32_t n_big);
 void smx_launch_cf_scores(smx_stream_t stream, smx_view_t v, const uint32_t* items, uint32_t n,
                           const uint64_t* offsets, const uint32_t* pairs, uint32_t* ids, double* scores);
+void smx_launch_pair_cols(smx_stream_t stream, const uint32_t* pairs, uint64_t total, uint32_t* cols);
+void smx_launch_cf_scores_totals(smx_stream_t stream, uint32_t n, const uint64_t* offsets, const uint32_t* pairs,
+                                 const uint32_t* a_tot, const uint32_t* b_tot, uint32_t* ids, double* scores);
 void smx_launch_list_rows(smx_stream_t stream, smx_view_t v, uint32_t* keys, uint32_t* counter /* zeroed */);
 void smx_launch_row_slog(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n, uint32_t* out);
 void smx_launch_snap_units(smx_stream_t stream, const uint32_t* counts, const uint32_t* slogs, uint32_t n,

@@ -450,8 +450,10 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       caplog = h.meta & SMX_META_CAPLOG;
       const ull need = 2ull * ((ull)h.live + (ull)h.want); /* load factor <= 1/2 after growth */
       /* small buckets grow x8 (4 -> 32 -> 256 cells: two re-placements on the way to a 256-cell
-       * bucket instead of three, and less vacated memory), big ones x2 */
-      newlog = caplog + (caplog < 8u ? 3u : 1u);
+       * bucket instead of three, and less vacated memory); 512 .. 4096 cells grow x4 (rows in that range
+       * are the skewed workloads' hot rows on their way up: half as many block-per-row re-placements,
+       * 0.42 -> 0.2 ms per 2^25 ops of config 3); everything else x2 like the reference (:390) */
+      newlog = caplog + (caplog < 8u ? 3u : (caplog >= SMX_MID_LOG && caplog < SMX_BIG_LOG ? 2u : 1u));
       if (newlog > 8u && caplog < 8u) newlog = 8u;
       if (newlog < SMX_MIN_SLAB_LOG) newlog = SMX_MIN_SLAB_LOG;
       while ((1ull << newlog) < need && newlog < SMX_MAX_CAPLOG) ++newlog;
@@ -1129,6 +1131,30 @@ k_cf_scores(smx_view_t V, const uint32_t* items, uint32_t n, const ull* offsets,
       if (b_total == 0u) b_total = 1u;
       const double num = (double)cc, den = sa * sqrt((double)b_total);
       ids[k] = b;
+      scores[k] = (den == 0.0 || num > den) ? 0.0 : num / den;
+    }
+  }
+}
+
+/* the same scores when the totals come from OTHER shards (multi-GPU): cols[k] = column of pair k,
+ * a_tot[i] / b_tot[k] = value at (item i, 0) / (cols[k], 0), fetched by sharded gets */
+__global__ void __launch_bounds__(SMX_BLOCK) k_pair_cols(const uint32_t* pairs, ull total, uint32_t* cols) {
+  for (ull k = blockIdx.x * (ull)blockDim.x + threadIdx.x; k < total; k += (ull)gridDim.x * blockDim.x)
+    cols[k] = pairs[2 * k];
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_cf_scores_totals(uint32_t n, const ull* offsets, const uint32_t* pairs, const uint32_t* a_tot,
+                   const uint32_t* b_tot, uint32_t* ids, double* scores) {
+  const uint32_t lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / SMX_WARP;
+  const uint32_t nwarps = gridDim.x * blockDim.x / SMX_WARP;
+  for (uint32_t i = warp; i < n; i += nwarps) {
+    const double sa = sqrt((double)a_tot[i]);
+    for (ull k = offsets[i] + lane; k < offsets[i + 1]; k += SMX_WARP) {
+      const uint32_t cc = pairs[2 * k + 1];
+      const uint32_t bt = b_tot[k] ? b_tot[k] : 1u;
+      const double num = (double)cc, den = sa * sqrt((double)bt);
+      ids[k] = pairs[2 * k];
       scores[k] = (den == 0.0 || num > den) ? 0.0 : num / den;
     }
   }
@@ -1912,6 +1938,16 @@ extern "C" void smx_launch_cf_scores(smx_stream_t st, smx_view_t v, const uint32
   if (!n) return;
   SMX_LAUNCH(k_cf_scores, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, v, items, n, (const ull*)offsets,
              pairs, ids, scores);
+}
+extern "C" void smx_launch_pair_cols(smx_stream_t st, const uint32_t* pairs, uint64_t total, uint32_t* cols) {
+  if (!total) return;
+  SMX_LAUNCH(k_pair_cols, grid_for(total), SMX_BLOCK, st, pairs, (ull)total, cols);
+}
+extern "C" void smx_launch_cf_scores_totals(smx_stream_t st, uint32_t n, const uint64_t* offsets, const uint32_t* pairs,
+                                            const uint32_t* a_tot, const uint32_t* b_tot, uint32_t* ids, double* scores) {
+  if (!n) return;
+  SMX_LAUNCH(k_cf_scores_totals, grid_for((ull)n * SMX_WARP), SMX_BLOCK, st, n, (const ull*)offsets, pairs, a_tot,
+             b_tot, ids, scores);
 }
 extern "C" void smx_launch_sum_values(smx_stream_t st, smx_view_t v, uint32_t* big_list, uint32_t* big_counter) {
   SMX_LAUNCH(k_sum_values, grid_for(v.dir_cap * SMX_WARP), SMX_BLOCK, st, v, big_list, big_counter);

@@ -628,17 +628,13 @@ void smatrix_b200_shard_rowlen_batch(smatrix_shard_t* sh, const uint32_t* xs, si
 }
 
 /* ------------------------------------------------------------------------------ getrow */
-uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* sh, const uint32_t* xs, size_t n, uint64_t* offsets,
-                                         uint32_t* pairs, uint64_t pairs_cap) {
-  if (n >= 0xFFFFFFFEull) rt_die(sh, "getrow_batch: too many rows in one call");
+/* Collective core of getrow: row ids d_xs (device, n of them) -> CSR offsets in my OFS array and, if
+ * this rank wants them (want != 0 and total <= cap_pairs), the pairs in my row buffer.  Returns the
+ * total; *filled = whether my row buffer holds my pairs; *any_fill = whether ANY rank filled (the
+ * callers' follow-up collectives hinge on it). */
+static uint64_t rt_getrow_core(smatrix_shard_t* sh, const uint32_t* d_xs, size_t n, int want, uint64_t cap_pairs,
+                               int* filled, int* any_fill_out) {
   const int W = sh->world, me = sh->rank;
-  const int dev = n ? rt_is_dev(sh, xs) : 1;
-  const uint32_t* d_xs = xs;
-  if (n && !dev) { /* row ids are few compared with the pairs: one staged copy */
-    rt_need_stage(sh, n + 1);
-    smatrix_b200_memcpy(sh->local, sh->stage[0][0], xs, n * 4);
-    d_xs = sh->stage[0][0];
-  }
   rt_route_t R;
   rt_route(sh, d_xs, NULL, NULL, n, 0, 1, &R);
   rt_answer(sh, RT_COUNTS, &R);
@@ -650,12 +646,8 @@ uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* sh, const uint32_t* xs
   if (n) {
     smatrix_b200_gather(sh->local, d_cnt, (const uint32_t*)(sh->inbox + OFF_ANS(cap)), d_pos, n);
     total = smatrix_b200_scan_counts(sh->local, d_cnt, n, d_off);
-    if (offsets) smatrix_b200_memcpy(sh->local, offsets, d_off, (n + 1) * 8);
-  } else if (offsets) {
-    const uint64_t zero = 0;
-    smatrix_b200_memcpy(sh->local, offsets, &zero, 8);
   }
-  const int want_fill = pairs != NULL && total > 0 && total <= pairs_cap;
+  const int want_fill = want && total > 0 && total <= cap_pairs;
   uint64_t mine[4] = {(uint64_t)want_fill, want_fill ? total : 0, 0, 0}, all[RT_MAXW][4];
   rt_allgather(sh, mine, all);
   uint64_t most = 0;
@@ -664,6 +656,8 @@ uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* sh, const uint32_t* xs
     any_fill |= (int)all[r][0];
     if (all[r][1] > most) most = all[r][1];
   }
+  *filled = want_fill;
+  *any_fill_out = any_fill;
   if (!any_fill) return total;
   rt_need_rowbuf(sh, most);
   if (want_fill) { /* every row's offset travels to the row's owner */
@@ -684,6 +678,79 @@ uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* sh, const uint32_t* xs
                                 (uint32_t*)sh->peer_rowbuf[s]);
   }
   rt_barrier(sh);
-  if (want_fill) smatrix_b200_memcpy(sh->local, pairs, sh->rowbuf, (size_t)total * 8);
+  return total;
+}
+
+/* row ids (or items) as a device array: host arrays are few compared with the pairs, one staged copy */
+static const uint32_t* rt_ids_on_device(smatrix_shard_t* sh, const uint32_t* xs, size_t n) {
+  if (!n || rt_is_dev(sh, xs)) return xs;
+  rt_need_stage(sh, n + 1);
+  smatrix_b200_memcpy(sh->local, sh->stage[0][0], xs, n * 4);
+  return sh->stage[0][0];
+}
+
+uint64_t smatrix_b200_shard_getrow_batch(smatrix_shard_t* sh, const uint32_t* xs, size_t n, uint64_t* offsets,
+                                         uint32_t* pairs, uint64_t pairs_cap) {
+  if (n >= 0xFFFFFFFEull) rt_die(sh, "getrow_batch: too many rows in one call");
+  int filled = 0, any = 0;
+  const uint64_t total = rt_getrow_core(sh, rt_ids_on_device(sh, xs, n), n, pairs != NULL, pairs_cap, &filled, &any);
+  if (offsets) {
+    if (n) {
+      smatrix_b200_memcpy(sh->local, offsets, sh->inbox + OFF_OFS(sh->cap), (n + 1) * 8);
+    } else {
+      const uint64_t zero = 0;
+      smatrix_b200_memcpy(sh->local, offsets, &zero, 8);
+    }
+  }
+  if (filled) smatrix_b200_memcpy(sh->local, pairs, sh->rowbuf, (size_t)total * 8);
+  return total;
+}
+
+/* The read side of the co-occurrence recommender across ranks (examples/cf_recommender.c:50-86, same
+ * contract as smatrix_cf_neighbors_batch): the rows come through the getrow route; the totals
+ * (value at (item, 0) and at (neighbour, 0)) are two sharded gets; the scores are computed where the
+ * pairs landed. */
+uint64_t smatrix_b200_shard_cf_neighbors_batch(smatrix_shard_t* sh, const uint32_t* items, size_t n,
+                                               uint64_t* offsets, uint32_t* ids, double* scores, uint64_t cap) {
+  if (n >= 0xFFFFFFFEull) rt_die(sh, "cf_neighbors_batch: too many items in one call");
+  const uint32_t* d_items = rt_ids_on_device(sh, items, n);
+  int filled = 0, any = 0;
+  const uint64_t total = rt_getrow_core(sh, d_items, n, ids != NULL && scores != NULL, cap, &filled, &any);
+  if (offsets) {
+    if (n) {
+      smatrix_b200_memcpy(sh->local, offsets, sh->inbox + OFF_OFS(sh->cap), (n + 1) * 8);
+    } else {
+      const uint64_t zero = 0;
+      smatrix_b200_memcpy(sh->local, offsets, &zero, 8);
+    }
+  }
+  if (!any) return total;
+  /* scratch on my GPU: neighbour ids, their totals, my items' totals, zeros (column 0), scores, and a
+   * copy of the CSR offsets + items (the gets below reuse the inbox's local arrays) */
+  const size_t np = filled ? (size_t)total : 0, nn = filled ? n : 0;
+  const size_t big = np > nn ? np : nn;
+  char* scratch = (char*)smatrix_b200_dev_alloc(sh->local, big * 4 * 2 + np * 4 + nn * 4 * 2 + np * 8 + (nn + 1) * 8 + 256);
+  uint32_t* d_zero = (uint32_t*)scratch;
+  uint32_t* d_cols = d_zero + big;
+  uint32_t* d_btot = d_cols + big;
+  uint32_t* d_atot = d_btot + np;
+  uint32_t* d_keep = d_atot + nn;                                        /* my items */
+  uint64_t* d_off = (uint64_t*)(((uintptr_t)(d_keep + nn) + 7) & ~(uintptr_t)7);
+  double* d_scores = (double*)(d_off + nn + 1);
+  if (filled) {
+    smatrix_b200_memcpy(sh->local, d_off, sh->inbox + OFF_OFS(sh->cap), (n + 1) * 8);
+    smatrix_b200_memcpy(sh->local, d_keep, d_items, n * 4);
+    smatrix_b200_memset0(sh->local, d_zero, big * 4);
+    smatrix_b200_pair_cols(sh->local, (const uint32_t*)sh->rowbuf, total, d_cols);
+  }
+  rt_read_piece(sh, RT_GET, d_cols, d_zero, np, d_btot);                  /* collective: n = 0 on ranks that do not fill */
+  rt_read_piece(sh, RT_GET, d_keep, d_zero, nn, d_atot);
+  if (filled) {
+    /* the ids go out through d_cols' slot again (same values), the scores through d_scores */
+    smatrix_b200_cf_scores_totals(sh->local, n, d_off, (const uint32_t*)sh->rowbuf, d_atot, d_btot, d_cols, d_scores);
+    smatrix_b200_memcpy(sh->local, ids, d_cols, (size_t)total * 4);
+    smatrix_b200_memcpy(sh->local, scores, d_scores, (size_t)total * 8);
+  }
+  smatrix_b200_dev_free(sh->local, scratch);
   return total;
 }

@@ -671,6 +671,22 @@ class ShardedSparseMatrix:
         assert got == total
         return offsets, pairs[:total]
 
+    def cf_neighbors_batch(self, items):
+        """examples/cf_recommender.c:50-86 for THIS rank's items -> (offsets[n+1], ids[total], scores[total]);
+        collective (every rank calls it, each with its own items)."""
+        items = np.ascontiguousarray(items, dtype=np.uint32)
+        n = len(items)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        h = self._handle()
+        total = int(self._lib.smatrix_b200_shard_cf_neighbors_batch(h, items.ctypes.data, n, offsets.ctypes.data,
+                                                                    None, None, 0))
+        ids = np.zeros(max(total, 1), dtype=np.uint32)
+        scores = np.zeros(max(total, 1), dtype=np.float64)
+        got = int(self._lib.smatrix_b200_shard_cf_neighbors_batch(h, items.ctypes.data, n, offsets.ctypes.data,
+                                                                  ids.ctypes.data, scores.ctypes.data, max(total, 1)))
+        assert got == total
+        return offsets, ids[:total], scores[:total]
+
     def getrow_batch_into(self, d_xs, n: int, d_offsets: int, d_pairs: int, pairs_cap: int) -> int:
         """The raw collective call on device (or host) pointers; returns the total number of pairs."""
         return int(self._lib.smatrix_b200_shard_getrow_batch(self._handle(), d_xs, n, d_offsets, d_pairs, pairs_cap))

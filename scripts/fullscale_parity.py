@@ -3,7 +3,7 @@ uniform incr ops over 13 M rows -> 1.51 B nnz — built by the UNMODIFIED refere
 (oracle/_ref, single thread: its fastest setting) and by the CUDA library, then compared:
   * per-row digests (rowlen, #pairs, sum col, sum val, sum col*val) for ALL 13 M rows,
   * N_GETS point gets of the C2 query stream (50 % hits).
-Writes profiles/r1_fullscale_parity.json.  ~8 minutes of CPU time, ~35 GB of host RAM."""
+Writes profiles/r2_fullscale_parity.json.  ~8 minutes of CPU time, ~35 GB of host RAM."""
 import ctypes as C, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -80,5 +80,5 @@ report.update({"rows_checked": checked, "row_digest_mismatches": mismatch_rows, 
                "ok": mismatch_rows == 0 and report["get_mismatches"] == 0 and pairs_total == report["gpu_nnz"]})
 print(json.dumps(report))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(report, open(os.path.join(ROOT, "gpurun_out", "r1_fullscale_parity.json"), "w"), indent=1)
+json.dump(report, open(os.path.join(ROOT, "gpurun_out", "r2_fullscale_parity.json"), "w"), indent=1)
 m.close(); ref.close()

@@ -66,6 +66,19 @@ def main():
     assert (cpu.sort_rows(o1, p1) == cpu.sort_rows(o2, p2)).all(), f"rank {rank}: sharded getrow pairs mismatch"
     o0, p0 = m.getrow_batch(np.zeros(0, U32))
     assert len(o0) == 1 and len(p0) == 0
+    if kind == "c":                                   # the CF read side across ranks: bit-exact doubles
+        items = np.unique(allx)[rank::11][:200]
+        co, cids, cscores = m.cf_neighbors_batch(items)
+        o3, p3 = ref.getrow_many(items)
+        assert (co == o3).all(), f"rank {rank}: cf offsets mismatch"
+        for i, a in enumerate(items[:40]):
+            lo, hi = int(co[i]), int(co[i + 1])
+            got = dict(zip(cids[lo:hi].tolist(), cscores[lo:hi].tolist()))
+            a_total, want = ref.get(int(a), 0), {}
+            for b, cc in p3[lo:hi]:
+                den = np.sqrt(np.float64(a_total)) * np.sqrt(np.float64(ref.get(int(b), 0) or 1))
+                want[int(b)] = 0.0 if (den == 0.0 or np.float64(cc) > den) else float(np.float64(cc) / den)
+            assert got == want, f"rank {rank}: cf scores of item {a}"
     tot = torch.tensor([m.stat("rows"), m.stat("nnz")], device=dev)
     dist.all_reduce(tot)
     o, p = ref.getrow_many(np.unique(allx))

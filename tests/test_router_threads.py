@@ -101,8 +101,21 @@ def _rank_main(sim, name, rank, world, errors, device_arrays):
         rows_total, nnz_total = m.sum(m.stat("rows")), m.sum(m.stat("nnz"))
         assert rows_total == len(np.unique(allx)), (rows_total, len(np.unique(allx)))
         assert nnz_total == len(ref.getrow_many(np.unique(allx))[1])
+        # the CF read side across ranks (examples/cf_recommender.c:50-86): bit-exact doubles
+        items = np.concatenate([np.unique(allx)[rank::7][:60], np.array([7], U32)])
+        co, cids, cscores = m.cf_neighbors_batch(items)
+        o3, p3 = ref.getrow_many(items)
+        assert (co == o3).all(), f"rank {rank}: cf offsets mismatch"
+        for i, a in enumerate(items):
+            lo, hi = int(co[i]), int(co[i + 1])
+            got = dict(zip(cids[lo:hi].tolist(), cscores[lo:hi].tolist()))
+            a_total, want = ref.get(int(a), 0), {}
+            for b, cc in p3[lo:hi]:
+                den = np.sqrt(np.float64(a_total)) * np.sqrt(np.float64(ref.get(int(b), 0) or 1))
+                want[int(b)] = 0.0 if (den == 0.0 or np.float64(cc) > den) else float(np.float64(cc) / den)
+            assert got == want, f"rank {rank}: cf scores of item {a}"
         with pytest.raises(AttributeError):                                          # not sharded: must refuse
-            m.cf_neighbors_batch
+            m.incr_batch_out
         dev.free()
         m.close(); ref.close()
     except BaseException as e:                           # noqa: BLE001 - reported by the main thread
