@@ -908,8 +908,14 @@ def run_c4(job: Job):
         h_pairs = job.pinned(2 * cap)
         h_rl = job.pinned(offsets.numel())
         KE = min(K, 4)
+        for w in range(min(a.warmup, 2)):               # warm-up of the host-pointer path (staging buffer, pinned pages)
+            nrow = cut[K] - cut[K - 1]
+            h_ids[:nrow].copy_(ids_all[cut[K - 1]:cut[K]])
+            job.torch.cuda.synchronize()
+            getrow(h_ids[:nrow], cap, h_off.data_ptr(), h_pairs.data_ptr()) if not sharded else \
+                m.getrow_batch_into(h_ids.data_ptr(), nrow, h_off.data_ptr(), h_pairs.data_ptr(), cap)
         h2d0, d2h0 = m.stat("h2d_bytes"), m.stat("d2h_bytes")
-        secs, epairs = 0.0, 0
+        secs, epairs, e_series = 0.0, 0, []
         for j in range(KE):
             nrow = cut[j + 1] - cut[j]
             h_ids[:nrow].copy_(ids_all[cut[j]:cut[j + 1]])
@@ -922,10 +928,12 @@ def run_c4(job: Job):
                 lib.smatrix_rowlen_batch(m._handle(), h_ids.data_ptr(), nrow, h_rl.data_ptr())
                 epairs += int(lib.smatrix_getrow_batch(m._handle(), h_ids.data_ptr(), nrow, h_off.data_ptr(),
                                                        h_pairs.data_ptr(), cap))
-            secs += job.max_over_ranks(time.perf_counter() - t0)
+            dt = job.max_over_ranks(time.perf_counter() - t0)
+            e_series.append(round(dt * 1e3, 2))
+            secs += dt
         h2d, d2h, epairs = job.sum_over_ranks(m.stat("h2d_bytes") - h2d0, m.stat("d2h_bytes") - d2h0, epairs)
         e2e = {"value": epairs / secs / 1e6, "unit": "Mpairs/s", "h2d_bytes_per_step": h2d // KE,
-               "d2h_bytes_per_step": d2h // KE, "ms_per_step": secs / KE * 1e3, "steps": KE,
+               "d2h_bytes_per_step": d2h // KE, "ms_per_step": secs / KE * 1e3, "steps": KE, "step_ms": e_series,
                "pcie_frac": (d2h / KE / world) / (secs / KE) / 55e9,
                "note": "row ids, rowlens, offsets and pairs in pinned HOST buffers through smatrix_rowlen_batch + "
                        "smatrix_getrow_batch; the D2H of 8 B per pair is inside the timed region (PCIe-bound); bytes = the "

@@ -46,6 +46,7 @@ typedef struct {
   char* base;
   size_t size;
   size_t used;
+  int owned; /* cudaMalloc'ed by us (freed at close); 0 = a block given back to the slab, e.g. a replaced directory */
 } smx_seg_t;
 
 struct smatrix_s {
@@ -229,7 +230,24 @@ static void push_segment(smatrix_t* s, char* base, size_t size) {
   g->base = base;
   g->size = size;
   g->used = 0;
+  g->owned = 1;
   s->seg_bytes += size;
+}
+
+/* a block carved from the slab that is no longer needed (a replaced directory) becomes a segment of
+ * its own: later reservations are served from it before fresh slab is touched */
+static void slab_give_back(smatrix_t* s, char* base, size_t size) {
+  size &= ~(size_t)127;
+  if (size < (1u << 16)) return;
+  push_segment(s, base, size);
+  s->segs[s->nsegs - 1].owned = 0;
+  s->seg_bytes -= size; /* it was counted when its parent segment was pushed */
+  /* keep the growing tail segment LAST (next_segment_size and the bump cursor look at it) */
+  if (s->nsegs >= 2) {
+    smx_seg_t t = s->segs[s->nsegs - 1];
+    s->segs[s->nsegs - 1] = s->segs[s->nsegs - 2];
+    s->segs[s->nsegs - 2] = t;
+  }
 }
 
 /* A contiguous, 128-byte aligned device region of `bytes` (not zeroed).  Carved from the arena
@@ -239,6 +257,15 @@ static void push_segment(smatrix_t* s, char* base, size_t size) {
  * long-lived table should reserve its arena up front (SMATRIX_ARENA_GIB). */
 static char* slab_reserve(smatrix_t* s, size_t bytes) {
   bytes = (bytes + 127) & ~(size_t)127;
+  for (int i = 0; i + 1 < s->nsegs; i++) { /* given-back blocks and the tails of earlier segments first */
+    smx_seg_t* f = &s->segs[i];
+    if (!f->owned && f->size - f->used >= bytes) {
+      char* p = f->base + f->used;
+      f->used += bytes;
+      s->slab_bytes += bytes;
+      return p;
+    }
+  }
   smx_seg_t* g = s->nsegs ? &s->segs[s->nsegs - 1] : NULL;
   if (!g || g->size - g->used < bytes) {
     size_t size = next_segment_size(s);
@@ -439,6 +466,7 @@ static void resize_dir(smatrix_t* s, uint64_t new_cap) {
   s->n_launches++;
   CK(cudaStreamSynchronize(s->stream));
   if (!s->dir_in_arena) CK(cudaFree(s->dir));
+  else slab_give_back(s, (char*)s->dir, (size_t)s->dir_cap * sizeof(smx_row_t)); /* the old directory's arena space */
   s->dir = nd;
   s->dir_in_arena = in_arena;
   s->dir_cap = new_cap;
@@ -959,9 +987,9 @@ uint64_t smatrix_getrow_batch(smatrix_t* s, const uint32_t* xs, size_t n, uint64
       timed_end(s);
       s->n_launches++;
     } else {
-      if (total * 8 > s->d_rowbuf_bytes) {
+      if (total * 8 > s->d_rowbuf_bytes) { /* grows with slack: batches of similar size must not re-allocate */
         if (s->d_rowbuf) cudaFree(s->d_rowbuf);
-        s->d_rowbuf_bytes = (size_t)total * 8;
+        s->d_rowbuf_bytes = (size_t)total * 8 + (size_t)total * 2 + 4096;
         s->d_rowbuf = (uint32_t*)dmalloc(s, s->d_rowbuf_bytes);
       }
       timed_begin(s);
@@ -1432,7 +1460,8 @@ void smatrix_close(smatrix_t* s) {
     printf("libsmatrix error: could not write %s; the previous snapshot (if any) was kept\n", s->fname);
     fflush(stdout);
   }
-  for (int i = 0; i < s->nsegs; i++) cudaFree(s->segs[i].base);
+  for (int i = 0; i < s->nsegs; i++)
+    if (s->segs[i].owned) cudaFree(s->segs[i].base);
   free(s->segs);
   if (!s->dir_in_arena) cudaFree(s->dir);
   cudaFree(s->d_ctl);
