@@ -334,15 +334,10 @@ class Job:
         """The product handle: SparseMatrix at N = 1, the C router's sharded matrix at N > 1.  Only
         handles that hold a table reserve the slab arena."""
         from libsmatrix_b200 import SparseMatrix
-        if arena_gib:
-            os.environ["SMATRIX_ARENA_GIB"] = str(arena_gib)
-        try:
-            if self.world > 1:
-                from libsmatrix_b200.sharded import open_sharded
-                return open_sharded(self.rank, self.world, self.local)
-            return SparseMatrix(device=self.local)
-        finally:
-            os.environ.pop("SMATRIX_ARENA_GIB", None)
+        if self.world > 1:
+            from libsmatrix_b200.sharded import open_sharded
+            return open_sharded(self.rank, self.world, self.local, arena_gib=arena_gib)
+        return SparseMatrix(device=self.local, arena_gib=arena_gib)
 
     def generator(self, m):
         """A single-GPU handle whose stream runs the synthetic-stream kernels (N > 1: a helper handle)."""

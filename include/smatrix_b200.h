@@ -19,6 +19,9 @@ extern "C" {
  * SMATRIX_RECYCLE (free lists of vacated buckets on/off), SMATRIX_PRESIZE (distinct-row estimate
  * that sizes the directory before a chunk of new rows, on/off). */
 smatrix_t* smatrix_b200_open(const char* fname, int device);
+/* the same with the slab arena given explicitly (bytes; 0 = segments on demand) instead of through
+ * $SMATRIX_ARENA_GIB — for hosts that open several handles with different needs from several threads */
+smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_bytes);
 
 /* File-backed handles: write the snapshot NOW (temporary file, fsync, atomic rename) and return 0
  * on success, -1 on failure (or when the handle has no file).  The reference streams dirty rows to

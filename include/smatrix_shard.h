@@ -37,6 +37,8 @@ typedef struct smatrix_shard_s smatrix_shard_t;
  * cannot be mapped (then on EVERY rank: the outcome is agreed on before anyone returns).
  * $SMATRIX_SHARD_TIMEOUT (seconds, default 300): how long a rank waits for its peers. */
 smatrix_shard_t* smatrix_b200_shard_open(const char* name, int rank, int world, int device);
+/* the same with this rank's slab arena given explicitly (bytes; 0 = on demand) instead of $SMATRIX_ARENA_GIB */
+smatrix_shard_t* smatrix_b200_shard_open_arena(const char* name, int rank, int world, int device, size_t arena_bytes);
 void smatrix_b200_shard_close(smatrix_shard_t* self);            /* collective */
 smatrix_t* smatrix_b200_shard_local(smatrix_shard_t* self);      /* this rank's own table (stats, timers) */
 int smatrix_b200_shard_rank(smatrix_shard_t* self);

@@ -42,6 +42,7 @@ PROTOTYPES = {
                                                C.c_void_p, C.c_uint64]),
     # include/smatrix_b200.h
     "smatrix_b200_open": (C.c_void_p, [C.c_char_p, C.c_int]),
+    "smatrix_b200_open_arena": (C.c_void_p, [C.c_char_p, C.c_int, C.c_size_t]),
     "smatrix_b200_snapshot": (C.c_int, [C.c_void_p]),
     "smatrix_b200_device": (C.c_int, [C.c_void_p]),
     "smatrix_b200_stream": (C.c_void_p, [C.c_void_p]),
@@ -102,6 +103,7 @@ PROTOTYPES = {
 # include/smatrix_shard.h
 PROTOTYPES.update({
     "smatrix_b200_shard_open": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "smatrix_b200_shard_open_arena": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_size_t]),
     "smatrix_b200_shard_close": (None, [C.c_void_p]),
     "smatrix_b200_shard_local": (C.c_void_p, [C.c_void_p]),
     "smatrix_b200_shard_rank": (C.c_int, [C.c_void_p]),

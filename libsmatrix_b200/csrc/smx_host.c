@@ -1363,6 +1363,10 @@ static int snapshot_load(smatrix_t* s, int fd) {
 
 /* ------------------------------------------------------------------------------ open / close */
 smatrix_t* smatrix_b200_open(const char* fname, int device) {
+  return smatrix_b200_open_arena(fname, device, (size_t)env_u32("SMATRIX_ARENA_GIB", 0) << 30);
+}
+
+smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_bytes) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     fprintf(stderr, "libsmatrix: no usable CUDA device (this build has no CPU path)\n");
@@ -1417,7 +1421,7 @@ smatrix_t* smatrix_b200_open(const char* fname, int device) {
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
   if (s->parts_log_max > 8) s->parts_log_max = 8;
-  s->arena_bytes = (size_t)env_u32("SMATRIX_ARENA_GIB", 0) << 30;
+  s->arena_bytes = arena_bytes;
   if (s->arena_bytes) push_segment(s, (char*)dmalloc(s, s->arena_bytes), s->arena_bytes);
   s->dir_cap = 1ull << s->dir_log_min;
   s->dir_in_arena = s->arena_bytes != 0; /* then nothing is cudaFree'd while batches are applied */

@@ -112,6 +112,11 @@ static void rt_die(smatrix_shard_t* sh, const char* fmt, ...) { /* reference src
   abort();
 }
 
+static uint32_t rt_env(const char* name, uint32_t dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? (uint32_t)strtoul(v, NULL, 0) : dflt;
+}
+
 static double rt_now(void) {
   struct timespec t;
   clock_gettime(CLOCK_MONOTONIC, &t);
@@ -238,12 +243,12 @@ static void rt_need_rowbuf(smatrix_shard_t* sh, uint64_t pairs) {
 }
 
 /* ------------------------------------------------------------------------------ open / close */
-static uint32_t rt_env(const char* name, uint32_t dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? (uint32_t)strtoul(v, NULL, 0) : dflt;
-}
 
 smatrix_shard_t* smatrix_b200_shard_open(const char* name, int rank, int world, int device) {
+  return smatrix_b200_shard_open_arena(name, rank, world, device, (size_t)rt_env("SMATRIX_ARENA_GIB", 0) << 30);
+}
+
+smatrix_shard_t* smatrix_b200_shard_open_arena(const char* name, int rank, int world, int device, size_t arena_bytes) {
   if (!name || world < 1 || world > RT_MAXW || rank < 0 || rank >= world) {
     fprintf(stderr, "libsmatrix: shard_open: bad arguments\n");
     return NULL;
@@ -291,7 +296,7 @@ smatrix_shard_t* smatrix_b200_shard_open(const char* name, int rank, int world, 
     }
     if (sh->shm->world != (uint32_t)world) { fprintf(stderr, "libsmatrix: world size mismatch on %s\n", sh->name); munmap(sh->shm, sizeof(rt_shm_t)); free(sh); return NULL; }
   }
-  sh->local = smatrix_b200_open(NULL, device);
+  sh->local = smatrix_b200_open_arena(NULL, device, arena_bytes);
   rt_blob_t* me = &sh->shm->blob[rank];
   me->pid = (int32_t)getpid();
   me->device = device;

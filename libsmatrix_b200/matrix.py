@@ -35,11 +35,13 @@ class DevPtr:
 
 class SparseMatrix:
     def __init__(self, file_path: str | None = None, device: int | None = None,
-                 _lib_path: str | None = None):
+                 _lib_path: str | None = None, arena_gib: float | None = None):
         self._lib = binding.load(_lib_path)
         self.filename = file_path
         fname = file_path.encode() if file_path is not None else None
-        if device is None:
+        if arena_gib is not None:       # explicit slab arena (otherwise $SMATRIX_ARENA_GIB, default: on demand)
+            self._h = self._lib.smatrix_b200_open_arena(fname, int(device or 0), int(arena_gib * (1 << 30)))
+        elif device is None:
             self._h = self._lib.smatrix_open(fname)
         else:
             self._h = self._lib.smatrix_b200_open(fname, int(device))

@@ -593,12 +593,16 @@ class ShardedSparseMatrix:
     """ctypes wrapper of smatrix_b200_shard_* — no computation and no routing logic here."""
 
     def __init__(self, rank: int, world: int, device: int = 0, name: str | None = None,
-                 _lib_path: str | None = None):
+                 _lib_path: str | None = None, arena_gib: float | None = None):
         from . import binding
         self._lib = binding.load(_lib_path)
         self.rank, self.world = rank, world
         self._name = name or default_name()
-        self._h = self._lib.smatrix_b200_shard_open(self._name.encode(), rank, world, int(device))
+        if arena_gib is not None:
+            self._h = self._lib.smatrix_b200_shard_open_arena(self._name.encode(), rank, world, int(device),
+                                                              int(arena_gib * (1 << 30)))
+        else:
+            self._h = self._lib.smatrix_b200_shard_open(self._name.encode(), rank, world, int(device))
         if not self._h:
             raise RuntimeError("smatrix_b200_shard_open failed (no CUDA device or no peer access)")
         self.local = SparseMatrix._borrow(self._lib, self._lib.smatrix_b200_shard_local(self._h))
@@ -729,12 +733,19 @@ class ShardedSparseMatrix:
         pass   # closing is collective: never from a finalizer
 
 
-def open_sharded(rank: int, world: int, device: int = 0, group=None, name: str | None = None):
+def open_sharded(rank: int, world: int, device: int = 0, group=None, name: str | None = None,
+                 arena_gib: float | None = None):
     """The C router when it can be set up, else (every rank alike — shard_open agrees on the outcome
     before anyone returns) the torch.distributed fallback.  $SMX_ROUTER=torch forces the fallback."""
     if os.environ.get("SMX_ROUTER", "c") != "torch":
         try:
-            return ShardedSparseMatrix(rank, world, device, name=name)
+            return ShardedSparseMatrix(rank, world, device, name=name, arena_gib=arena_gib)
         except RuntimeError as e:
             print(f"[smatrix sharded] rank {rank}: C router unavailable ({e}); using torch.distributed", flush=True)
-    return TorchShardedSparseMatrix(rank, world, device, group=group)
+    if arena_gib:      # the fallback's tables read the arena size from the environment at open
+        os.environ["SMATRIX_ARENA_GIB"] = str(int(arena_gib))
+    try:
+        return TorchShardedSparseMatrix(rank, world, device, group=group)
+    finally:
+        if arena_gib:
+            os.environ.pop("SMATRIX_ARENA_GIB", None)

@@ -62,7 +62,45 @@ def test_committed_bench_lines_carry_the_contract_keys(n):
         assert r["random_sector"]["incr_frac"] > 0.4          # north_star: >= 40 % of the random-sector roofline
 
 
+ROUND2 = [("r2_bench_n1.json", "incr_mops_c2", 1), ("r2_bench_n1_steps20.json", "incr_mops_c2", 1),
+          ("r2_bench_c3_n1.json", "incr_mops_c3", 1), ("r2_bench_c4_n1.json", "getrow_mpairs_c4", 1),
+          ("r2_bench_n2.json", "incr_mops_c2", 2), ("r2_bench_n8.json", "incr_mops_c2", 8),
+          ("r2_bench_c5_n2.json", "incr_mops_c5", 2), ("r2_bench_c5_n8.json", "incr_mops_c5", 8)]
+
+
+@pytest.mark.parametrize("name,metric,n", ROUND2)
+def test_round2_bench_lines(name, metric, n):
+    """Every committed round-2 line: the contract keys, zero parity mismatches against the CPU reference
+    (incl. sharded getrow at N > 1), the size-independent checks, roofline + e2e + cpu_baseline present."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not recorded yet")
+    d = _line(path)
+    assert BASE_KEYS <= set(d) and d["metric"] == metric and d["n_gpus"] == n
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "u32" and d["warmup"] >= 3
+    assert "workload" in d["config"] and d["gpu_launches"] > 0 and d["value"] > 0
+    c = d["clocks"]
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    p = d["parity"]
+    assert p["mismatches"] == 0 and p["ranks"] == n and p["checker"] == "reference"
+    assert p["gets"] > 0 and p["rowlens"] > 0 and p["getrow_pairs"] > 0
+    assert all(v for k, v in d["checks"].items() if k.endswith("_ok") or k.endswith("_exact"))
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    if n > 1:
+        assert r["nvlink"]["remote_bytes_per_rank_per_step"] > 0 and d["scaling"] in ("weak", "strong")
+    if metric == "incr_mops_c2" and n == 1:
+        assert r["random_sector"]["incr_frac"] > 0.4          # north_star: >= 40 % of the random-sector roofline
+
+
 def test_full_scale_parity_record():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_fullscale_parity.json")))
+    assert d["ok"] and d["row_digest_mismatches"] == 0 and d["get_mismatches"] == 0
+    assert d["rows_checked"] == 13_000_000 and d["pairs_compared"] == d["gpu_nnz"] == 1_510_576_950
     d = json.load(open(os.path.join(ROOT, "profiles", "r1_fullscale_parity.json")))
     assert d["ok"] and d["row_digest_mismatches"] == 0 and d["get_mismatches"] == 0
     assert d["rows_checked"] == 13_000_000 and d["pairs_compared"] == d["gpu_nnz"] == 1_510_576_950
