@@ -582,10 +582,16 @@ _seq = [0]
 
 
 def default_name() -> str:
-    """A rendezvous name every rank of one launch derives alike: the launcher's pid (torchrun agent /
-    the test that spawned the ranks), the rendezvous port, and how many sharded matrices this process
-    has opened so far (every rank opens them in the same order)."""
+    """A rendezvous name every rank of one launch agrees on.  With a torch.distributed group already up,
+    rank 0 picks it (pid + counter) and broadcasts it — plumbing only, once per matrix.  Otherwise it is
+    derived from what the ranks of one launch share: the launcher's pid (torchrun agent / the test that
+    spawned the ranks), the rendezvous port, and how many sharded matrices this process has opened so
+    far (every rank opens them in the same order)."""
     _seq[0] += 1
+    if dist.is_available() and dist.is_initialized():
+        box = [f"smx_{os.getpid()}_{_seq[0]}" if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
     return f"smx_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}_{_seq[0]}"
 
 
