@@ -115,6 +115,7 @@ struct smatrix_s {
 
   unsigned long long* free_ptr[SMX_CLASSES]; /* device stacks of vacated buckets, per size class */
   uint32_t free_cap[SMX_CLASSES];
+  int debug;                                 /* SMATRIX_DEBUG: growth decisions on stderr */
   int recycle;                               /* SMATRIX_RECYCLE (default 1) */
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
 
@@ -442,6 +443,7 @@ static void presize_dir(smatrix_t* s, const smx_ops_t* ops) {
   double est = zeros >= 1.0 ? -(double)m * ln_unit(zeros / (double)m) : (double)n;
   if (est > (double)n) est = (double)n;
   const uint64_t cap = pow2_at_least((uint64_t)(4.0 * ((double)used + 1.1 * est)) + 64);
+  if (s->debug) fprintf(stderr, "[smatrix] presize: %llu ops, %.0f zero bits, ~%.0f distinct rows\n", (unsigned long long)n, zeros, est);
   if (cap > s->dir_cap) resize_dir(s, cap);
 }
 
@@ -453,6 +455,10 @@ static uint64_t pow2_at_least(uint64_t v) {
 
 static void resize_dir(smatrix_t* s, uint64_t new_cap) {
   double t0 = now_ns();
+  if (s->debug)
+    fprintf(stderr, "[smatrix] directory %llu -> %llu entries (rows %llu, refused ops %u of which directory-full %u)\n",
+            (unsigned long long)s->dir_cap, (unsigned long long)new_cap, (unsigned long long)s->h_ctl->dir_used,
+            s->h_ctl->n_defer, s->h_ctl->n_dirfull);
   smx_view_t from = view_of(s);
   /* with an arena the directory lives in it too (cudaMalloc / cudaFree of multi-GiB blocks stall for
    * tens of ms on these hosts); a replaced directory's arena space is not reused */
@@ -1414,6 +1420,7 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   if (s->chunk_max > (1u << 30)) s->chunk_max = 1u << 30;
   s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
   s->recycle = (int)env_u32("SMATRIX_RECYCLE", 1);
+  s->debug = (int)env_u32("SMATRIX_DEBUG", 0);
   s->presize = (int)env_u32("SMATRIX_PRESIZE", 1);
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;

@@ -494,11 +494,14 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       p.off = recycled ? (SMX_PLAN_RECYCLED | recycled) : (base + incl - bytes);
       S.plan[j] = p;
       if (recycled) agg_inc(&V.ctl->n_recycled);
-      if (caplog >= SMX_BIG_LOG) S.big[agg_inc(&V.ctl->n_big)] = j;
+      /* which kernel re-places the row: old buckets of >= 512 cells whose NEW bucket fits 32 KB of shared
+       * memory go to one block each (k_migrate_mid); anything bigger is filled in place by the whole grid
+       * (k_migrate_big); the rest (old < 512 cells) by one warp (k_migrate) */
+      const bool by_grid = caplog >= SMX_BIG_LOG || (caplog >= SMX_MID_LOG && newlog > SMX_MID_SMEM_LOG);
+      if (by_grid) S.big[agg_inc(&V.ctl->n_big)] = j;
       else if (caplog >= SMX_MID_LOG) S.mid[agg_inc(&V.ctl->n_mid)] = j;
       /* fresh buckets that are filled in place (global CAS) need a zeroed region */
-      const bool in_place = caplog >= SMX_BIG_LOG ||
-                            (caplog >= SMX_MID_LOG ? newlog > SMX_MID_SMEM_LOG : newlog > SMX_SMEM_MIGRATE_LOG);
+      const bool in_place = by_grid || (caplog < SMX_MID_LOG && newlog > SMX_SMEM_MIGRATE_LOG);
       if (in_place && !recycled) agg_inc64(&V.ctl->need_zero);
     }
   }
@@ -611,7 +614,7 @@ k_migrate_mid(smx_view_t V, smx_lists_t S, uint32_t n_mid, char* region) {
     ull* ob = (ull*)h.slots;
     ull* nb = plan_bucket(p, region);
     const uint32_t cap = 1u << caplog;
-    if (p.newlog <= SMX_MID_SMEM_LOG) {
+    { /* k_grow_plan only sends rows here whose new bucket fits the shared-memory buffer */
       const uint32_t ncap = 1u << p.newlog, nsec = ncap >> 2;
       for (uint32_t i = threadIdx.x; i < ncap; i += blockDim.x) sb[i] = 0ull;
       __syncthreads();
@@ -622,12 +625,6 @@ k_migrate_mid(smx_view_t V, smx_lists_t S, uint32_t n_mid, char* region) {
       }
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < ncap; i += blockDim.x) nb[i] = sb[i];
-    } else {
-      for (uint32_t s0 = threadIdx.x; s0 < cap; s0 += blockDim.x) {
-        const ull c = ob[s0];
-        ob[s0] = 0ull;
-        if (c != 0ull) place_cell(nb, p.newlog, c);
-      }
     }
     __syncthreads(); /* every thread has read the header and finished with sb */
     if (threadIdx.x == 0) finish_growth(e, h, nb, p.newlog);
@@ -1343,7 +1340,9 @@ __global__ void __launch_bounds__(SMX_BLOCK)
 k_sketch_set(const uint32_t* xs, uint32_t n, uint32_t* bitmap, uint32_t bits_log) {
   const uint32_t mask = (uint32_t)((1ull << bits_log) - 1ull);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t h = smx_mix_owner(xs[i]) & mask;
+    /* NOT mix_owner: on a shard every row has the same mix_owner(x) mod G, which would leave part of the
+     * bitmap unreachable and bias the estimate low (measured at G = 2: 16 M estimated for 24 M rows) */
+    const uint32_t h = smx_mix_col(xs[i] ^ 0x5bd1e995u) & mask;
     const uint32_t bit = 1u << (h & 31u);
     if (!(__ldcg(&bitmap[h >> 5]) & bit)) atomicOr(&bitmap[h >> 5], bit);
   }
