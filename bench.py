@@ -565,16 +565,21 @@ def run_write_workload(job: Job, name: str):
                  "getrow_value_sum": int(pairs[1::2].to(torch.int64).sum().item())}
         del pairs, offs, ids, sample
 
-    # ---- roofline probes in the same process (random 32 B sector reads / 4 B atomics, 32 GiB)
+    m.close()
+    torch.cuda.empty_cache()      # the timed batches are back with the driver before the next tables reserve their arenas
+
+    # ---- roofline probes in the same process (random 32 B sector reads / 4 B atomics over 32 GiB), after the
+    # table is gone: the probe buffer and a 120 GiB arena do not fit one GPU together
     probes = None
     if not a.no_probes and rank == 0:
-        pm = job.generator(m)
+        from libsmatrix_b200 import SparseMatrix
+        pm = SparseMatrix(device=job.local)
         foot, acc = 32 << 30, 1 << 30
         probes = {"footprint_gib": 32,
                   "random_read_32B_per_s": pm.probe_random_read(foot, acc, 32),
                   "random_read_8B_per_s": pm.probe_random_read(foot, acc, 8),
                   "random_atomic_4B_per_s": pm.probe_random_atomic(foot, acc)}
-    m.close()
+        pm.close()
 
     e2e = None if a.no_e2e else run_e2e_writes(job, wl, mk)
     parity = None if a.no_parity else run_parity_writes(job, wl)
