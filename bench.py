@@ -456,11 +456,14 @@ def run_write_workload(job: Job, name: str):
         wl.incr(scratch, wx, wy)
     del_me = scratch.get_batch(wx, wy)
     del del_me
+    # how large an inbox the warm-up batches needed: a hash-sharded skewed stream (c3) sends the hottest rows'
+    # ops to ONE owner, which then receives more than a batch's worth
+    inbox_ops = max(B, scratch.route_stats()["max_inbox_ops"]) if world > 1 else B
     scratch.close()
 
     m = mk()
     if world > 1:
-        m.reserve_route(B)      # inboxes + IPC exchange: communicator-style set-up, untimed
+        m.reserve_route(inbox_ops)      # inboxes + IPC exchange: communicator-style set-up, untimed
     g = job.generator(m)
 
     # ---- prefill (untimed, measured separately)
@@ -581,7 +584,7 @@ def run_write_workload(job: Job, name: str):
                   "random_atomic_4B_per_s": pm.probe_random_atomic(foot, acc)}
         pm.close()
 
-    e2e = None if a.no_e2e else run_e2e_writes(job, wl, mk)
+    e2e = None if a.no_e2e else run_e2e_writes(job, wl, mk, inbox_ops)
     parity = None if a.no_parity else run_parity_writes(job, wl)
 
     nnz_total, rows_seen, vsum_total = job.sum_over_ranks(nnz_local, rows_local, vsum_local)
@@ -666,7 +669,7 @@ def run_write_workload(job: Job, name: str):
     return line
 
 
-def run_e2e_writes(job: Job, wl: WriteWorkload, mk):
+def run_e2e_writes(job: Job, wl: WriteWorkload, mk, inbox_ops=None):
     """Same stream, HOST buffers: each timed step is one incr_batch(host arrays) call per rank —
     H2D of the batch, (N > 1: the route,) the update, and the D2H reads of the control block.
     Per step: barrier, wall clock around the call, max over ranks.  Byte counts = the library's own
@@ -684,7 +687,7 @@ def run_e2e_writes(job: Job, wl: WriteWorkload, mk):
     scratch.close()
     m = mk()
     if world > 1:
-        m.reserve_route(B)
+        m.reserve_route(inbox_ops or B)
     g = job.generator(m)
     for k in range(wl.prefill):
         wl.gen_ops(g, wl.first_of(k), B, dx, dy)

@@ -86,7 +86,10 @@ uint64_t smatrix_b200_shard_cf_neighbors_batch(smatrix_shard_t* self, const uint
  * (count, count exchange, scatter over NVLink, arrival barrier), time spent applying the inbox,
  * number of routes, bytes this rank stored into OTHER ranks' inboxes. */
 enum { SMX_SHARD_STAT_ROUTE_NS = 0, SMX_SHARD_STAT_APPLY_NS = 1, SMX_SHARD_STAT_ROUTES = 2,
-       SMX_SHARD_STAT_REMOTE_BYTES = 3 };
+       SMX_SHARD_STAT_REMOTE_BYTES = 3,
+       SMX_SHARD_STAT_MAX_INBOX_OPS = 4 /* largest inbox any routed batch needed so far (the same on every rank;
+                                           not reset): hash-sharding a skewed stream sends the hottest rows' ops to
+                                           ONE owner, so size smatrix_b200_shard_reserve from a warm-up's value */ };
 uint64_t smatrix_b200_shard_stat(smatrix_shard_t* self, int which);
 void smatrix_b200_shard_stat_reset(smatrix_shard_t* self);
 

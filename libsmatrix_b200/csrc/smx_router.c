@@ -348,7 +348,7 @@ void smatrix_b200_shard_close(smatrix_shard_t* sh) {
 uint64_t smatrix_b200_shard_stat(smatrix_shard_t* sh, int which) {
   return (which >= 0 && which < 8) ? sh->stat[which] : 0;
 }
-void smatrix_b200_shard_stat_reset(smatrix_shard_t* sh) { memset(sh->stat, 0, sizeof sh->stat); }
+void smatrix_b200_shard_stat_reset(smatrix_shard_t* sh) { memset(sh->stat, 0, 4 * sizeof sh->stat[0]); /* the accounting, not the high-water marks */ }
 smatrix_t* smatrix_b200_shard_local(smatrix_shard_t* sh) { return sh->local; }
 int smatrix_b200_shard_rank(smatrix_shard_t* sh) { return sh->rank; }
 int smatrix_b200_shard_world(smatrix_shard_t* sh) { return sh->world; }
@@ -409,6 +409,7 @@ static void rt_route(smatrix_shard_t* sh, const uint32_t* d_xs, const uint32_t* 
     if (in > need) need = in;
   }
   if (want_ord && total >= 0xFFFFFFFFull) rt_die(sh, "ordered collective batches are limited to 2^32 - 2 ops");
+  if (need > sh->stat[SMX_SHARD_STAT_MAX_INBOX_OPS]) sh->stat[SMX_SHARD_STAT_MAX_INBOX_OPS] = need;
   rt_need_inbox(sh, need); /* every rank sees the same matrix: the same decision everywhere */
   R->n_recv = 0;
   R->bias = 0;

@@ -707,7 +707,7 @@ class ShardedSparseMatrix:
 
     def route_stats(self, reset: bool = False) -> dict:
         g = lambda k: int(self._lib.smatrix_b200_shard_stat(self._handle(), k))
-        d = {"route_ms": g(0) / 1e6, "apply_ms": g(1) / 1e6, "routes": g(2), "remote_bytes": g(3)}
+        d = {"route_ms": g(0) / 1e6, "apply_ms": g(1) / 1e6, "routes": g(2), "remote_bytes": g(3), "max_inbox_ops": g(4)}
         if reset:
             self._lib.smatrix_b200_shard_stat_reset(self._handle())
         return d
