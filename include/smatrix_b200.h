@@ -179,6 +179,11 @@ void smatrix_b200_lane_sync(smatrix_t* self, int lane);
 void smatrix_b200_apply_ordered(smatrix_t* self, int op, const uint32_t* d_xs, const uint32_t* d_ys,
                                 const uint32_t* d_vals, const uint32_t* d_ords, size_t n);
 
+/* the same, additionally returning every op's value as if the batch had been applied one op at a time in
+ * the order d_ords gives (smatrix_*_batch_out for permuted batches; used by the multi-GPU router) */
+void smatrix_b200_apply_ordered_out(smatrix_t* self, int op, const uint32_t* d_xs, const uint32_t* d_ys,
+                                    const uint32_t* d_vals, const uint32_t* d_ords, size_t n, uint32_t* d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,16 @@ void smatrix_b200_shard_decr_batch(smatrix_shard_t* self, const uint32_t* xs, co
 void smatrix_b200_shard_set_batch(smatrix_shard_t* self, const uint32_t* xs, const uint32_t* ys,
                                   const uint32_t* vals, size_t n);
 
+/* The same three, additionally returning what every single call would have returned (out[i] = value of the
+ * cell right after op i when the COLLECTIVE batch is applied one op at a time in input order; same contract
+ * as smatrix_*_batch_out, src/smatrix.c:230,241,252).  Always ordered; one piece per call. */
+void smatrix_b200_shard_incr_batch_out(smatrix_shard_t* self, const uint32_t* xs, const uint32_t* ys,
+                                       const uint32_t* vals, size_t n, uint32_t* out);
+void smatrix_b200_shard_decr_batch_out(smatrix_shard_t* self, const uint32_t* xs, const uint32_t* ys,
+                                       const uint32_t* vals, size_t n, uint32_t* out);
+void smatrix_b200_shard_set_batch_out(smatrix_shard_t* self, const uint32_t* xs, const uint32_t* ys,
+                                      const uint32_t* vals, size_t n, uint32_t* out);
+
 /* n x smatrix_get / smatrix_rowlen (src/smatrix.c:174-185, :212-223): queries travel to the owners,
  * the owners' kernels write the answers straight into the asking rank's buffer. */
 void smatrix_b200_shard_get_batch(smatrix_shard_t* self, const uint32_t* xs, const uint32_t* ys,

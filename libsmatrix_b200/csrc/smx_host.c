@@ -851,6 +851,26 @@ void smatrix_b200_apply_ordered(smatrix_t* s, int op, const uint32_t* d_xs, cons
   leave(s);
 }
 
+/* apply_ordered + the per-op return values (N1) for a permuted batch: out[i] = value of op i's cell right
+ * after op i in the sequential order given by d_ords.  Device arrays, one chunk. */
+void smatrix_b200_apply_ordered_out(smatrix_t* s, int op, const uint32_t* d_xs, const uint32_t* d_ys,
+                                    const uint32_t* d_vals, const uint32_t* d_ords, size_t n, uint32_t* d_out) {
+  if (n == 0) return;
+  if (op < 0 || op > 2) smx_die("apply_ordered_out: op must be 0 (incr), 1 (decr) or 2 (set)");
+  if (n > (1u << 30)) smx_die("apply_ordered_out: at most 2^30 ops per call (one chunk)");
+  enter(s);
+  process_chunk_ordered(s, op, d_xs, d_ys, d_vals, d_ords, (uint32_t)n);
+  ensure_batch_out(s, (uint32_t)n);
+  smx_ops_t ops;
+  ops.xs = d_xs; ops.ys = d_ys; ops.vs = d_vals; ops.idx = d_ords; ops.v_const = 1u; ops.n = (uint32_t)n;
+  smx_launch_batch_out(s->stream, view_of(s), ops, op == 2 ? SMX_OP_SETZERO : op, d_out, s->bo_addr[0], s->bo_addr[1],
+                       s->bo_idx[0], s->bo_idx[1], s->bo_seg, s->bo_tiles, s->bo_sort, s->bo_sort_bytes);
+  s->n_launches += 9;
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaGetLastError());
+  leave(s);
+}
+
 /* ------------------------------------------------------------------------------ read path */
 #define READ_STEP (1u << 26)
 

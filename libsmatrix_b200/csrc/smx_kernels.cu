@@ -1820,12 +1820,21 @@ extern "C" size_t smx_batch_out_sort_bytes(uint32_t n) {
   (void)n;
   return 64;
 #else
-  size_t bytes = 0;
+  size_t bytes = 0, bytes32 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const ull*)nullptr, (ull*)nullptr, (const uint32_t*)nullptr,
                                   (uint32_t*)nullptr, (int)n, 0, 48);
-  return bytes + 256;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes32, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n, 0, 32);
+  return (bytes > bytes32 ? bytes : bytes32) + 256;
 #endif
 }
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_permute_addrs(const ull* addrs, const uint32_t* order, uint32_t n, ull* out) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) out[k] = addrs[order[k]];
+}
+/* ops.idx == NULL: input order = array order.  Otherwise ops.idx[i] is op i's place in the input order (the
+ * multi-GPU router hands over permuted batches): the ops are first ordered by that index, then stably by
+ * cell, so inside a cell's group they are in input order again. */
 extern "C" void smx_launch_batch_out(smx_stream_t st, smx_view_t v, smx_ops_t ops, int op, uint32_t* out,
                                      uint64_t* addrs_a, uint64_t* addrs_b, uint32_t* idx_a, uint32_t* idx_b,
                                      uint64_t* seg, uint64_t* tile_agg, void* sort_tmp, size_t sort_bytes) {
@@ -1836,27 +1845,42 @@ extern "C" void smx_launch_batch_out(smx_stream_t st, smx_view_t v, smx_ops_t op
     return;
   }
   SMX_LAUNCH(k_find_addr, grid_for(n), SMX_BLOCK, st, v, ops, (ull*)addrs_a, idx_a);
+  const ull* s_addr = (const ull*)addrs_b; /* sorted cell addresses / op indices end up here */
+  const uint32_t* s_idx = idx_b;
 #ifdef SMX_HOSTSIM
   (void)sort_tmp; (void)sort_bytes;
   {
     std::vector<uint32_t> order(n);
     for (uint32_t i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return addrs_a[a] < addrs_a[b]; });
+    const uint32_t* ords = ops.idx;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      if (addrs_a[a] != addrs_a[b]) return addrs_a[a] < addrs_a[b];
+      return ords ? ords[a] < ords[b] : false;
+    });
     for (uint32_t p = 0; p < n; p++) { addrs_b[p] = addrs_a[order[p]]; idx_b[p] = order[p]; }
   }
 #else
   /* LSD radix sort: stable, so ops of one cell stay in input order (device addresses fit in 48 bits) */
-  cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, (const ull*)addrs_a, (ull*)addrs_b, (const uint32_t*)idx_a,
-                                  idx_b, (int)n, 0, 48, (cudaStream_t)st);
+  if (ops.idx) {
+    cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, ops.idx, out /* scratch for the sorted keys */,
+                                    (const uint32_t*)idx_a, idx_b, (int)n, 0, 32, (cudaStream_t)st);
+    SMX_LAUNCH(k_permute_addrs, grid_for(n), SMX_BLOCK, st, (const ull*)addrs_a, (const uint32_t*)idx_b, n, (ull*)addrs_b);
+    cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, (const ull*)addrs_b, (ull*)addrs_a, (const uint32_t*)idx_b,
+                                    idx_a, (int)n, 0, 48, (cudaStream_t)st);
+    s_addr = (const ull*)addrs_a;
+    s_idx = idx_a;
+  } else {
+    cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, (const ull*)addrs_a, (ull*)addrs_b, (const uint32_t*)idx_a,
+                                    idx_b, (int)n, 0, 48, (cudaStream_t)st);
+  }
 #endif
   const int negate = (op == SMX_OP_DECR) ? 1 : 0;
   const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  SMX_LAUNCH(k_out_gather, grid_for(n), SMX_BLOCK, st, ops, negate, (const ull*)addrs_b, (const uint32_t*)idx_b, (ull*)seg);
+  SMX_LAUNCH(k_out_gather, grid_for(n), SMX_BLOCK, st, ops, negate, s_addr, s_idx, (ull*)seg);
   SMX_LAUNCH(k_seg_tile, tiles, SMX_BLOCK, st, (const ull*)seg, n, (ull*)tile_agg);
   SMX_LAUNCH(k_seg_tiles, 1, 1, st, (ull*)tile_agg, tiles);
   SMX_LAUNCH(k_seg_apply, tiles, SMX_BLOCK, st, (ull*)seg, n, (const ull*)tile_agg);
-  SMX_LAUNCH(k_out_write, grid_for(n), SMX_BLOCK, st, ops, negate, (const ull*)addrs_b, (const uint32_t*)idx_b,
-             (const ull*)seg, out);
+  SMX_LAUNCH(k_out_write, grid_for(n), SMX_BLOCK, st, ops, negate, s_addr, s_idx, (const ull*)seg, out);
 }
 
 extern "C" void smx_launch_get(smx_stream_t st, smx_view_t v, const uint32_t* xs, const uint32_t* ys,

@@ -540,6 +540,77 @@ void smatrix_b200_shard_set_batch(smatrix_shard_t* sh, const uint32_t* xs, const
   rt_write(sh, 2, xs, ys, vals, n, 1); /* last writer in GLOBAL input order wins */
 }
 
+/* The same batches, returning what every single call would have returned (SURVEY.md 8f N1 across ranks):
+ * the ops travel with their global input-order index, every owner applies its inbox in that order and
+ * computes the per-op values (smatrix_b200_apply_ordered_out), and the values travel back like read answers.
+ * One piece per call (host slices are staged whole): the order is global. */
+static void rt_write_out(smatrix_shard_t* sh, int op, const uint32_t* xs, const uint32_t* ys, const uint32_t* vals,
+                         size_t n, uint32_t* out) {
+  if (n >= 0xFFFFFFFFull) rt_die(sh, "sharded batch too large for one call");
+  if (n && !out) rt_die(sh, "batch_out: out must not be NULL");
+  const int W = sh->world, me = sh->rank;
+  const int dev = n ? rt_is_dev(sh, xs) : 1;
+  if (n && (rt_is_dev(sh, ys) != dev || (vals && rt_is_dev(sh, vals) != dev) || rt_is_dev(sh, out) != dev))
+    rt_die(sh, "batch arrays must be all host or all device pointers");
+  uint64_t mine[4] = {n, n ? (vals != NULL) + 1u : 0u, 0, 0}, all[RT_MAXW][4];
+  rt_allgather(sh, mine, all);
+  uint64_t nmax = 0;
+  int has_vals = -1;
+  for (int r = 0; r < W; r++) {
+    if (all[r][0] > nmax) nmax = all[r][0];
+    if (all[r][1]) {
+      const int hv = (int)all[r][1] - 1;
+      if (has_vals >= 0 && has_vals != hv) rt_die(sh, "every rank must pass vals, or none (NULL = all ones)");
+      has_vals = hv;
+    }
+  }
+  if (nmax == 0) return;
+  if (has_vals < 0) has_vals = 0;
+  const uint32_t *d_xs = xs, *d_ys = ys, *d_vs = has_vals ? vals : NULL;
+  if (n && !dev) {
+    rt_need_stage(sh, n + 1);
+    smatrix_b200_memcpy(sh->local, sh->stage[0][0], xs, n * 4);
+    smatrix_b200_memcpy(sh->local, sh->stage[0][1], ys, n * 4);
+    if (has_vals) smatrix_b200_memcpy(sh->local, sh->stage[0][2], vals, n * 4);
+    d_xs = sh->stage[0][0]; d_ys = sh->stage[0][1]; d_vs = has_vals ? sh->stage[0][2] : NULL;
+  }
+  rt_route_t R;
+  rt_route(sh, d_xs, d_ys, d_vs, n, 1, 1, &R);
+  const uint64_t cap = sh->cap;
+  uint32_t* d_ret = (uint32_t*)(sh->inbox + OFF_CNT(cap)); /* per-op values of MY inbox, inbox order */
+  if (R.n_recv)
+    smatrix_b200_apply_ordered_out(sh->local, op, (const uint32_t*)(sh->inbox + OFF_X(cap)),
+                                   (const uint32_t*)(sh->inbox + OFF_Y(cap)),
+                                   has_vals ? (const uint32_t*)(sh->inbox + OFF_V(cap)) : NULL,
+                                   (const uint32_t*)(sh->inbox + OFF_O(cap)), (size_t)R.n_recv, d_ret);
+  for (int i = 0; i < W; i++) { /* every sender's run goes back into that sender's answer buffer */
+    const int s = (me + i) % W;
+    const uint64_t c = R.cnt[s][me];
+    if (c)
+      smatrix_b200_memcpy(sh->local, (uint32_t*)(sh->peer_inbox[s] + OFF_ANS(cap)) + rt_send_base(&R, s, me),
+                          d_ret + R.recv_start[s], (size_t)c * 4);
+  }
+  rt_barrier(sh);
+  if (n) {
+    uint32_t* d_out = dev ? out : sh->stage[0][3];
+    smatrix_b200_gather(sh->local, d_out, (const uint32_t*)(sh->inbox + OFF_ANS(cap)),
+                        (const uint32_t*)(sh->inbox + OFF_POS(cap)), n);
+    if (!dev) smatrix_b200_memcpy(sh->local, out, d_out, n * 4);
+  }
+}
+void smatrix_b200_shard_incr_batch_out(smatrix_shard_t* sh, const uint32_t* xs, const uint32_t* ys,
+                                       const uint32_t* vals, size_t n, uint32_t* out) {
+  rt_write_out(sh, 0, xs, ys, vals, n, out);
+}
+void smatrix_b200_shard_decr_batch_out(smatrix_shard_t* sh, const uint32_t* xs, const uint32_t* ys,
+                                       const uint32_t* vals, size_t n, uint32_t* out) {
+  rt_write_out(sh, 1, xs, ys, vals, n, out);
+}
+void smatrix_b200_shard_set_batch_out(smatrix_shard_t* sh, const uint32_t* xs, const uint32_t* ys,
+                                      const uint32_t* vals, size_t n, uint32_t* out) {
+  rt_write_out(sh, 2, xs, ys, vals, n, out);
+}
+
 /* ------------------------------------------------------------------------------ reads */
 enum { RT_GET = 0, RT_ROWLEN = 1, RT_COUNTS = 2 };
 

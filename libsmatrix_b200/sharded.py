@@ -640,6 +640,32 @@ class ShardedSparseMatrix:
     def set_batch(self, xs, ys, vals=None):
         self._write(self._lib.smatrix_b200_shard_set_batch, xs, ys, vals)
 
+    def _write_out(self, fn, xs, ys, vals, out):
+        """-> out[i] = what single call i of the COLLECTIVE batch would have returned (input order)."""
+        keep: list = []
+        A = SparseMatrix._arg
+        px, py, pv = A(xs, keep), A(ys, keep), A(vals, keep)
+        if isinstance(xs, DevPtr):
+            if not isinstance(out, DevPtr):
+                raise ValueError("raw device arrays need a raw device `out`")
+            po = out.ptr
+        else:
+            out = self._out_like(xs, out)
+            po = out.data_ptr() if torch.is_tensor(out) else out.ctypes.data
+        if torch.is_tensor(xs) and xs.is_cuda:
+            torch.cuda.current_stream(xs.device).synchronize()
+        fn(self._handle(), px, py, pv, self._n(xs), po)
+        return out
+
+    def incr_batch_out(self, xs, ys, vals=None, out=None):
+        return self._write_out(self._lib.smatrix_b200_shard_incr_batch_out, xs, ys, vals, out)
+
+    def decr_batch_out(self, xs, ys, vals=None, out=None):
+        return self._write_out(self._lib.smatrix_b200_shard_decr_batch_out, xs, ys, vals, out)
+
+    def set_batch_out(self, xs, ys, vals=None, out=None):
+        return self._write_out(self._lib.smatrix_b200_shard_set_batch_out, xs, ys, vals, out)
+
     def _out_like(self, xs, out):
         n = self._n(xs)
         if out is not None:

@@ -66,6 +66,21 @@ def main():
     assert (cpu.sort_rows(o1, p1) == cpu.sort_rows(o2, p2)).all(), f"rank {rank}: sharded getrow pairs mismatch"
     o0, p0 = m.getrow_batch(np.zeros(0, U32))
     assert len(o0) == 1 and len(p0) == 0
+    if kind == "c":                                   # per-op return values across ranks
+        for op in ("incr", "decr", "set", "incr"):
+            bx = (rng.zipf(1.4, 60000) % 500).astype(U32) * U32(2654435761)
+            by = (rng.zipf(1.3, 60000) % 9).astype(U32)
+            bv = rng.integers(1, 1000, 60000).astype(U32)
+            want = ref.apply(op, bx, by, bv, want_out=True)
+            s6 = sl(60000)
+            got = getattr(m, op + "_batch_out")(bx[s6], by[s6], bv[s6])
+            assert (np.asarray(got) == want[s6]).all(), f"rank {rank}: sharded {op}_batch_out mismatch (host arrays)"
+        bx = (rng.zipf(1.4, 60000) % 500).astype(U32) * U32(2654435761)
+        by = (rng.zipf(1.3, 60000) % 9 + 1).astype(U32)
+        want = ref.apply("incr", bx, by, np.ones(60000, U32), want_out=True)
+        got = m.incr_batch_out(t(bx[sl(60000)]), t(by[sl(60000)]), None)          # device arrays, all ones
+        assert (got.cpu().numpy().view(U32) == want[sl(60000)]).all(), f"rank {rank}: sharded incr_batch_out mismatch (device)"
+        allx = np.concatenate([allx, bx]); ally = np.concatenate([ally, by])
     if kind == "c":                                   # the CF read side across ranks: bit-exact doubles
         items = np.unique(allx)[rank::11][:200]
         co, cids, cscores = m.cf_neighbors_batch(items)

@@ -114,8 +114,19 @@ def _rank_main(sim, name, rank, world, errors, device_arrays):
                 den = np.sqrt(np.float64(a_total)) * np.sqrt(np.float64(ref.get(int(b), 0) or 1))
                 want[int(b)] = 0.0 if (den == 0.0 or np.float64(cc) > den) else float(np.float64(cc) / den)
             assert got == want, f"rank {rank}: cf scores of item {a}"
-        with pytest.raises(AttributeError):                                          # not sharded: must refuse
-            m.incr_batch_out
+        # per-op return values across ranks: heavy key duplication, column 0, all three ops
+        for op in ("incr", "decr", "set", "incr"):
+            bx = (rng.zipf(1.4, 6000) % 50).astype(U32) * U32(2654435761)
+            by = (rng.zipf(1.3, 6000) % 9).astype(U32)
+            bv = rng.integers(1, 1000, 6000).astype(U32)
+            want = ref.apply(op, bx, by, bv, want_out=True)
+            s6 = sl(6000)
+            dout = dev.up(np.zeros(len(bx[s6]), U32)) if device_arrays else None
+            got = getattr(m, op + "_batch_out")(put(bx[s6]), put(by[s6]), put(bv[s6]), out=dout)
+            got = dev.down(got) if device_arrays else np.asarray(got)
+            assert (got == want[s6]).all(), f"rank {rank}: sharded {op}_batch_out mismatch"
+        with pytest.raises(AttributeError):                                          # not a sharded call: must refuse
+            m.getRow
         dev.free()
         m.close(); ref.close()
     except BaseException as e:                           # noqa: BLE001 - reported by the main thread
