@@ -450,10 +450,11 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       caplog = h.meta & SMX_META_CAPLOG;
       const ull need = 2ull * ((ull)h.live + (ull)h.want); /* load factor <= 1/2 after growth */
       /* small buckets grow x8 (4 -> 32 -> 256 cells: two re-placements on the way to a 256-cell
-       * bucket instead of three, and less vacated memory); 512 .. 4096 cells grow x4 (rows in that range
-       * are the skewed workloads' hot rows on their way up: half as many block-per-row re-placements,
-       * 0.42 -> 0.2 ms per 2^25 ops of config 3); everything else x2 like the reference (:390) */
-      newlog = caplog + (caplog < 8u ? 3u : (caplog >= SMX_MID_LOG && caplog < SMX_BIG_LOG ? 2u : 1u));
+       * bucket instead of three, and less vacated memory); 256 -> 512 like the reference (:390); buckets of
+       * 512 cells and more grow x4: rows that get there are a skewed workload's hot rows on their way up,
+       * and every re-placement of a big row is millions of random atomics (config 3 spent a third of each
+       * step on it with x2) — memory is the cheaper side of that trade on a 180 GB part */
+      newlog = caplog + (caplog < 8u ? 3u : (caplog >= SMX_MID_LOG ? 2u : 1u));
       if (newlog > 8u && caplog < 8u) newlog = 8u;
       if (newlog < SMX_MIN_SLAB_LOG) newlog = SMX_MIN_SLAB_LOG;
       while ((1ull << newlog) < need && newlog < SMX_MAX_CAPLOG) ++newlog;
