@@ -455,3 +455,30 @@ def scenario_batch_out(make, n: int = 40000):
     assert (got == want).all()
     compare(m, ref, np.arange(62), xs, ys)
     m.close(); ref.close()
+
+
+def scenario_recycling_churn(make, waves: int = 6, rows_per_wave: int = 400):
+    """Bucket recycling (replaces smatrix_mfree on every resize, src/smatrix.c:383-416): rows are born in
+    waves and grow through every size class at different times, so buckets vacated by older rows are
+    reused by younger ones — and a reused bucket must never leak a previous owner's cells."""
+    rng = np.random.default_rng(71)
+    m, ref = make(), checker()
+    born = []
+    for w in range(waves):
+        ids = (np.arange(w * rows_per_wave, (w + 1) * rows_per_wave, dtype=U32) * U32(2654435761))
+        born.append(ids)
+        xs, ys = [], []
+        for age, old in enumerate(reversed(born)):           # older rows get more (and new) columns each wave
+            k = 6 * 3 ** min(age, 5)                          # 6, 18, 54, ... columns per row this wave
+            xs.append(np.repeat(old, k))
+            ys.append(rng.integers(1, 40 * 3 ** min(age, 5) + 40, size=len(old) * k).astype(U32))
+        xs, ys = np.concatenate(xs), np.concatenate(ys)
+        perm = rng.permutation(len(xs))
+        vs = rng.integers(1, 2**32, len(xs), dtype=np.uint64).astype(U32)
+        apply_both(m, ref, "incr", xs[perm], ys[perm], vs[perm])
+    allrows = np.concatenate(born)
+    sample = rng.integers(0, len(xs), 20000)
+    compare(m, ref, np.concatenate([allrows, np.array([7, 8], U32)]), xs[sample], ys[sample])
+    assert m.stat("recycled") > 0, "younger rows should have reused buckets vacated by older ones"
+    assert m.stat("free_bytes") >= 0 and m.stat("bucket_bytes") >= m.stat("live_bucket_bytes")
+    m.close(); ref.close()

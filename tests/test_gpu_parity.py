@@ -75,6 +75,10 @@ def test_col0_ordering(make):
     ps.scenario_col0_ordering(make)
 
 
+def test_recycling_churn(make):
+    ps.scenario_recycling_churn(make)
+
+
 def test_big_row(make):
     ps.scenario_big_row(make, n_cols=300000)
 
