@@ -14,7 +14,7 @@ extern "C" {
 
 /* smatrix_open on an explicit CUDA device ordinal (smatrix_open uses $SMATRIX_DEVICE, default 0).
  * Environment read at open: SMATRIX_ARENA_GIB (reserve that much slab memory up front instead of
- * cudaMalloc'ing segments on demand), SMATRIX_CHUNK (ops per internal chunk, default 2^25),
+ * cudaMalloc'ing segments on demand), SMATRIX_CHUNK (ops per internal chunk, default 2^26),
  * SMATRIX_DIR_LOG2 (initial directory size), SMATRIX_PREAGG (warp pre-aggregation on/off),
  * SMATRIX_RECYCLE (free lists of vacated buckets on/off), SMATRIX_PRESIZE (distinct-row estimate
  * that sizes the directory before a chunk of new rows, on/off). */

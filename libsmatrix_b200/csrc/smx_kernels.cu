@@ -9,13 +9,17 @@
  * Kernel                replaces (reference src/smatrix.c)
  *   k_upsert            smatrix_lookup(write) + cmap_lookup/insert + rmap_probe/insert + the
  *                       value update of set/incr/decr  (:225-304, :343-380, :621-713)
- *   k_grow_plan/migrate smatrix_rmap_resize (:383-416)
- *   k_dir_rehash        smatrix_cmap_resize (:715-741)
+ *   k_grow_plan, k_free_push, k_migrate / _mid / _big
+ *                       smatrix_rmap_resize + smatrix_mfree of the old map (:383-416, :151-166)
+ *   k_dir_rehash, k_sketch_*   smatrix_cmap_resize (:715-741)
  *   k_get               smatrix_get (:174-185)
  *   k_rowlen            smatrix_rowlen (:212-223)
- *   k_row_counts/scan/getrow_fill   smatrix_getrow (:189-210) for whole batches of rows
+ *   k_row_counts, scan, k_getrow_inline / _fill / _chunks   smatrix_getrow (:189-210) for batches of rows
  *   k_set_max/mark/commit  last-writer-wins resolution for smatrix_set batches (:225-234 applied
  *                       sequentially)
+ *   k_snap_units / _rows / _big   the row blocks of the .smx file (:454-482) in the loader's layout (:499-545)
+ *   k_partition_count / _scatter  no counterpart: chunk ordering by directory slice, and the multi-GPU
+ *                       route (every owner's run stored straight into that owner's inbox over NVLink)
  *
  * Concurrency rules the code relies on (DESIGN.md "Concurrency"):
  *   - cells and directory entries are only ever claimed 0 -> key by a 64-bit CAS and keys never
@@ -1733,7 +1737,7 @@ extern "C" void smx_launch_upsert(smx_stream_t st, smx_view_t v, smx_ops_t ops, 
                                   int preaggregate) {
   if (m == 0) return;
   /* NOT a persistent grid: one block per 4 x 256 ops, so blocks retire continuously and kernels of
-   * other streams (the multi-GPU router's partition + NCCL copies) interleave with an update in
+   * other streams (uploads of the next host-array piece, a second handle's kernels) interleave with an update in
    * flight instead of waiting for 1184 resident blocks to drain */
   ull want_blocks = ((ull)m + 4ull * SMX_BLOCK - 1) / (4ull * SMX_BLOCK);
   if (want_blocks < 1) want_blocks = 1;
