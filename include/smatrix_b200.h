@@ -58,8 +58,9 @@ enum {
   SMX_STAT_RECYCLED = 19,   /* row growths served from the free lists so far                   */
   SMX_STAT_H2D_BYTES = 20,  /* bytes copied host -> device by this handle so far (batches, tables) */
   SMX_STAT_D2H_BYTES = 21,  /* bytes copied device -> host (answers, control-block reads)      */
-  SMX_STAT_BUCKET_BYTES = 22 /* slab bytes ever handed out for column buckets; / LIVE_BUCKET_BYTES = the
+  SMX_STAT_BUCKET_BYTES = 22, /* slab bytes ever handed out for column buckets; / LIVE_BUCKET_BYTES = the
                                 allocator's overhead (vacated buckets wait on the free lists)   */
+  SMX_STAT_SPILLED = 23     /* cells of big rows that did not fit their shared-memory tile during a re-placement */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 

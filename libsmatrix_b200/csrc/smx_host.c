@@ -116,6 +116,10 @@ struct smatrix_s {
   unsigned long long* free_ptr[SMX_CLASSES]; /* device stacks of vacated buckets, per size class */
   uint32_t free_cap[SMX_CLASSES];
   int debug;                                 /* SMATRIX_DEBUG: growth decisions on stderr */
+  int migrate_tiles;                         /* SMATRIX_MIGRATE_TILES (default 1): big rows are re-placed tile by tile in shared memory */
+  unsigned long long* d_spill;               /* cells that did not fit their tile (16 bytes each) */
+  uint32_t spill_cap;
+  uint64_t n_spilled;
   int recycle;                               /* SMATRIX_RECYCLE (default 1) */
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
 
@@ -398,9 +402,28 @@ static void grow_rows(smatrix_t* s, uint32_t n_grow) {
   double t2 = now_ns();
   /* buckets built in shared memory are written out whole; only in-place (global CAS) fills need zeros */
   if (bytes && s->h_ctl->need_zero) CK(cudaMemsetAsync(region, 0, bytes, s->stream));
-  smx_launch_migrate(s->stream, v, s->lists, n_grow, n_mid, n_big, region);
+  const int tiles = s->migrate_tiles && n_big;
+  smx_launch_migrate(s->stream, v, s->lists, n_grow, n_mid, n_big, region, tiles);
+  if (tiles) { /* big rows: new buckets built tile by tile in shared memory (k_migrate_tiles) */
+    for (;;) {
+      if (!s->d_spill) {
+        s->spill_cap = s->spill_cap ? s->spill_cap : (1u << 16);
+        s->d_spill = (unsigned long long*)dmalloc(s, (size_t)s->spill_cap * 16);
+      }
+      CK(cudaMemsetAsync(&s->d_ctl->n_spill, 0, 4, s->stream));
+      smx_launch_migrate_tiles(s->stream, v, s->lists, n_big, region, s->d_spill, s->spill_cap);
+      copy_d2h(s, &s->h_small[38], &s->d_ctl->n_spill, 4, s->stream);
+      CK(cudaStreamSynchronize(s->stream));
+      if (s->h_small[38] <= s->spill_cap) break;
+      CK(cudaFree(s->d_spill)); /* the list was too short: step 1 only reads the old buckets, so it can run again */
+      s->d_spill = NULL;
+      s->spill_cap = s->h_small[38] + s->h_small[38] / 2 + 1024;
+    }
+    smx_launch_migrate_tiles_finish(s->stream, v, s->lists, n_big, region, s->d_spill, s->h_small[38]);
+    s->n_spilled += s->h_small[38];
+  }
   if (s->timing) CK(cudaStreamSynchronize(s->stream)); /* attribute the device time to this phase */
-  s->n_launches += (n_grow > n_mid + n_big ? 1 : 0) + (n_mid ? 1 : 0) + (n_big ? 2 : 0);
+  s->n_launches += (n_grow > n_mid + n_big ? 1 : 0) + (n_mid ? 1 : 0) + (n_big ? 3 : 0);
   s->n_row_grows += n_grow;
   s->n_recycled += s->h_ctl->n_recycled;
   s->phase_ns[PH_GROW_PLAN] += t1 - t0;
@@ -1441,6 +1464,8 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   s->preagg = (int)env_u32("SMATRIX_PREAGG", 1);
   s->recycle = (int)env_u32("SMATRIX_RECYCLE", 1);
   s->debug = (int)env_u32("SMATRIX_DEBUG", 0);
+  s->migrate_tiles = (int)env_u32("SMATRIX_MIGRATE_TILES", 1);
+  s->spill_cap = env_u32("SMATRIX_SPILL_CAP", 1u << 16);
   s->presize = (int)env_u32("SMATRIX_PRESIZE", 1);
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;
@@ -1514,6 +1539,7 @@ void smatrix_close(smatrix_t* s) {
   if (s->d_tmp64) cudaFree(s->d_tmp64);
   if (s->d_rowbuf) cudaFree(s->d_rowbuf);
   if (s->d_info) cudaFree(s->d_info);
+  if (s->d_spill) cudaFree(s->d_spill);
   if (s->bo_cap) {
     cudaFree(s->bo_addr[0]); cudaFree(s->bo_addr[1]); cudaFree(s->bo_idx[0]); cudaFree(s->bo_idx[1]);
     cudaFree(s->bo_seg); cudaFree(s->bo_tiles); cudaFree(s->bo_out); cudaFree(s->bo_sort);
@@ -1613,6 +1639,7 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
       break;
     case SMX_STAT_RECYCLED: r = s->n_recycled; break;
     case SMX_STAT_BUCKET_BYTES: r = s->bucket_bytes; break;
+    case SMX_STAT_SPILLED: r = s->n_spilled; break;
     case SMX_STAT_H2D_BYTES: r = s->h2d_bytes; break;
     case SMX_STAT_D2H_BYTES: r = s->d2h_bytes; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;

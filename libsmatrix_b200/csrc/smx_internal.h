@@ -73,6 +73,8 @@ typedef struct {
   uint32_t n_big;                /* of those, rows whose OLD bucket is >= 2^SMX_BIG_LOG      */
   uint32_t n_mid;                /*           rows whose OLD bucket is 2^SMX_MID_LOG .. 2^(SMX_BIG_LOG-1) */
   uint32_t n_recycled;           /* planned buckets taken from the free lists                */
+  uint32_t n_spill;              /* cells k_migrate_tiles could not place inside their tile (spill list length) */
+  uint32_t pad_round;
   unsigned long long plan_bytes; /* bytes of FRESH slab planned by grow_plan                 */
   unsigned long long need_zero;  /* planned buckets that are filled in place (global CAS) and so
                                     need a zeroed region; shared-memory-built buckets do not  */
@@ -135,7 +137,15 @@ void smx_launch_upsert(smx_stream_t stream, smx_view_t v, smx_ops_t ops, smx_lis
 void smx_launch_grow_plan(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow);
 void smx_launch_free_push(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow);
 void smx_launch_migrate(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_grow,
-                        uint32_t n_mid, uint32_t n_big, void* region_base);
+                        uint32_t n_mid, uint32_t n_big, void* region_base, int skip_big);
+/* big rows, two steps: (1) every new bucket is built tile by tile in shared memory; cells that do not fit
+ * their tile go to `spill` (capacity spill_cap entries of 16 bytes, length in ctl->n_spill — if it
+ * exceeds the capacity the host enlarges the list and runs step 1 again: it only reads the old buckets);
+ * (2) the spilled cells are inserted, the old buckets zeroed, the headers switched */
+void smx_launch_migrate_tiles(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_big, void* region_base,
+                              unsigned long long* spill, uint32_t spill_cap);
+void smx_launch_migrate_tiles_finish(smx_stream_t stream, smx_view_t v, smx_lists_t l, uint32_t n_big, void* region_base,
+                                     const unsigned long long* spill, uint32_t n_spill);
 /* distinct-row estimate (linear counting): set bit hash(x) of a zeroed bitmap of 2^bits_log bits,
  * then count the zero bits into ctl->scratch */
 void smx_launch_sketch(smx_stream_t stream, const uint32_t* xs, uint32_t n, uint32_t* bitmap,

@@ -662,6 +662,89 @@ __global__ void k_migrate_big_finish(smx_view_t V, smx_lists_t S, uint32_t n_big
   }
 }
 
+/* Big rows, built instead of filled: the new bucket is cut into tiles of MIG_TILE sectors; a block zeroes a
+ * tile in shared memory, streams in the old sectors whose cells can have their new home in it (old home =
+ * new home mod old size; plus the few sectors behind that range that linear probing pushed cells into),
+ * places the cells with shared-memory CAS in the usual probe order and streams the tile out — no global
+ * atomic, no zeroed target.  A cell whose probe run reaches the end of its tile goes to a small spill
+ * list and is inserted with the ordinary global probe (place_cell) once all tiles are written: from its
+ * home to the tile's end every sector is full, so the probe invariant holds.  k_migrate_big (one global
+ * CAS per cell, 80 % of the random-atomic rate) stays as the reference path (SMATRIX_MIGRATE_TILES=0). */
+#ifndef MIG_TILE_LOG
+#define MIG_TILE_LOG 10u /* the CPU tests also build a variant with tiny tiles, where cells spill all the time */
+#endif
+#define MIG_TILE (1u << MIG_TILE_LOG) /* sectors per tile: 4096 cells = 32 KB */
+__device__ __forceinline__ bool sector_is_full(const ull* sec) {
+  ull c[4];
+  ld_sector(sec, c);
+  return c[0] != 0ull && c[1] != 0ull && c[2] != 0ull && c[3] != 0ull;
+}
+/* the cells of one old sector whose new home lies in the tile [t0, t0 + MIG_TILE) go into the tile */
+__device__ __forceinline__ void tile_take_sector(const ull* sec, ull* sm, uint32_t t0, uint32_t n_new, uint32_t j,
+                                                 smx_ctl_t* ctl, ull* spill, uint32_t spill_cap) {
+  ull c[4];
+  ld_sector(sec, c);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (c[k] == 0ull) continue;
+    const uint32_t hn = smx_mix_col((uint32_t)c[k]) & (n_new - 1u);
+    if (hn - t0 >= MIG_TILE) continue; /* its home is in another tile */
+    bool placed = false;
+    for (uint32_t q = hn - t0; q < MIG_TILE && !placed; ++q) /* same probe order as slot_upsert, inside the tile */
+      for (int w = 0; w < 4 && !placed; ++w) placed = (atomicCAS(&sm[4u * q + w], 0ull, c[k]) == 0ull);
+    if (!placed) { /* the run of full sectors reaches the end of the tile: global probe later */
+      const uint32_t at = atomicAdd(&ctl->n_spill, 1u);
+      if (at < spill_cap) { spill[2ull * at] = (ull)j; spill[2ull * at + 1] = c[k]; }
+    }
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_migrate_tiles(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region, ull* spill, uint32_t spill_cap) {
+  __shared__ ull sm[4u * MIG_TILE];
+  const uint32_t j = S.big[big_first + blockIdx.y];
+  const smx_plan_t p = S.plan[j];
+  const smx_row_t* e = V.dir + p.entry;
+  const Hdr h = ld_hdr(e);
+  const ull* ob = (const ull*)h.slots;
+  ull* nb = plan_bucket(p, region);
+  const uint32_t n_old = 1u << ((h.meta & SMX_META_CAPLOG) - 2u), n_new = 1u << (p.newlog - 2u); /* sectors */
+  const uint32_t n_tiles = n_new >> MIG_TILE_LOG, mask = n_old - 1u;
+  const uint32_t len = n_old < MIG_TILE ? n_old : MIG_TILE;
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t t0 = t << MIG_TILE_LOG;
+    const uint32_t r0 = n_old < MIG_TILE ? 0u : (t0 & mask); /* old home = new home mod old size */
+    for (uint32_t i = threadIdx.x; i < 4u * MIG_TILE; i += blockDim.x) sm[i] = 0ull;
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < len; s += blockDim.x)
+      tile_take_sector(ob + 4ull * ((r0 + s) & mask), sm, t0, n_new, j, V.ctl, spill, spill_cap);
+    /* cells with a home in the range that linear probing pushed behind it: they can only sit in the
+     * sectors that follow as long as the sector before is full (a handful at most; one thread) */
+    if (threadIdx.x == 0 && len < n_old)
+      for (uint32_t s = len; s < n_old && sector_is_full(ob + 4ull * ((r0 + s - 1u) & mask)); ++s)
+        tile_take_sector(ob + 4ull * ((r0 + s) & mask), sm, t0, n_new, j, V.ctl, spill, spill_cap);
+    __syncthreads();
+    ull* out = nb + 4ull * t0;
+    for (uint32_t i = threadIdx.x; i < 4u * MIG_TILE; i += blockDim.x) out[i] = sm[i];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_spill_insert(smx_view_t V, smx_lists_t S, char* region, const ull* spill, uint32_t n_spill) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_spill; i += gridDim.x * blockDim.x) {
+    const smx_plan_t p = S.plan[(uint32_t)spill[2ull * i]];
+    place_cell(plan_bucket(p, region), p.newlog, spill[2ull * i + 1]);
+  }
+}
+/* the vacated buckets of the big rows go to the free lists zeroed (grid x strides over one row, y) */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_zero_old_big(smx_view_t V, smx_lists_t S, uint32_t big_first) {
+  const smx_plan_t p = S.plan[S.big[big_first + blockIdx.y]];
+  const Hdr h = ld_hdr(V.dir + p.entry);
+  ull* ob = (ull*)h.slots;
+  const ull cap = 1ull << (h.meta & SMX_META_CAPLOG);
+  for (ull s = blockIdx.x * (ull)blockDim.x + threadIdx.x; s < cap; s += (ull)gridDim.x * blockDim.x) ob[s] = 0ull;
+}
+
 /* ------------------------------------------------------------------------------------------
  * directory growth (replaces smatrix_cmap_resize, :715-741): re-place every entry into `to`
  * ---------------------------------------------------------------------------------------- */
@@ -1766,7 +1849,7 @@ extern "C" void smx_launch_free_push(smx_stream_t st, smx_view_t v, smx_lists_t 
 }
 
 extern "C" void smx_launch_migrate(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_grow,
-                                   uint32_t n_mid, uint32_t n_big, void* region) {
+                                   uint32_t n_mid, uint32_t n_big, void* region, int skip_big) {
   if (!n_grow) return;
   if (n_grow > n_mid + n_big)
     SMX_LAUNCH(k_migrate, grid_for((ull)n_grow * SMX_WARP), SMX_BLOCK, st, v, l, n_grow, (char*)region);
@@ -1774,6 +1857,7 @@ extern "C" void smx_launch_migrate(smx_stream_t st, smx_view_t v, smx_lists_t l,
     const uint32_t cap = (uint32_t)smx_grid_blocks();
     SMX_LAUNCH(k_migrate_mid, n_mid < cap ? n_mid : cap, SMX_BLOCK, st, v, l, n_mid, (char*)region);
   }
+  if (skip_big) return; /* the caller re-places the big rows with smx_launch_migrate_tiles */
   for (uint32_t first = 0; first < n_big; first += 32768u) {
     const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
     dim3 grid(SMX_WARP > 1 ? 64u : 2u, cnt, 1u);
@@ -1782,6 +1866,24 @@ extern "C" void smx_launch_migrate(smx_stream_t st, smx_view_t v, smx_lists_t l,
   if (n_big) SMX_LAUNCH(k_migrate_big_finish, grid_for(n_big), SMX_BLOCK, st, v, l, n_big, (char*)region);
 }
 
+extern "C" void smx_launch_migrate_tiles(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_big, void* region,
+                                         unsigned long long* spill, uint32_t spill_cap) {
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? 32u : 2u, cnt, 1u);
+    SMX_LAUNCH(k_migrate_tiles, grid, SMX_BLOCK, st, v, l, first, (char*)region, (ull*)spill, spill_cap);
+  }
+}
+extern "C" void smx_launch_migrate_tiles_finish(smx_stream_t st, smx_view_t v, smx_lists_t l, uint32_t n_big, void* region,
+                                                const unsigned long long* spill, uint32_t n_spill) {
+  if (n_spill) SMX_LAUNCH(k_spill_insert, grid_for(n_spill), SMX_BLOCK, st, v, l, (char*)region, (const ull*)spill, n_spill);
+  for (uint32_t first = 0; first < n_big; first += 32768u) {
+    const uint32_t cnt = (n_big - first < 32768u) ? n_big - first : 32768u;
+    dim3 grid(SMX_WARP > 1 ? 32u : 2u, cnt, 1u);
+    SMX_LAUNCH(k_zero_old_big, grid, SMX_BLOCK, st, v, l, first);
+  }
+  if (n_big) SMX_LAUNCH(k_migrate_big_finish, grid_for(n_big), SMX_BLOCK, st, v, l, n_big, (char*)region);
+}
 extern "C" void smx_launch_sketch(smx_stream_t st, const uint32_t* xs, uint32_t n, uint32_t* bitmap,
                                   uint32_t bits_log, smx_ctl_t* ctl) {
   if (!n) return;

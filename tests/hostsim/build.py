@@ -10,20 +10,26 @@ CSRC = os.path.join(ROOT, "libsmatrix_b200", "csrc")
 SO = os.path.join(HERE, "libsmatrix_hostsim.so")
 
 
-def build() -> str:
+def build(defines: list[str] | None = None, suffix: str = "") -> str:
+    """defines / suffix: a variant of the simulator library with other compile-time knobs (e.g. tiny
+    re-placement tiles), written next to the default one."""
+    return _build(os.path.join(HERE, f"libsmatrix_hostsim{suffix}.so"), defines or [], suffix)
+
+
+def _build(SO: str, defines: list[str], suffix: str) -> str:
     srcs = [os.path.join(CSRC, "smx_kernels.cu"), os.path.join(CSRC, "smx_host.c"),
             os.path.join(HERE, "fake_runtime.cpp"), os.path.join(CSRC, "smx_router.c"), os.path.join(HERE, "hostsim.h"),
             os.path.join(CSRC, "smx_internal.h")]
     if os.path.exists(SO) and all(os.path.getmtime(s) < os.path.getmtime(SO) for s in srcs):
         return SO
     common = ["-O1", "-g", "-fPIC", "-DSMX_HOSTSIM", f"-I{HERE}", f"-I{CSRC}", "-Wall",
-              "-Wno-unknown-pragmas", "-Wno-unused-function"]
+              "-Wno-unknown-pragmas", "-Wno-unused-function"] + defines
     objs = []
     for src, cc, extra in ((srcs[0], "g++", ["-x", "c++", "-std=c++17"]),
                            (srcs[1], "gcc", ["-std=gnu11"]),
                            (srcs[2], "g++", ["-std=c++17"]),
                            (srcs[3], "gcc", ["-std=gnu11"])):
-        o = os.path.join(HERE, os.path.basename(src) + ".o")
+        o = os.path.join(HERE, os.path.basename(src) + suffix + ".o")
         subprocess.run([cc] + common + extra + ["-c", src, "-o", o], check=True)
         objs.append(o)
     # -Bsymbolic: the fake cuda* symbols must bind inside this library even when a real

@@ -141,3 +141,36 @@ def test_golden_fixtures(make):
         o, p = m.getrow_batch(g["rows"])
         assert (o == g["offsets"]).all() and (cpu.sort_rows(o, p) == g["pairs_sorted"]).all(), f
         m.close()
+
+
+# ---- big-row re-placement tile by tile (k_migrate_tiles): a simulator variant with TINY tiles (8 sectors instead of
+# 1024), where runs of full sectors reach a tile's end all the time, so the spill list, its insertion pass and the
+# "list too short -> enlarge and run again" loop are exercised on every growth of a big row
+@pytest.fixture(scope="module")
+def sim_small_tiles():
+    from hostsim import build as hb
+    return hb.build(defines=["-DMIG_TILE_LOG=3u"], suffix="_smalltiles")
+
+
+@pytest.mark.parametrize("spill_cap", [2, 1 << 16], ids=["spill-list-regrows", "spill-list-fits"])
+def test_tile_replacement_with_spills(sim_small_tiles, monkeypatch, spill_cap):
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", "6")
+    monkeypatch.setenv("SMATRIX_CHUNK", "30000")
+    monkeypatch.setenv("SMATRIX_SPILL_CAP", str(spill_cap))
+    spilled = []
+
+    def make():
+        m = SparseMatrix(_lib_path=sim_small_tiles)
+        close = m.close
+        m.close = lambda: (spilled.append(m.stat("spilled")), close())[1]
+        return m
+    ps.scenario_big_row(make, n_cols=60000)
+    ps.scenario_read_path_zipf(make, n_rows=300, max_len=30000)
+    ps.scenario_recycling_churn(make, waves=5, rows_per_wave=60)
+    assert sum(spilled) > 0, "tiny tiles must spill"
+
+
+def test_tile_replacement_off_is_identical(sim, monkeypatch):
+    monkeypatch.setenv("SMATRIX_MIGRATE_TILES", "0")        # the reference path: one global CAS per cell
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", "6")
+    ps.scenario_big_row(lambda: SparseMatrix(_lib_path=sim), n_cols=30000)
