@@ -701,6 +701,7 @@ __device__ __forceinline__ void tile_take_sector(const ull* sec, ull* sm, uint32
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_migrate_tiles(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region, ull* spill, uint32_t spill_cap) {
   __shared__ ull sm[4u * MIG_TILE];
+  __shared__ uint32_t s_stop;
   const uint32_t j = S.big[big_first + blockIdx.y];
   const smx_plan_t p = S.plan[j];
   const smx_row_t* e = V.dir + p.entry;
@@ -718,10 +719,23 @@ k_migrate_tiles(smx_view_t V, smx_lists_t S, uint32_t big_first, char* region, u
     for (uint32_t s = threadIdx.x; s < len; s += blockDim.x)
       tile_take_sector(ob + 4ull * ((r0 + s) & mask), sm, t0, n_new, j, V.ctl, spill, spill_cap);
     /* cells with a home in the range that linear probing pushed behind it: they can only sit in the
-     * sectors that follow as long as the sector before is full (a handful at most; one thread) */
-    if (threadIdx.x == 0 && len < n_old)
-      for (uint32_t s = len; s < n_old && sector_is_full(ob + 4ull * ((r0 + s - 1u) & mask)); ++s)
-        tile_take_sector(ob + 4ull * ((r0 + s) & mask), sm, t0, n_new, j, V.ctl, spill, spill_cap);
+     * sectors that follow as long as the sector before is full.  Usually none or a handful — but a row
+     * that grows because ops were turned away is 7/8 full and has runs of hundreds of full sectors, so
+     * the block walks them together: 32 sectors first, then 256 at a time, up to the first hole */
+    if (len < n_old) {
+      for (uint32_t base = len, step = SMX_WARP; base < n_old; base += step, step = blockDim.x) {
+        if (threadIdx.x == 0) s_stop = 0xFFFFFFFFu;
+        __syncthreads();
+        const uint32_t s = base + threadIdx.x;
+        const bool in = threadIdx.x < step && s < n_old;
+        if (in && !sector_is_full(ob + 4ull * ((r0 + s - 1u) & mask))) atomicMin(&s_stop, s);
+        __syncthreads();
+        const uint32_t stop = s_stop; /* the first sector whose predecessor has a hole: nothing of ours from there on */
+        if (in && s < stop) tile_take_sector(ob + 4ull * ((r0 + s) & mask), sm, t0, n_new, j, V.ctl, spill, spill_cap);
+        __syncthreads();
+        if (stop != 0xFFFFFFFFu) break;
+      }
+    }
     __syncthreads();
     ull* out = nb + 4ull * t0;
     for (uint32_t i = threadIdx.x; i < 4u * MIG_TILE; i += blockDim.x) out[i] = sm[i];
