@@ -83,6 +83,7 @@ struct smatrix_shard_s {
   uint32_t* stage[2][4];
   size_t stage_cap;
   uint32_t piece;
+  uint32_t taper_min; /* the last staged piece is cut into 1/2, 1/4, 1/4 if a quarter has at least this many ops */
   uint64_t stat[8]; /* SMX_SHARD_STAT_* */
 };
 
@@ -259,6 +260,8 @@ smatrix_shard_t* smatrix_b200_shard_open_arena(const char* name, int rank, int w
   sh->timeout_s = (double)rt_env("SMATRIX_SHARD_TIMEOUT", 300);
   sh->piece = rt_env("SMATRIX_SHARD_PIECE", RT_PIECE_DEFAULT);
   if (sh->piece < 1024) sh->piece = 1024;
+  sh->taper_min = rt_env("SMATRIX_SHARD_TAPER_MIN", 1u << 20);
+  if (sh->taper_min < 1) sh->taper_min = 1;
   snprintf(sh->name, sizeof sh->name, "/%s", name[0] == '/' ? name + 1 : name);
   /* rank 0 creates the segment; the others wait for it to appear and to be initialised */
   int fd = -1;
@@ -440,6 +443,20 @@ static void rt_route(smatrix_shard_t* sh, const uint32_t* d_xs, const uint32_t* 
       (uint64_t)(n - R->cnt[me][me]) * 4u * (1u + (d_ys != NULL) + (d_vs != NULL) + (want_ord != 0));
 }
 
+/* Host slices go through the device in pieces: `base` equal pieces, the last of them cut again into 1/2, 1/4,
+ * 1/4 — a call is bound by the upload, and what is not overlapped with it is the route + update of the LAST
+ * piece.  Boundary k of rank-local slice n, the same piece count on every rank: */
+static uint64_t rt_pieces(uint64_t base, int taper) { return taper ? base + 2 : base; }
+static size_t rt_piece_lo(uint64_t k, uint64_t base, int taper, size_t n) {
+  uint64_t q; /* boundary in quarters of a base piece */
+  if (!taper) q = 4 * k;
+  else if (k < base) q = 4 * k;
+  else if (k == base) q = 4 * base - 2;
+  else if (k == base + 1) q = 4 * base - 1;
+  else q = 4 * base;
+  return (size_t)((unsigned __int128)q * n / (4 * base));
+}
+
 /* ------------------------------------------------------------------------------ staging of host arrays */
 static void rt_need_stage(smatrix_shard_t* sh, size_t ops) {
   if (ops <= sh->stage_cap) return;
@@ -503,10 +520,12 @@ static void rt_write(smatrix_shard_t* sh, int op, const uint32_t* xs, const uint
   /* host slices: staged piece by piece, the upload of piece k+1 under the route + update of piece k.
    * An ordered batch is staged whole: its global order is rank-major over whole slices. */
   const uint64_t piece = ordered ? nmax : sh->piece;
-  const uint64_t pieces = (nmax + piece - 1) / piece;
+  const uint64_t base = (nmax + piece - 1) / piece;
+  const int taper = !ordered && nmax / base >= 4ull * sh->taper_min; /* quarter pieces of at least taper_min ops */
+  const uint64_t pieces = rt_pieces(base, taper);
   rt_need_stage(sh, (size_t)(piece < nmax ? piece : nmax) + 1);
   const uint32_t* src[3] = {xs, ys, has_vals ? vals : NULL};
-#define PIECE_LO(k) ((size_t)((uint64_t)(k) * n / pieces))
+#define PIECE_LO(k) rt_piece_lo((k), base, taper, n)
   for (int a = 0; a < 3 && n && !dev; a++) /* piece 0 */
     if (src[a]) smatrix_b200_memcpy_async(sh->local, sh->stage[0][a], src[a] + PIECE_LO(0), (PIECE_LO(1) - PIECE_LO(0)) * 4, 0);
   for (uint64_t k = 0; k < pieces; k++) {
@@ -665,9 +684,11 @@ static void rt_read(smatrix_shard_t* sh, int kind, const uint32_t* xs, const uin
   }
   /* host arrays: piece k+1 goes up (lane 0) and the answers of piece k-1 come down (lane 1 / 2)
    * while piece k is routed and answered */
-  const uint64_t piece = sh->piece, pieces = (nmax + piece - 1) / piece;
+  const uint64_t piece = sh->piece, base = (nmax + piece - 1) / piece;
+  const int taper = nmax / base >= 4ull * sh->taper_min;
+  const uint64_t pieces = rt_pieces(base, taper);
   rt_need_stage(sh, (size_t)(piece < nmax ? piece : nmax) + 1);
-#define PIECE_LO(k) ((size_t)((uint64_t)(k) * n / pieces))
+#define PIECE_LO(k) rt_piece_lo((k), base, taper, n)
   if (!dev && n) {
     smatrix_b200_memcpy_async(sh->local, sh->stage[0][0], xs, (PIECE_LO(1) - PIECE_LO(0)) * 4, 0);
     if (kind == RT_GET) smatrix_b200_memcpy_async(sh->local, sh->stage[0][1], ys, (PIECE_LO(1) - PIECE_LO(0)) * 4, 0);

@@ -138,7 +138,8 @@ def _rank_main(sim, name, rank, world, errors, device_arrays):
 @pytest.mark.parametrize("world", [2, 3])
 def test_c_router_ranks_as_threads(sim, world, device_arrays, monkeypatch):
     monkeypatch.setenv("SMATRIX_DIR_LOG2", "8")
-    monkeypatch.setenv("SMATRIX_SHARD_PIECE", "4096")      # host slices are staged in several pieces
+    monkeypatch.setenv("SMATRIX_SHARD_PIECE", "4096")      # host slices are staged in several pieces ...
+    monkeypatch.setenv("SMATRIX_SHARD_TAPER_MIN", "256")   # ... the last of them cut into 1/2, 1/4, 1/4
     monkeypatch.setenv("SMATRIX_SHARD_INBOX", "1024")      # the inboxes must grow on demand
     monkeypatch.setenv("SMATRIX_SHARD_TIMEOUT", "60")
     name = f"smxtest_{os.getpid()}_{world}_{int(device_arrays)}"
