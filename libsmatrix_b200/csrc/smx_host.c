@@ -37,7 +37,6 @@
 
 #define SMX_DIR_LOG_DEFAULT 20u
 #define SMX_CHUNK_DEFAULT (1u << 26) /* measured on B200: 5.17 vs 5.50 ms per 2^26 ops with 2^25 (profiles/r2_summary.md) */
-#define SMX_TAPER_MIN (1u << 21) /* host-pointer batches: the last pieces shrink down to this many ops */
 #define SMX_STAGE_MAX (1u << 23) /* host-pointer batches: piece size with the best copy/update overlap (measured) */
 #define SMX_SEG_MIN ((size_t)64 << 20)
 #define SMX_SEG_MAX ((size_t)16 << 30)
@@ -724,16 +723,15 @@ static void write_batch(smatrix_t* s, int api_op, const uint32_t* xs, const uint
     }
     CK(cudaStreamSynchronize(s->stream));
   } else {
-    /* host arrays: double-buffered upload on the copy stream overlaps the previous chunk's update.  The
-     * call is bound by the upload; what is NOT overlapped is the update of the last piece, so the last
-     * `step` ops go up in shrinking pieces (1/2, 1/4, 1/4: the exposed tail is a quarter piece) */
+    /* host arrays: double-buffered upload on the copy stream overlaps the previous chunk's update.
+     * (Shrinking the last pieces to expose less of the final update was measured and does not pay on one
+     * GPU: 10.71 vs 10.62 ms per 2^26 ops — the extra pieces cost more than the shorter tail saves.) */
     uint32_t step = s->chunk_max < s->stage_max ? s->chunk_max : s->stage_max;
     if (n < step) step = (uint32_t)n;
     ensure_stage(s, step);
     size_t off = 0;
     int b = 0;
-#define SMX_PIECE_LEN(remaining) \
-  ((uint32_t)((remaining) > step ? step : ((remaining) > SMX_TAPER_MIN ? ((remaining) + 1) / 2 : (remaining))))
+#define SMX_PIECE_LEN(remaining) ((uint32_t)((remaining) > step ? step : (remaining)))
     uint32_t len = SMX_PIECE_LEN(n - off);
     const uint32_t* src[3] = {xs, ys, vs};
     for (int a = 0; a < 3; a++)
@@ -933,10 +931,8 @@ void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, siz
     cudaStream_t sts[4] = {s->stream, s->copy_stream, s->read_stream[0], s->read_stream[1]};
     uint32_t k = 0, len = 0;
     for (size_t off = 0; off < n; off += len, k++) {
-      /* the last `step` queries go in shrinking pieces (1/2, 1/4, 1/4): the look-up and download of the
-       * final piece are the part of the call that no upload hides */
       const size_t rem = n - off;
-      len = (uint32_t)(rem > step ? step : (rem > (SMX_TAPER_MIN >> 1) ? (rem + 1) / 2 : rem));
+      len = (uint32_t)(rem > step ? step : rem);
       const uint32_t q = k & 3u;
       cudaStream_t st = sts[q];
       uint32_t* const* buf = s->stage[q >> 1];
