@@ -83,7 +83,7 @@ struct smatrix_shard_s {
   uint32_t* stage[2][4];
   size_t stage_cap;
   uint32_t piece;
-  uint32_t taper_min; /* the last staged piece is cut into 1/2, 1/4, 1/4 if a quarter has at least this many ops */
+  uint32_t taper_min; /* 0 = off; else the last staged piece is cut into 1/2, 1/4, 1/4 if a quarter has this many ops */
   uint64_t stat[8]; /* SMX_SHARD_STAT_* */
 };
 
@@ -260,8 +260,7 @@ smatrix_shard_t* smatrix_b200_shard_open_arena(const char* name, int rank, int w
   sh->timeout_s = (double)rt_env("SMATRIX_SHARD_TIMEOUT", 300);
   sh->piece = rt_env("SMATRIX_SHARD_PIECE", RT_PIECE_DEFAULT);
   if (sh->piece < 1024) sh->piece = 1024;
-  sh->taper_min = rt_env("SMATRIX_SHARD_TAPER_MIN", 1u << 20);
-  if (sh->taper_min < 1) sh->taper_min = 1;
+  sh->taper_min = rt_env("SMATRIX_SHARD_TAPER_MIN", 0); /* off: measured at N = 2, 11.8 - 12.0 vs 11.5 ms per step */
   snprintf(sh->name, sizeof sh->name, "/%s", name[0] == '/' ? name + 1 : name);
   /* rank 0 creates the segment; the others wait for it to appear and to be initialised */
   int fd = -1;
@@ -443,9 +442,10 @@ static void rt_route(smatrix_shard_t* sh, const uint32_t* d_xs, const uint32_t* 
       (uint64_t)(n - R->cnt[me][me]) * 4u * (1u + (d_ys != NULL) + (d_vs != NULL) + (want_ord != 0));
 }
 
-/* Host slices go through the device in pieces: `base` equal pieces, the last of them cut again into 1/2, 1/4,
- * 1/4 — a call is bound by the upload, and what is not overlapped with it is the route + update of the LAST
- * piece.  Boundary k of rank-local slice n, the same piece count on every rank: */
+/* Host slices go through the device in pieces: `base` equal pieces; optionally ($SMATRIX_SHARD_TAPER_MIN) the
+ * last of them is cut again into 1/2, 1/4, 1/4 so that less of the final route + update is exposed — measured:
+ * the extra pieces cost more than the shorter tail saves, so it is off by default.  Boundary k of rank-local
+ * slice n, the same piece count on every rank: */
 static uint64_t rt_pieces(uint64_t base, int taper) { return taper ? base + 2 : base; }
 static size_t rt_piece_lo(uint64_t k, uint64_t base, int taper, size_t n) {
   uint64_t q; /* boundary in quarters of a base piece */
@@ -521,7 +521,7 @@ static void rt_write(smatrix_shard_t* sh, int op, const uint32_t* xs, const uint
    * An ordered batch is staged whole: its global order is rank-major over whole slices. */
   const uint64_t piece = ordered ? nmax : sh->piece;
   const uint64_t base = (nmax + piece - 1) / piece;
-  const int taper = !ordered && nmax / base >= 4ull * sh->taper_min; /* quarter pieces of at least taper_min ops */
+  const int taper = !ordered && sh->taper_min && nmax / base >= 4ull * sh->taper_min;
   const uint64_t pieces = rt_pieces(base, taper);
   rt_need_stage(sh, (size_t)(piece < nmax ? piece : nmax) + 1);
   const uint32_t* src[3] = {xs, ys, has_vals ? vals : NULL};
@@ -685,7 +685,7 @@ static void rt_read(smatrix_shard_t* sh, int kind, const uint32_t* xs, const uin
   /* host arrays: piece k+1 goes up (lane 0) and the answers of piece k-1 come down (lane 1 / 2)
    * while piece k is routed and answered */
   const uint64_t piece = sh->piece, base = (nmax + piece - 1) / piece;
-  const int taper = nmax / base >= 4ull * sh->taper_min;
+  const int taper = sh->taper_min && nmax / base >= 4ull * sh->taper_min;
   const uint64_t pieces = rt_pieces(base, taper);
   rt_need_stage(sh, (size_t)(piece < nmax ? piece : nmax) + 1);
 #define PIECE_LO(k) rt_piece_lo((k), base, taper, n)
