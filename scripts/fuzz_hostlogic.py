@@ -1,5 +1,6 @@
 """Randomised stress of the host logic on the serial simulator (tests/hostsim): random knob
-settings (directory size, chunk size, partition threshold / slice size, pre-aggregation) x random
+settings (directory size, chunk size, partition threshold / slice size, pre-aggregation, recycling,
+directory pre-sizing, tile re-placement with tiny tiles and short spill lists, arena mode) x random
 op mixes (incr / decr / set, column-0 rates, key widths, batch sizes, *_batch_out) against the
 checker.  Not part of the test suite; run it after touching smx_host.c:   python scripts/fuzz_hostlogic.py [runs] [seed]"""
 import os, sys, time
@@ -13,6 +14,7 @@ from conftest import safe_stream
 
 U32 = np.uint32
 sim = hb.build()
+sim_small = hb.build(defines=["-DMIG_TILE_LOG=3u"], suffix="_smalltiles")   # tiny re-placement tiles: cells spill all the time
 runs = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else int(time.time())
 print("seed0", seed0, flush=True)
@@ -21,11 +23,14 @@ for run in range(runs):
     knobs = {"SMATRIX_DIR_LOG2": int(rng.integers(3, 12)), "SMATRIX_CHUNK": int(rng.choice([97, 777, 3000, 20000, 1 << 26])),
              "SMATRIX_PARTITION_MIN": int(rng.choice([16, 500, 1 << 20])), "SMATRIX_SLICE_LOG2": int(rng.integers(2, 8)),
              "SMATRIX_PARTS_LOG2": int(rng.integers(1, 9)), "SMATRIX_PREAGG": int(rng.integers(0, 2)),
-             "SMATRIX_STAGE": int(rng.choice([1024, 5000, 1 << 23]))}
+             "SMATRIX_STAGE": int(rng.choice([1024, 5000, 1 << 23])), "SMATRIX_RECYCLE": int(rng.integers(0, 2)),
+             "SMATRIX_PRESIZE": int(rng.integers(0, 2)), "SMATRIX_MIGRATE_TILES": int(rng.integers(0, 2)),
+             "SMATRIX_SPILL_CAP": int(rng.choice([1, 64, 1 << 16])), "SMATRIX_ARENA_GIB": int(rng.choice([0, 0, 1]))}
+    lib = sim_small if rng.random() < 0.5 else sim
     for k, v in knobs.items():
         os.environ[k] = str(v)
-    m, ref = SparseMatrix(_lib_path=sim), ps.checker()
-    n_rows, n_cols = int(rng.choice([3, 40, 400, 5000])), int(rng.choice([2, 30, 300, 3000]))
+    m, ref = SparseMatrix(_lib_path=lib), ps.checker()
+    n_rows, n_cols = int(rng.choice([3, 40, 400, 5000])), int(rng.choice([2, 30, 300, 3000, 40000]))
     wide = bool(rng.integers(0, 2)); col0 = float(rng.choice([0.0, 0.02, 0.3]))
     desc = f"run {run} seed {seed0 + run} knobs {knobs} rows {n_rows} cols {n_cols} wide {wide} col0 {col0}"
     try:
