@@ -540,6 +540,23 @@ def run_write_workload(job: Job, name: str):
     get_ns = m.stat("kernel_ns")
     m.set_kernel_timing(False)
     get_mops = G * world / (ms_get * 1e-3) / 1e6
+    sliced = m.stat("sliced_gets")
+    # the same queries looked up in input order (smatrix_b200_set_get_slices(0)): the A side of the slice-order A/B
+    ref_out = out.clone()
+    m.set_get_slices(0)
+    m.set_kernel_timing(True)
+    job.barrier()
+    m.timer_start()
+    for off in range(0, G, B):
+        cnt = min(B, G - off)
+        m.get_batch(qx[off:off + cnt], qy[off:off + cnt], out[off:off + cnt])
+    ms_get0 = job.max_over_ranks(m.timer_stop_ms())
+    job.barrier()
+    get0_ns = m.stat("kernel_ns")
+    m.set_kernel_timing(False)
+    m.set_get_slices(int(os.environ.get("SMATRIX_GET_SLICES", 1)))
+    get_same = bool((out == ref_out).all().item())
+    del ref_out
     hits = int((out != 0).sum().item())
     first_q = rank * G
     odd = out[1::2] if first_q % 2 == 0 else out[0::2]
@@ -591,7 +608,7 @@ def run_write_workload(job: Job, name: str):
     applied = wl.n_batches * B * world
     checks = {"value_sum": vsum_total, "ops_applied": applied, "value_sum_ok": vsum_total == applied,
               "hit_fraction_exact": (odd_hits == 0 and hits == G - G // 2) if world == 1 else (odd_hits == 0),
-              "rows_ok": rows_seen <= wl.rows_total}
+              "rows_ok": rows_seen <= wl.rows_total, "get_orders_agree": get_same}
 
     cpu = None
     if rank == 0 and not a.no_cpu:
@@ -619,8 +636,12 @@ def run_write_workload(job: Job, name: str):
                 "avg_launch_ms": upsert_ns / upsert_launches / 1e6 if upsert_ns else None,
                 "kernel_share_of_step": upsert_ns / 1e6 / ms_build if upsert_ns else None}
     get_ach = GET_BYTES * G / (get_ns * 1e-9) / 1e9 if get_ns else None
-    roofline["get"] = {"kernel": "k_get", "achieved": get_ach, "frac": (get_ach / peak) if get_ach else None,
-                       "algorithmic_bytes_per_op": GET_BYTES}
+    roofline["get"] = {"kernel": "k_get (+ k_partition_count / _scatter, k_parts_prefix, k_gather when the batch is looked up "
+                                 "in directory-slice order)", "achieved": get_ach, "frac": (get_ach / peak) if get_ach else None,
+                       "algorithmic_bytes_per_op": GET_BYTES, "sliced_fraction": sliced / G,
+                       "input_order": {"get_mops": G * world / (ms_get0 * 1e-3) / 1e6, "get_ms": ms_get0,
+                                       "achieved": GET_BYTES * G / (get0_ns * 1e-9) / 1e9 if get0_ns else None,
+                                       "same_answers": get_same}}
     if probes:
         r32 = probes["random_read_32B_per_s"]
         roofline["random_sector"] = {
@@ -629,8 +650,11 @@ def run_write_workload(job: Job, name: str):
             "incr_frac": INCR_SECTORS * (K * B / (upsert_ns * 1e-9)) / r32 if upsert_ns else None,
             "incr_frac_step": INCR_SECTORS * (K * B / (ms_build * 1e-3)) / r32,
             "get_frac": GET_SECTORS * (G / (get_ns * 1e-9)) / r32 if get_ns else None,
+            "get_frac_input_order": GET_SECTORS * (G / (get0_ns * 1e-9)) / r32 if get0_ns else None,
             "note": "achieved = ops/s x algorithmic random sectors per op (3 incr, 2 get) / measured random 32 B read rate; "
-                    "incr_frac: inside k_upsert, incr_frac_step: over the whole timed region"}
+                    "incr_frac: inside k_upsert, incr_frac_step: over the whole timed region; get_frac counts 2 sectors per query "
+                    "although the slice-ordered look-up fetches a directory entry from DRAM once per row and batch, not once "
+                    "per query (it can exceed 1); get_frac_input_order is the plain kernel"}
     if route:
         per_step = route["remote_bytes"] / max(K, 1)
         roofline["nvlink"] = {"bound": "nvlink", "peak": 900.0, "unit": "GB/s",

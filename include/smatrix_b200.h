@@ -17,7 +17,8 @@ extern "C" {
  * cudaMalloc'ing segments on demand), SMATRIX_CHUNK (ops per internal chunk, default 2^26),
  * SMATRIX_DIR_LOG2 (initial directory size), SMATRIX_PREAGG (warp pre-aggregation on/off),
  * SMATRIX_RECYCLE (free lists of vacated buckets on/off), SMATRIX_PRESIZE (distinct-row estimate
- * that sizes the directory before a chunk of new rows, on/off). */
+ * that sizes the directory before a chunk of new rows, on/off), SMATRIX_GET_SLICES (see
+ * smatrix_b200_set_get_slices). */
 smatrix_t* smatrix_b200_open(const char* fname, int device);
 /* the same with the slab arena given explicitly (bytes; 0 = segments on demand) instead of through
  * $SMATRIX_ARENA_GIB — for hosts that open several handles with different needs from several threads */
@@ -60,13 +61,21 @@ enum {
   SMX_STAT_D2H_BYTES = 21,  /* bytes copied device -> host (answers, control-block reads)      */
   SMX_STAT_BUCKET_BYTES = 22, /* slab bytes ever handed out for column buckets; / LIVE_BUCKET_BYTES = the
                                 allocator's overhead (vacated buckets wait on the free lists)   */
-  SMX_STAT_SPILLED = 23     /* cells of big rows that did not fit their shared-memory tile during a re-placement */
+  SMX_STAT_SPILLED = 23,    /* cells of big rows that did not fit their shared-memory tile during a re-placement */
+  SMX_STAT_SLICED_GETS = 24 /* point reads answered in directory-slice order so far (see set_get_slices)  */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 
 /* When on, every update/get kernel launch is bracketed by CUDA events on the launch stream and
  * the sum is reported as SMX_STAT_KERNEL_NS (used for the roofline figure). */
 void smatrix_b200_set_kernel_timing(smatrix_t* self, int on);
+
+/* Point reads on device arrays (smatrix_get_batch): 0 = look every query up in input order; 1 (default,
+ * $SMATRIX_GET_SLICES) = order a batch by directory slice first when it holds at least 2^20 queries and
+ * at least two per row of the table (the directory entries of a slice then stay in L2 and are fetched
+ * from DRAM once per row instead of once per query), answers are put back into input order; 2 = always.
+ * The answers are the same in every mode. */
+void smatrix_b200_set_get_slices(smatrix_t* self, int mode);
 
 /* Pinned host memory (cudaHostAlloc) so that host-pointer batches overlap copy and update. */
 void* smatrix_b200_host_alloc(size_t bytes);

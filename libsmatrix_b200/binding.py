@@ -51,6 +51,7 @@ PROTOTYPES = {
     "smatrix_b200_timer_stop_ms": (C.c_float, [C.c_void_p]),
     "smatrix_b200_stat": (C.c_uint64, [C.c_void_p, C.c_int]),
     "smatrix_b200_set_kernel_timing": (None, [C.c_void_p, C.c_int]),
+    "smatrix_b200_set_get_slices": (None, [C.c_void_p, C.c_int]),
     "smatrix_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "smatrix_b200_host_free": (None, [C.c_void_p]),
     "smatrix_b200_dev_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
@@ -133,7 +134,8 @@ PROTOTYPES.update({
 STAT = {"rows": 0, "nnz": 1, "dir_cap": 2, "slab_bytes": 3, "device_bytes": 4, "launches": 5,
         "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9, "ns_partition": 10, "ns_upsert": 11,
         "ns_grow_plan": 12, "ns_slab": 13, "ns_migrate": 14, "ns_dir": 15, "value_sum": 16,
-        "live_bucket_bytes": 17, "free_bytes": 18, "recycled": 19, "h2d_bytes": 20, "d2h_bytes": 21, "bucket_bytes": 22, "spilled": 23}
+        "live_bucket_bytes": 17, "free_bytes": 18, "recycled": 19, "h2d_bytes": 20, "d2h_bytes": 21, "bucket_bytes": 22, "spilled": 23,
+        "sliced_gets": 24}
 
 _cache: dict[str, C.CDLL] = {}
 

@@ -122,6 +122,9 @@ struct smatrix_s {
   uint64_t n_spilled;
   int recycle;                               /* SMATRIX_RECYCLE (default 1) */
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
+  int get_slices;                            /* SMATRIX_GET_SLICES: 0 = point reads in input order, 1 (default) = by directory slice
+                                              * when the batch revisits rows often enough, 2 = always */
+  uint64_t n_sliced_gets;                    /* queries answered through the slice-ordered path */
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
   uint64_t bucket_bytes;         /* slab bytes handed out for column buckets (fresh, not recycled) */
@@ -566,6 +569,26 @@ static void maybe_shrink_dir(smatrix_t* s) {
   if (fit * 4 <= s->dir_cap) resize_dir(s, fit);
 }
 
+/* directory slices of a batch: 2^parts_log of them, slice(x) = (mix_row(x) & (dir_cap - 1)) >> shift */
+static void slice_geometry(const smatrix_t* s, uint32_t* parts_log, uint32_t* shift) {
+  uint32_t dir_log = 0;
+  while ((1ull << dir_log) < s->dir_cap) dir_log++;
+  uint32_t pl = dir_log > s->slice_log ? dir_log - s->slice_log : 0; /* default: slices of 2^17 entries = 8 MiB */
+  if (pl > s->parts_log_max) pl = s->parts_log_max;
+  *parts_log = pl;
+  *shift = dir_log - pl;
+}
+/* the four arrays a slice-ordered batch lives in (x, y, values / answers, index / position) */
+static void ensure_parts(smatrix_t* s, uint32_t n) {
+  if (n <= s->part_cap) return;
+  if (s->part_cap) {
+    CK(cudaStreamSynchronize(s->stream));
+    for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
+  }
+  s->part_cap = s->list_cap > n ? s->list_cap : n;
+  for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)scratch_alloc(s, (size_t)s->part_cap * 4);
+}
+
 /* Reorder a chunk so that ops on rows of the same directory slice are adjacent: the slice of the
  * directory (a few MB) then stays in L2 while its ops are applied, and a row header costs one
  * DRAM read + one write-back per chunk instead of one per op.  Ops on column 0 go to parts of their
@@ -575,19 +598,10 @@ static void maybe_shrink_dir(smatrix_t* s) {
  * Returns 1 if the chunk was partitioned; *n_main = number of ops that are not on column 0. */
 static int partition_chunk(smatrix_t* s, smx_ops_t* ops, int api_op, uint32_t* n_main) {
   const uint32_t n = ops->n;
-  uint32_t dir_log = 0;
-  while ((1ull << dir_log) < s->dir_cap) dir_log++;
-  uint32_t parts_log = dir_log > s->slice_log ? dir_log - s->slice_log : 0; /* default: slices of 2^17 entries = 8 MiB */
-  if (parts_log > s->parts_log_max) parts_log = s->parts_log_max;
-  const uint32_t slices = 1u << parts_log, parts = 2u * slices, shift = dir_log - parts_log;
-  if (n > s->part_cap) {
-    if (s->part_cap) {
-      CK(cudaStreamSynchronize(s->stream));
-      for (int a = 0; a < 4; a++) scratch_free(s, s->part[a]);
-    }
-    s->part_cap = s->list_cap > n ? s->list_cap : n;
-    for (int a = 0; a < 4; a++) s->part[a] = (uint32_t*)scratch_alloc(s, (size_t)s->part_cap * 4);
-  }
+  uint32_t parts_log, shift;
+  slice_geometry(s, &parts_log, &shift);
+  const uint32_t slices = 1u << parts_log, parts = 2u * slices;
+  ensure_parts(s, n);
   ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
   unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
@@ -901,6 +915,43 @@ void smatrix_b200_apply_ordered_out(smatrix_t* s, int op, const uint32_t* d_xs, 
 /* ------------------------------------------------------------------------------ read path */
 #define READ_STEP (1u << 26)
 
+/* Point reads by directory slice.  A query costs two dependent random DRAM touches (directory entry,
+ * bucket sector) and that, not bandwidth, bounds k_get.  When a batch asks for the same rows several
+ * times — q queries over R rows touch only R (1 - e^(-q/R)) distinct entries — ordering the queries
+ * by directory slice (the write path's partition, without the column-0 parts) keeps a slice's few MB
+ * of entries in L2 while its queries run, so the directory touch reaches DRAM once per ROW instead
+ * of once per QUERY.  Answers come out in slice order and k_gather puts them back through the
+ * inverse permutation the scatter leaves; a tile's queries land in one contiguous run per slice, so
+ * that gather reads whole sectors.  The cursors are prefixed on the device (k_parts_prefix): nothing
+ * between the five launches waits for the host.  Costs one streaming pass each way (~28 B/query),
+ * so it only pays when rows repeat: at q/R = 1 saved touches and added passes break even. */
+static int get_slices_pay(const smatrix_t* s, uint32_t n) {
+  if (s->get_slices == 0 || n < 2) return 0;
+  uint32_t parts_log, shift;
+  slice_geometry(s, &parts_log, &shift);
+  if (parts_log == 0) return 0; /* the whole directory is one slice */
+  if (s->get_slices >= 2) return 1;
+  return n >= s->part_min && (uint64_t)n >= 2 * s->h_ctl->dir_used;
+}
+static void get_sliced(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys, uint32_t n, uint32_t* d_out) {
+  uint32_t parts_log, shift;
+  slice_geometry(s, &parts_log, &shift);
+  const uint32_t slices = 1u << parts_log, mask = (uint32_t)(s->dir_cap - 1);
+  ensure_parts(s, n);
+  ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
+  unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
+  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
+  CK(cudaMemsetAsync(d_counts, 0, slices * 8, s->stream));
+  smx_launch_partition_count(s->stream, d_xs, NULL, n, slices, mask, shift, 0, d_counts);
+  smx_launch_parts_prefix(s->stream, d_counts, slices, d_cursors);
+  smx_launch_partition_scatter(s->stream, d_xs, d_ys, NULL, n, slices, mask, shift, 0, d_cursors, s->part[0],
+                               s->part[1], NULL, NULL, NULL, s->part[3], NULL, 0);
+  smx_launch_get(s->stream, view_of(s), s->part[0], s->part[1], n, s->part[2]);
+  smx_launch_gather(s->stream, d_out, s->part[2], s->part[3], n);
+  s->n_launches += 5;
+  s->n_sliced_gets += n;
+}
+
 void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, size_t n,
                        uint32_t* out) {
   if (n == 0) return;
@@ -912,9 +963,13 @@ void smatrix_get_batch(smatrix_t* s, const uint32_t* xs, const uint32_t* ys, siz
     for (size_t off = 0; off < n; off += READ_STEP) {
       const uint32_t len = (uint32_t)((n - off < READ_STEP) ? n - off : READ_STEP);
       timed_begin(s);
-      smx_launch_get(s->stream, view_of(s), xs + off, ys + off, len, out + off);
+      if (get_slices_pay(s, len)) {
+        get_sliced(s, xs + off, ys + off, len, out + off);
+      } else {
+        smx_launch_get(s->stream, view_of(s), xs + off, ys + off, len, out + off);
+        s->n_launches++;
+      }
       timed_end(s);
-      s->n_launches++;
       CK(cudaStreamSynchronize(s->stream));
       timed_collect(s);
     }
@@ -1474,6 +1529,7 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   s->presize = (int)env_u32("SMATRIX_PRESIZE", 1);
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;
+  s->get_slices = (int)env_u32("SMATRIX_GET_SLICES", 1);
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
@@ -1599,6 +1655,12 @@ void smatrix_b200_set_kernel_timing(smatrix_t* s, int on) {
   leave(s);
 }
 
+void smatrix_b200_set_get_slices(smatrix_t* s, int mode) {
+  enter(s);
+  s->get_slices = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  leave(s);
+}
+
 uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
   uint64_t r = 0;
   enter(s);
@@ -1645,6 +1707,7 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
     case SMX_STAT_RECYCLED: r = s->n_recycled; break;
     case SMX_STAT_BUCKET_BYTES: r = s->bucket_bytes; break;
     case SMX_STAT_SPILLED: r = s->n_spilled; break;
+    case SMX_STAT_SLICED_GETS: r = s->n_sliced_gets; break;
     case SMX_STAT_H2D_BYTES: r = s->h2d_bytes; break;
     case SMX_STAT_D2H_BYTES: r = s->d2h_bytes; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;

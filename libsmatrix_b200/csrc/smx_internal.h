@@ -223,6 +223,8 @@ void smx_launch_partition_scatter(smx_stream_t stream, const uint32_t* xs, const
                                   const unsigned long long* dst_tab /* nullable, device: [5][world] =
                                      per-part x / y / v / src output bases + routed-position bases */,
                                   uint32_t src_bias /* added to every osrc value */);
+void smx_launch_parts_prefix(smx_stream_t stream, const unsigned long long* counts, uint32_t parts,
+                             unsigned long long* cursors /* [parts] = exclusive prefix of counts */);
 void smx_launch_gather(smx_stream_t stream, uint32_t* out, const uint32_t* vals, const uint32_t* pos,
                        uint32_t n);
 void smx_launch_route_offsets(smx_stream_t stream, const uint64_t* offs, const uint32_t* pos, uint32_t n,

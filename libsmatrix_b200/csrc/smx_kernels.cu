@@ -1637,6 +1637,17 @@ k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t w
   for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
     if (hist[k]) atomicAdd(&counts[k], (ull)hist[k]);
 }
+/* cursors[p] = first output index of part p = exclusive prefix of counts (<= 256 parts: one thread;
+ * the read path uses it so that no host round trip sits between the count and the scatter) */
+__global__ void k_parts_prefix(const ull* counts, uint32_t parts, ull* cursors) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ull at = 0ull;
+    for (uint32_t p = 0; p < parts; ++p) {
+      cursors[p] = at;
+      at += counts[p];
+    }
+  }
+}
 /* Tiled partition: a block stages a tile of ops in shared memory sorted by part, reserves one
  * contiguous range per part with a single global atomic, and writes whole runs — so every
  * (tile, part) run reaches L2 as full sectors no matter how many parts there are.  Order inside a
@@ -2184,6 +2195,10 @@ extern "C" void smx_launch_partition_scatter(smx_stream_t st, const uint32_t* xs
   else if (pos) SMX_SCATTER(false, true)
   else SMX_SCATTER(false, false)
 #undef SMX_SCATTER
+}
+extern "C" void smx_launch_parts_prefix(smx_stream_t st, const unsigned long long* counts, uint32_t parts,
+                                        unsigned long long* cursors) {
+  SMX_LAUNCH(k_parts_prefix, 1, 32, st, (const ull*)counts, parts, (ull*)cursors);
 }
 extern "C" void smx_launch_gather(smx_stream_t st, uint32_t* out, const uint32_t* vals,
                                   const uint32_t* pos, uint32_t n) {

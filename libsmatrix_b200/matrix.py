@@ -296,6 +296,10 @@ class SparseMatrix:
     def set_kernel_timing(self, on: bool):
         self._lib.smatrix_b200_set_kernel_timing(self._handle(), 1 if on else 0)
 
+    def set_get_slices(self, mode: int):
+        """0: point reads in input order; 1: by directory slice when rows repeat (default); 2: always."""
+        self._lib.smatrix_b200_set_get_slices(self._handle(), int(mode))
+
     @property
     def device(self) -> int:
         return int(self._lib.smatrix_b200_device(self._handle()))

@@ -551,7 +551,7 @@ class TorchShardedSparseMatrix:
         return self.local.stat(name)
 
     _LOCAL_CONTROLS = frozenset((
-        "timer_start", "timer_stop_ms", "set_kernel_timing", "sync", "gen_c2_ops", "gen_c2_queries",
+        "timer_start", "timer_stop_ms", "set_kernel_timing", "set_get_slices", "sync", "gen_c2_ops", "gen_c2_queries",
         "gen_c3_ops", "gen_c3_queries", "gen_c4_lens", "gen_c4_ops", "probe_random_read",
         "probe_random_atomic", "dev_alloc", "dev_free", "memcpy", "device", "stream"))
 

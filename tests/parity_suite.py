@@ -482,3 +482,50 @@ def scenario_recycling_churn(make, waves: int = 6, rows_per_wave: int = 400):
     assert m.stat("recycled") > 0, "younger rows should have reused buckets vacated by older ones"
     assert m.stat("free_bytes") >= 0 and m.stat("bucket_bytes") >= m.stat("live_bucket_bytes")
     m.close(); ref.close()
+
+
+def scenario_sliced_gets(make, n_rows: int = 3000, n_cols: int = 90, n_ops: int = 60000,
+                         sizes=(1, 2, 7, 8, 9, 2047, 2048, 2049, 50001)):
+    """Point reads on DEVICE arrays in the three modes of smatrix_b200_set_get_slices (input order /
+    by directory slice when rows repeat / always by slice): the answers must be those of smatrix_get
+    (src/smatrix.c:174-185) in INPUT order whatever order the look-ups ran in — hits, missing columns,
+    missing rows, column 0, duplicates; batch sizes around the partition tile (2048 queries on the GPU,
+    8 on the simulator)."""
+    from libsmatrix_b200.matrix import DevPtr
+    rng = np.random.default_rng(99)
+    m, ref = make(), checker()
+    xs = (rng.integers(0, n_rows, n_ops).astype(U32) * U32(2654435761))
+    ys = rng.integers(0, n_cols, n_ops).astype(U32)                    # column 0 included
+    vs = rng.integers(1, 2**32, n_ops, dtype=np.uint64).astype(U32)
+    apply_both(m, ref, "incr", xs, ys, vs)
+    import os
+    can_slice = m.stat("dir_cap") > (1 << int(os.environ.get("SMATRIX_SLICE_LOG2", 17)))   # more than one slice
+    part_min = int(os.environ.get("SMATRIX_PARTITION_MIN", 1 << 20))
+
+    def up(a):
+        p = m.dev_alloc(max(a.nbytes, 8))
+        if a.nbytes:
+            m.memcpy(p, a.ctypes.data, a.nbytes)
+        return p
+
+    for n in sizes:
+        pick = rng.integers(0, n_ops, n)
+        qx, qy = xs[pick].copy(), ys[pick].copy()
+        qy[1::3] += U32(n_cols)                                        # columns nobody wrote
+        qx[2::7] += U32(1)                                             # rows nobody wrote
+        want = ref.get_many(qx, qy)
+        dx, dy, do = up(qx), up(qy), m.dev_alloc(4 * n + 8)
+        for mode, sliced in ((0, False), (2, can_slice), (1, can_slice and n >= 2 * m.stat("rows") and n >= part_min)):
+            m.set_get_slices(mode)
+            before = m.stat("sliced_gets")
+            m._lib.smatrix_b200_memset0(m._handle(), do, 4 * n)
+            m.get_batch(DevPtr(dx, n), DevPtr(dy, n), DevPtr(do, n))
+            got = np.empty(n, U32)
+            m.memcpy(got.ctypes.data, do, 4 * n)
+            assert (got == want).all(), f"mode {mode}, n {n}: {int((got != want).sum())} mismatches"
+            took = m.stat("sliced_gets") - before
+            assert took == (n if sliced and n >= 2 else 0), (mode, n, took)
+        for p in (dx, dy, do):
+            m.dev_free(p)
+    m.set_get_slices(1)
+    m.close(); ref.close()

@@ -182,6 +182,19 @@ def test_device_pointer_batches():
     m.close(); ref.close()
 
 
+def test_sliced_gets(make):
+    """smatrix_get_batch on device arrays: input order, by directory slice when rows repeat, always by slice."""
+    ps.scenario_sliced_gets(make)
+
+
+def test_sliced_gets_many_rows(monkeypatch):
+    """The production geometry: a directory of 2^21 entries = 16 slices of 2^17, 2^22 queries over 400 K rows
+    (mode 1 picks the slice order by itself), against the reference."""
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", "21")
+    ps.scenario_sliced_gets(lambda: SparseMatrix(), n_rows=400_000, n_cols=30, n_ops=3_000_000,
+                            sizes=(1 << 20, (1 << 22) + 5))
+
+
 def test_c2_stream_device_generator_matches_host():
     import torch
     m = SparseMatrix()

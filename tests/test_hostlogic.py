@@ -105,6 +105,12 @@ def test_batch_out(make):
     ps.scenario_batch_out(make, n=6000)
 
 
+def test_sliced_gets(make, monkeypatch):
+    monkeypatch.setenv("SMATRIX_PARTITION_MIN", "16")       # mode 1 needs >= this many queries ...
+    monkeypatch.setenv("SMATRIX_SLICE_LOG2", "3")           # ... and more than one directory slice
+    ps.scenario_sliced_gets(make, n_rows=300, n_cols=40, n_ops=6000, sizes=(1, 2, 7, 8, 9, 15, 16, 17, 599, 600, 5001))
+
+
 def test_cf_read_side(make):
     ps.scenario_cf_read_side(make, n_baskets=300, n_items=80)
 
