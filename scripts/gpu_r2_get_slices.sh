@@ -11,6 +11,6 @@ print(' get', d['roofline']['get']); print(' rs', d['roofline'].get('random_sect
 print(' e2e',d['e2e']['value'],d['e2e']['get_mops'],d['e2e']['h2d_ceiling']['frac'])
 PY
 M=dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum,launch__grid_size
-timeout 400 ncu --metrics $M --clock-control none -k regex:"k_get|k_gather|k_parts_prefix|k_partition_scatter|k_row_counts|k_rowlen" --launch-skip 30 --csv --log-file gpurun_out/r2g_dram_traffic_c2_reads.csv \
+timeout 200 ncu --metrics $M --clock-control none -k regex:"k_get|k_gather|k_parts_prefix|k_partition_scatter|k_row_counts|k_rowlen" --launch-skip 30 --launch-count 56 --csv --log-file gpurun_out/r2g_dram_traffic_c2_reads.csv \
   python bench.py --steps 4 --warmup 1 --no-e2e --no-cpu --no-probes --no-parity > /dev/null 2> gpurun_out/r2g_traffic_c2_reads.err; echo "c2 read traffic rc=$?"
 grep -c k_get gpurun_out/r2g_dram_traffic_c2_reads.csv
