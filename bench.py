@@ -541,21 +541,30 @@ def run_write_workload(job: Job, name: str):
     m.set_kernel_timing(False)
     get_mops = G * world / (ms_get * 1e-3) / 1e6
     sliced = m.stat("sliced_gets")
-    # the same queries looked up in input order (smatrix_b200_set_get_slices(0)): the A side of the slice-order A/B
+    # the same queries looked up in input order (smatrix_b200_set_get_slices(0)): the A side of the slice-order A/B;
+    # $SMX_BENCH_GET_VARIANTS = further set_get_slices() values to time on the same table (measurement switches)
     ref_out = out.clone()
-    m.set_get_slices(0)
-    m.set_kernel_timing(True)
-    job.barrier()
-    m.timer_start()
-    for off in range(0, G, B):
-        cnt = min(B, G - off)
-        m.get_batch(qx[off:off + cnt], qy[off:off + cnt], out[off:off + cnt])
-    ms_get0 = job.max_over_ranks(m.timer_stop_ms())
-    job.barrier()
-    get0_ns = m.stat("kernel_ns")
-    m.set_kernel_timing(False)
-    m.set_get_slices(int(os.environ.get("SMATRIX_GET_SLICES", 1)))
-    get_same = bool((out == ref_out).all().item())
+    get_variants = {}
+    get_same = True
+    for variant in [0] + [int(v, 0) for v in os.environ.get("SMX_BENCH_GET_VARIANTS", "").split(",") if v]:
+        m.set_get_slices(variant)
+        out.zero_()
+        m.set_kernel_timing(True)
+        job.barrier()
+        m.timer_start()
+        for off in range(0, G, B):
+            cnt = min(B, G - off)
+            m.get_batch(qx[off:off + cnt], qy[off:off + cnt], out[off:off + cnt])
+        ms_v = job.max_over_ranks(m.timer_stop_ms())
+        job.barrier()
+        ns_v = m.stat("kernel_ns")
+        m.set_kernel_timing(False)
+        same = bool((out == ref_out).all().item())
+        get_same = get_same and same
+        get_variants[variant] = {"get_mops": G * world / (ms_v * 1e-3) / 1e6, "get_ms": ms_v, "kernels_ms": ns_v / 1e6,
+                                 "same_answers": same}
+    ms_get0, get0_ns = get_variants[0]["get_ms"], get_variants[0]["kernels_ms"] * 1e6
+    m.set_get_slices(int(os.environ.get("SMATRIX_GET_SLICES", "1"), 0))
     del ref_out
     hits = int((out != 0).sum().item())
     first_q = rank * G
@@ -641,7 +650,9 @@ def run_write_workload(job: Job, name: str):
                        "algorithmic_bytes_per_op": GET_BYTES, "sliced_fraction": sliced / G,
                        "input_order": {"get_mops": G * world / (ms_get0 * 1e-3) / 1e6, "get_ms": ms_get0,
                                        "achieved": GET_BYTES * G / (get0_ns * 1e-9) / 1e9 if get0_ns else None,
-                                       "same_answers": get_same}}
+                                       "same_answers": get_variants[0]["same_answers"]}}
+    if len(get_variants) > 1:
+        roofline["get"]["variants"] = get_variants
     if probes:
         r32 = probes["random_read_32B_per_s"]
         roofline["random_sector"] = {

@@ -124,6 +124,7 @@ struct smatrix_s {
   int presize;                               /* SMATRIX_PRESIZE (default 1): distinct-row estimate before a chunk of new rows */
   int get_slices;                            /* SMATRIX_GET_SLICES: 0 = point reads in input order, 1 (default) = by directory slice
                                               * when the batch revisits rows often enough, 2 = always */
+  int get_flags;                             /* measurement switches of the slice-ordered look-up (SMX_GET_*) */
   uint64_t n_sliced_gets;                    /* queries answered through the slice-ordered path */
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
@@ -925,17 +926,32 @@ void smatrix_b200_apply_ordered_out(smatrix_t* s, int op, const uint32_t* d_xs, 
  * that gather reads whole sectors.  The cursors are prefixed on the device (k_parts_prefix): nothing
  * between the five launches waits for the host.  Costs one streaming pass each way (~28 B/query),
  * so it only pays when rows repeat: at q/R = 1 saved touches and added passes break even. */
+enum {
+  SMX_GET_KEEP = 4,    /* bucket sectors with the ordinary L2 priority (default: evict-first, they are read once) */
+  SMX_GET_NARROW = 8,  /* the write path's slice count (<= 2^SMATRIX_PARTS_LOG2) instead of up to 256 slices */
+  SMX_GET_STRIDE = 16  /* look-ups by the resident-grid kernel of the input-order path (blocks drift across slices) */
+};
+static void get_geometry(const smatrix_t* s, uint32_t* parts_log, uint32_t* shift) {
+  slice_geometry(s, parts_log, shift);
+  if (!(s->get_flags & SMX_GET_NARROW)) { /* no column-0 parts here, so all 256 parts can be slices */
+    const uint32_t dir_log = *parts_log + *shift;
+    uint32_t pl = dir_log > s->slice_log ? dir_log - s->slice_log : 0;
+    if (pl > 8) pl = 8;
+    *parts_log = pl;
+    *shift = dir_log - pl;
+  }
+}
 static int get_slices_pay(const smatrix_t* s, uint32_t n) {
   if (s->get_slices == 0 || n < 2) return 0;
   uint32_t parts_log, shift;
-  slice_geometry(s, &parts_log, &shift);
+  get_geometry(s, &parts_log, &shift);
   if (parts_log == 0) return 0; /* the whole directory is one slice */
   if (s->get_slices >= 2) return 1;
   return n >= s->part_min && (uint64_t)n >= 2 * s->h_ctl->dir_used;
 }
 static void get_sliced(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys, uint32_t n, uint32_t* d_out) {
   uint32_t parts_log, shift;
-  slice_geometry(s, &parts_log, &shift);
+  get_geometry(s, &parts_log, &shift);
   const uint32_t slices = 1u << parts_log, mask = (uint32_t)(s->dir_cap - 1);
   ensure_parts(s, n);
   ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
@@ -946,7 +962,8 @@ static void get_sliced(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
   smx_launch_parts_prefix(s->stream, d_counts, slices, d_cursors);
   smx_launch_partition_scatter(s->stream, d_xs, d_ys, NULL, n, slices, mask, shift, 0, d_cursors, s->part[0],
                                s->part[1], NULL, NULL, NULL, s->part[3], NULL, 0);
-  smx_launch_get(s->stream, view_of(s), s->part[0], s->part[1], n, s->part[2]);
+  if (s->get_flags & SMX_GET_STRIDE) smx_launch_get(s->stream, view_of(s), s->part[0], s->part[1], n, s->part[2]);
+  else smx_launch_get_tiled(s->stream, view_of(s), s->part[0], s->part[1], n, s->part[2], !(s->get_flags & SMX_GET_KEEP));
   smx_launch_gather(s->stream, d_out, s->part[2], s->part[3], n);
   s->n_launches += 5;
   s->n_sliced_gets += n;
@@ -1530,6 +1547,8 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;
   s->get_slices = (int)env_u32("SMATRIX_GET_SLICES", 1);
+  s->get_flags = s->get_slices & (SMX_GET_KEEP | SMX_GET_NARROW | SMX_GET_STRIDE);
+  s->get_slices = (s->get_slices & 3) > 2 ? 2 : (s->get_slices & 3);
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
@@ -1657,7 +1676,9 @@ void smatrix_b200_set_kernel_timing(smatrix_t* s, int on) {
 
 void smatrix_b200_set_get_slices(smatrix_t* s, int mode) {
   enter(s);
-  s->get_slices = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  if (mode < 0) mode = 0;
+  s->get_slices = (mode & 3) > 2 ? 2 : (mode & 3);
+  s->get_flags = mode & (SMX_GET_KEEP | SMX_GET_NARROW | SMX_GET_STRIDE);
   leave(s);
 }
 

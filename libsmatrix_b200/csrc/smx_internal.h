@@ -160,6 +160,10 @@ size_t smx_batch_out_sort_bytes(uint32_t n);
 void smx_launch_batch_out(smx_stream_t stream, smx_view_t v, smx_ops_t ops, int op, uint32_t* out,
                           uint64_t* addrs_a, uint64_t* addrs_b, uint32_t* idx_a, uint32_t* idx_b,
                           uint64_t* seg, uint64_t* tile_agg, void* sort_tmp, size_t sort_bytes);
+/* slice-ordered queries: one block per 4 x 256 consecutive queries, dispatched in order; once != 0: bucket
+ * sectors are loaded evict-first */
+void smx_launch_get_tiled(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
+                          uint32_t n, uint32_t* out, int once);
 void smx_launch_get(smx_stream_t stream, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
                     uint32_t n, uint32_t* out);
 void smx_launch_rowlen(smx_stream_t stream, smx_view_t v, const uint32_t* xs, uint32_t n,

@@ -113,6 +113,18 @@ __device__ __forceinline__ void ld_sector_t(const void* p, ull c[4]) {
 #endif
 }
 __device__ __forceinline__ void ld_sector(const void* p, ull c[4]) { ld_sector_t<SMX_CELL_FETCH64 != 0>(p, c); }
+/* the same sector for a reader that will not come back to it: no L1 allocation, first in line for
+ * eviction from L2 (SASS LDG.E.NA.EFL2.LTC64B.256).  The slice-ordered point reads use it for bucket
+ * sectors, so that the single-use bucket lines do not push the slice's directory entries — which are
+ * asked for again and again while the slice's queries run — out of L2. */
+__device__ __forceinline__ void ld_sector_once(const void* p, ull c[4]) {
+#ifdef SMX_HOSTSIM
+  memcpy(c, p, 32);
+#else
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(c[0]), "=l"(c[1]), "=l"(c[2]), "=l"(c[3]) : "l"(p) : "memory");
+#endif
+}
 __device__ __forceinline__ void ld_hsector(const void* p, ull c[4]) { ld_sector_t<SMX_HDR_FETCH64 != 0>(p, c); }
 
 struct Hdr {
@@ -284,6 +296,7 @@ __device__ __forceinline__ int slot_upsert(smx_row_t* e, const Hdr& h, uint32_t 
 }
 
 /* read-only probe: value of column y (y != 0) or 0 */
+template <bool ONCE = false>
 __device__ __forceinline__ uint32_t slot_find(const smx_row_t* e, const Hdr& h, uint32_t y,
                                               uint32_t** where) {
   const uint32_t caplog = h.meta & SMX_META_CAPLOG;
@@ -293,7 +306,8 @@ __device__ __forceinline__ uint32_t slot_find(const smx_row_t* e, const Hdr& h, 
   for (uint32_t probe = 0; probe < nsec; ++probe, s = (s + 1u) & (nsec - 1u)) {
     const ull* sec = base + 4ull * s;
     ull c[4];
-    ld_sector(sec, c);
+    if (ONCE) ld_sector_once(sec, c);
+    else ld_sector(sec, c);
     bool hole = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -960,17 +974,39 @@ __global__ void __launch_bounds__(SMX_BLOCK) k_fill_out(smx_ops_t O, uint32_t* o
 /* ------------------------------------------------------------------------------------------
  * K4 / K5: point reads
  * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t get_one(const smx_view_t& V, uint32_t x, uint32_t y, bool once) {
+  smx_row_t* e;
+  Hdr h;
+  if (dir_find(V, x, false, &e, &h) != DIR_FOUND) return 0u;
+  if (y == 0u) return h.c0;
+  return once ? slot_find<true>(e, h, y, nullptr) : slot_find<false>(e, h, y, nullptr);
+}
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_get(smx_view_t V, const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t* out) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    smx_row_t* e;
-    Hdr h;
-    uint32_t val = 0u;
-    if (dir_find(V, xs[i], false, &e, &h) == DIR_FOUND) {
-      const uint32_t y = ys[i];
-      val = (y == 0u) ? h.c0 : slot_find(e, h, y, nullptr);
-    }
-    out[i] = val;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = get_one(V, xs[i], ys[i], false);
+}
+/* The look-up of SLICE-ORDERED queries.  Not a resident grid with a stride loop: blocks of a resident
+ * grid drift apart (an SM that is a few per cent faster is several slices ahead after the ~200
+ * iterations of a 2^26-query batch), and then the directory entries of many slices compete for L2
+ * at once.  One block per GET_TILE consecutive queries, dispatched in order as earlier blocks retire
+ * (like k_upsert), keeps all resident blocks inside a window of ~1 M queries = one or two slices. */
+#define GET_TILE_ITEMS 4
+template <bool ONCE>
+__global__ void __launch_bounds__(SMX_BLOCK, 8)
+k_get_tiled(smx_view_t V, const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t* out) {
+  const ull base = (ull)blockIdx.x * (GET_TILE_ITEMS * SMX_BLOCK);
+  uint32_t x[GET_TILE_ITEMS], y[GET_TILE_ITEMS];
+#pragma unroll
+  for (int k = 0; k < GET_TILE_ITEMS; ++k) {
+    const ull i = base + (ull)k * SMX_BLOCK + threadIdx.x;
+    x[k] = i < n ? xs[i] : 0u;
+    y[k] = i < n ? ys[i] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < GET_TILE_ITEMS; ++k) {
+    const ull i = base + (ull)k * SMX_BLOCK + threadIdx.x;
+    if (i < n) out[i] = get_one(V, x[k], y[k], ONCE);
   }
 }
 
@@ -2015,6 +2051,18 @@ extern "C" void smx_launch_batch_out(smx_stream_t st, smx_view_t v, smx_ops_t op
   SMX_LAUNCH(k_out_write, grid_for(n), SMX_BLOCK, st, ops, negate, s_addr, s_idx, (const ull*)seg, out);
 }
 
+extern "C" void smx_launch_get_tiled(smx_stream_t st, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
+                                     uint32_t n, uint32_t* out, int once) {
+  if (!n) return;
+  const uint32_t grid = (uint32_t)(((ull)n + GET_TILE_ITEMS * SMX_BLOCK - 1) / (GET_TILE_ITEMS * SMX_BLOCK));
+  if (once) {
+    auto k = k_get_tiled<true>;
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, v, xs, ys, n, out);
+  } else {
+    auto k = k_get_tiled<false>;
+    SMX_LAUNCH(k, grid, SMX_BLOCK, st, v, xs, ys, n, out);
+  }
+}
 extern "C" void smx_launch_get(smx_stream_t st, smx_view_t v, const uint32_t* xs, const uint32_t* ys,
                                uint32_t n, uint32_t* out) {
   if (!n) return;

@@ -2,7 +2,7 @@
 # point reads in directory-slice order: GPU parity of the three modes, the c2 line (carries the input-order A side),
 # and the DRAM traffic of the read kernels on the full-scale table
 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "sliced or device_pointer" > gpurun_out/r2g_pytest_sliced.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2g_pytest_sliced.log
-python bench.py --steps 20 --warmup 3 > gpurun_out/r2g_bench_n1_steps20.json 2> gpurun_out/r2g_bench_n1_steps20.err; echo "c2/20 rc=$?"; tail -3 gpurun_out/r2g_bench_n1_steps20.err
+SMX_BENCH_GET_VARIANTS=6,10,14,18,26 python bench.py --steps 20 --warmup 3 > gpurun_out/r2g_bench_n1_steps20.json 2> gpurun_out/r2g_bench_n1_steps20.err; echo "c2/20 rc=$?"; tail -3 gpurun_out/r2g_bench_n1_steps20.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r2g_bench_n1_steps20.json'))

@@ -515,7 +515,11 @@ def scenario_sliced_gets(make, n_rows: int = 3000, n_cols: int = 90, n_ops: int 
         qx[2::7] += U32(1)                                             # rows nobody wrote
         want = ref.get_many(qx, qy)
         dx, dy, do = up(qx), up(qy), m.dev_alloc(4 * n + 8)
-        for mode, sliced in ((0, False), (2, can_slice), (1, can_slice and n >= 2 * m.stat("rows") and n >= part_min)):
+        auto = can_slice and n >= 2 * m.stat("rows") and n >= part_min
+        # + the measurement switches: 4 = ordinary L2 priority for bucket sectors, 8 = the write path's slice
+        # count, 16 = resident-grid look-up kernel
+        for mode, sliced in ((0, False), (2, can_slice), (1, auto), (2 | 4, can_slice), (2 | 8, can_slice),
+                             (2 | 16, can_slice), (1 | 4 | 8 | 16, auto)):
             m.set_get_slices(mode)
             before = m.stat("sliced_gets")
             m._lib.smatrix_b200_memset0(m._handle(), do, 4 * n)
