@@ -564,6 +564,21 @@ def run_write_workload(job: Job, name: str):
         get_variants[variant] = {"get_mops": G * world / (ms_v * 1e-3) / 1e6, "get_ms": ms_v, "kernels_ms": ns_v / 1e6,
                                  "same_answers": same}
     ms_get0, get0_ns = get_variants[0]["get_ms"], get_variants[0]["kernels_ms"] * 1e6
+    # $SMX_BENCH_GET_BATCHES: 2^27 of the queries again in batches of these sizes, input order (0) vs always by slice (2):
+    # where the slice order starts to pay as a function of queries per call / rows in the table
+    get_sweep = {}
+    for bs in [int(v, 0) for v in os.environ.get("SMX_BENCH_GET_BATCHES", "").split(",") if v]:
+        tot = min(G, 1 << 27)
+        for mode in (0, 2):
+            m.set_get_slices(mode)
+            job.barrier()
+            m.timer_start()
+            for off in range(0, tot, bs):
+                cnt = min(bs, tot - off)
+                m.get_batch(qx[off:off + cnt], qy[off:off + cnt], out[off:off + cnt])
+            ms_v = job.max_over_ranks(m.timer_stop_ms())
+            get_sweep[f"{bs}:{mode}"] = round(tot * world / (ms_v * 1e-3) / 1e6, 1)
+        get_same = get_same and bool((out[:tot] == ref_out[:tot]).all().item())
     m.set_get_slices(int(os.environ.get("SMATRIX_GET_SLICES", "1"), 0))
     del ref_out
     hits = int((out != 0).sum().item())
@@ -653,6 +668,8 @@ def run_write_workload(job: Job, name: str):
                                        "same_answers": get_variants[0]["same_answers"]}}
     if len(get_variants) > 1:
         roofline["get"]["variants"] = get_variants
+    if get_sweep:
+        roofline["get"]["batch_sweep_mops"] = get_sweep
     if probes:
         r32 = probes["random_read_32B_per_s"]
         roofline["random_sector"] = {

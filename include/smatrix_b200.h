@@ -62,7 +62,8 @@ enum {
   SMX_STAT_BUCKET_BYTES = 22, /* slab bytes ever handed out for column buckets; / LIVE_BUCKET_BYTES = the
                                 allocator's overhead (vacated buckets wait on the free lists)   */
   SMX_STAT_SPILLED = 23,    /* cells of big rows that did not fit their shared-memory tile during a re-placement */
-  SMX_STAT_SLICED_GETS = 24 /* point reads answered in directory-slice order so far (see set_get_slices)  */
+  SMX_STAT_SLICED_GETS = 24,/* point reads answered in directory-slice order so far (see set_get_slices)  */
+  SMX_STAT_WIDE_CHUNKS = 25 /* write chunks without ops on column 0 that were ordered over 256 slices ($SMATRIX_WIDE_SLICES) */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 

@@ -86,7 +86,8 @@ struct smatrix_s {
   uint32_t part_cap;
   uint32_t part_min; /* chunks smaller than this are applied in input order */
   uint32_t slice_log; /* log2(directory entries per slice) */
-  uint32_t parts_log_max; /* at most 2^this parts (<= 8) */
+  uint32_t parts_log_max; /* at most 2^this slices (<= 7: with their column-0 twins that is 256 parts) */
+  int wide_slices;        /* SMATRIX_WIDE_SLICES: chunks without ops on column 0 use 256 slices */
 
 
   uint32_t* d_small; /* 64 words */
@@ -126,6 +127,7 @@ struct smatrix_s {
                                               * when the batch revisits rows often enough, 2 = always */
   int get_flags;                             /* measurement switches of the slice-ordered look-up (SMX_GET_*) */
   uint64_t n_sliced_gets;                    /* queries answered through the slice-ordered path */
+  uint64_t n_wide_chunks;                    /* write chunks ordered over 256 slices (no ops on column 0) */
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
   uint64_t bucket_bytes;         /* slab bytes handed out for column buckets (fresh, not recycled) */
@@ -598,30 +600,49 @@ static void ensure_parts(smatrix_t* s, uint32_t n) {
  * a set batch, a chunk that writes column 0, or a caller-supplied order.
  * Returns 1 if the chunk was partitioned; *n_main = number of ops that are not on column 0. */
 static int partition_chunk(smatrix_t* s, smx_ops_t* ops, int api_op, uint32_t* n_main) {
-  const uint32_t n = ops->n;
+  const uint32_t n = ops->n, mask = (uint32_t)(s->dir_cap - 1);
   uint32_t parts_log, shift;
   slice_geometry(s, &parts_log, &shift);
-  const uint32_t slices = 1u << parts_log, parts = 2u * slices;
+  uint32_t slices = 1u << parts_log, parts = 2u * slices;
+  /* With the column-0 parts a chunk has at most 128 slices.  A chunk WITHOUT ops on column 0 (configs 2
+   * and 5) does not need them: count over twice as many slices (+ their column-0 twins, 512 bins), and
+   * use all 256 parts as slices if the twins stay empty — else fold neighbouring bins back. */
+  const int fine = s->wide_slices && parts_log == 7 && parts_log + shift > s->slice_log + 7;
   ensure_parts(s, n);
-  ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
-  unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
-  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
-  unsigned long long h[SMX_MAX_PARTS_H], cur[SMX_MAX_PARTS_H];
+  ensure_tmp(s, 0, 3 * SMX_MAX_PARTS_H * 8);
+  unsigned long long* d_counts = (unsigned long long*)s->d_tmp64; /* up to 2 * SMX_MAX_PARTS_H bins */
+  unsigned long long* d_cursors = d_counts + 2 * SMX_MAX_PARTS_H;
+  unsigned long long h[2 * SMX_MAX_PARTS_H], cur[SMX_MAX_PARTS_H];
   double t0 = now_ns();
-  CK(cudaMemsetAsync(d_counts, 0, parts * 8, s->stream));
-  smx_launch_partition_count(s->stream, ops->xs, ops->ys, n, parts, (uint32_t)(s->dir_cap - 1), shift, slices, d_counts);
-  copy_d2h(s, h, d_counts, parts * 8, s->stream);
+  const uint32_t bins = fine ? 2u * parts : parts;
+  CK(cudaMemsetAsync(d_counts, 0, bins * 8, s->stream));
+  smx_launch_partition_count(s->stream, ops->xs, ops->ys, n, bins, mask, fine ? shift - 1 : shift, bins / 2, d_counts);
+  copy_d2h(s, h, d_counts, bins * 8, s->stream);
   CK(cudaStreamSynchronize(s->stream));
+  uint32_t split0 = slices;
+  if (fine) {
+    unsigned long long on_col0 = 0;
+    for (uint32_t p = parts; p < bins; p++) on_col0 += h[p];
+    if (on_col0 == 0) { /* 256 slices, no column-0 parts: the first half of the bins is the histogram */
+      slices = parts;
+      split0 = 0;
+      shift -= 1;
+      s->n_wide_chunks++;
+    } else {
+      for (uint32_t p = 0; p < parts; p++) h[p] = h[2 * p] + h[2 * p + 1]; /* in place: 2p >= p */
+    }
+  }
   unsigned long long at = 0;
+  *n_main = n;
   for (uint32_t p = 0; p < parts; p++) {
-    if (p == slices) *n_main = (uint32_t)at;
+    if (split0 && p == split0) *n_main = (uint32_t)at;
     cur[p] = at;
     at += h[p];
   }
   const int want_idx = api_op == 2 || *n_main != n || ops->idx != NULL;
   copy_h2d(s, d_cursors, cur, parts * 8, s->stream);
-  smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, (uint32_t)(s->dir_cap - 1),
-                               shift, slices, d_cursors, s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
+  smx_launch_partition_scatter(s->stream, ops->xs, ops->ys, ops->vs, n, parts, mask, shift, split0, d_cursors,
+                               s->part[0], s->part[1], ops->vs ? s->part[2] : NULL,
                                want_idx ? s->part[3] : NULL, ops->idx, NULL, NULL, 0);
   s->n_launches += 2;
   if (s->timing) CK(cudaStreamSynchronize(s->stream));
@@ -928,12 +949,14 @@ void smatrix_b200_apply_ordered_out(smatrix_t* s, int op, const uint32_t* d_xs, 
  * so it only pays when rows repeat: at q/R = 1 saved touches and added passes break even. */
 enum {
   SMX_GET_KEEP = 4,    /* bucket sectors with the ordinary L2 priority (default: evict-first, they are read once) */
-  SMX_GET_NARROW = 8,  /* the write path's slice count (<= 2^SMATRIX_PARTS_LOG2) instead of up to 256 slices */
-  SMX_GET_STRIDE = 16  /* look-ups by the resident-grid kernel of the input-order path (blocks drift across slices) */
+  SMX_GET_WIDE = 8,    /* up to 256 slices instead of the write path's count (<= 2^SMATRIX_PARTS_LOG2 = 128) */
+  SMX_GET_STRIDE = 16, /* look-ups by the resident-grid kernel of the input-order path (blocks drift across slices) */
+  SMX_GET_STRIDE_GATHER = 32, /* answers put back by a resident-grid gather */
+  SMX_GET_FLAGS = 4 | 8 | 16 | 32
 };
 static void get_geometry(const smatrix_t* s, uint32_t* parts_log, uint32_t* shift) {
   slice_geometry(s, parts_log, shift);
-  if (!(s->get_flags & SMX_GET_NARROW)) { /* no column-0 parts here, so all 256 parts can be slices */
+  if (s->get_flags & SMX_GET_WIDE) { /* no column-0 parts here, so all 256 parts can be slices */
     const uint32_t dir_log = *parts_log + *shift;
     uint32_t pl = dir_log > s->slice_log ? dir_log - s->slice_log : 0;
     if (pl > 8) pl = 8;
@@ -954,9 +977,9 @@ static void get_sliced(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
   get_geometry(s, &parts_log, &shift);
   const uint32_t slices = 1u << parts_log, mask = (uint32_t)(s->dir_cap - 1);
   ensure_parts(s, n);
-  ensure_tmp(s, 0, 2 * SMX_MAX_PARTS_H * 8);
+  ensure_tmp(s, 0, 3 * SMX_MAX_PARTS_H * 8);
   unsigned long long* d_counts = (unsigned long long*)s->d_tmp64;
-  unsigned long long* d_cursors = d_counts + SMX_MAX_PARTS_H;
+  unsigned long long* d_cursors = d_counts + 2 * SMX_MAX_PARTS_H;
   CK(cudaMemsetAsync(d_counts, 0, slices * 8, s->stream));
   smx_launch_partition_count(s->stream, d_xs, NULL, n, slices, mask, shift, 0, d_counts);
   smx_launch_parts_prefix(s->stream, d_counts, slices, d_cursors);
@@ -964,7 +987,8 @@ static void get_sliced(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys,
                                s->part[1], NULL, NULL, NULL, s->part[3], NULL, 0);
   if (s->get_flags & SMX_GET_STRIDE) smx_launch_get(s->stream, view_of(s), s->part[0], s->part[1], n, s->part[2]);
   else smx_launch_get_tiled(s->stream, view_of(s), s->part[0], s->part[1], n, s->part[2], !(s->get_flags & SMX_GET_KEEP));
-  smx_launch_gather(s->stream, d_out, s->part[2], s->part[3], n);
+  if (s->get_flags & SMX_GET_STRIDE_GATHER) smx_launch_gather_stride(s->stream, d_out, s->part[2], s->part[3], n);
+  else smx_launch_gather(s->stream, d_out, s->part[2], s->part[3], n);
   s->n_launches += 5;
   s->n_sliced_gets += n;
 }
@@ -1547,12 +1571,13 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;
   s->get_slices = (int)env_u32("SMATRIX_GET_SLICES", 1);
-  s->get_flags = s->get_slices & (SMX_GET_KEEP | SMX_GET_NARROW | SMX_GET_STRIDE);
+  s->get_flags = s->get_slices & SMX_GET_FLAGS;
   s->get_slices = (s->get_slices & 3) > 2 ? 2 : (s->get_slices & 3);
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
-  if (s->parts_log_max > 8) s->parts_log_max = 8;
+  if (s->parts_log_max > 7) s->parts_log_max = 7; /* 2 x 128 = SMX_MAX_PARTS_H parts */
+  s->wide_slices = (int)env_u32("SMATRIX_WIDE_SLICES", 0);
   s->arena_bytes = arena_bytes;
   if (s->arena_bytes) push_segment(s, (char*)dmalloc(s, s->arena_bytes), s->arena_bytes);
   s->dir_cap = 1ull << s->dir_log_min;
@@ -1678,7 +1703,7 @@ void smatrix_b200_set_get_slices(smatrix_t* s, int mode) {
   enter(s);
   if (mode < 0) mode = 0;
   s->get_slices = (mode & 3) > 2 ? 2 : (mode & 3);
-  s->get_flags = mode & (SMX_GET_KEEP | SMX_GET_NARROW | SMX_GET_STRIDE);
+  s->get_flags = mode & SMX_GET_FLAGS;
   leave(s);
 }
 
@@ -1729,6 +1754,7 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
     case SMX_STAT_BUCKET_BYTES: r = s->bucket_bytes; break;
     case SMX_STAT_SPILLED: r = s->n_spilled; break;
     case SMX_STAT_SLICED_GETS: r = s->n_sliced_gets; break;
+    case SMX_STAT_WIDE_CHUNKS: r = s->n_wide_chunks; break;
     case SMX_STAT_H2D_BYTES: r = s->h2d_bytes; break;
     case SMX_STAT_D2H_BYTES: r = s->d2h_bytes; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;

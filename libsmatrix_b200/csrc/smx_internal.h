@@ -231,6 +231,8 @@ void smx_launch_parts_prefix(smx_stream_t stream, const unsigned long long* coun
                              unsigned long long* cursors /* [parts] = exclusive prefix of counts */);
 void smx_launch_gather(smx_stream_t stream, uint32_t* out, const uint32_t* vals, const uint32_t* pos,
                        uint32_t n);
+void smx_launch_gather_stride(smx_stream_t stream, uint32_t* out, const uint32_t* vals, const uint32_t* pos,
+                              uint32_t n);
 void smx_launch_route_offsets(smx_stream_t stream, const uint64_t* offs, const uint32_t* pos, uint32_t n,
                              uint32_t world, const unsigned long long* tab /* device: [2][world] */);
 uint32_t smx_scan_scratch_items(uint32_t n); /* number of uint64 block sums smx_launch_scan needs */

@@ -1649,6 +1649,9 @@ k_probe_atomic(uint32_t* buf, ull n_words, ull accesses) {
  * K8: owner-rank bucketing for the multi-GPU router
  * ---------------------------------------------------------------------------------------- */
 #define SMX_MAX_PARTS 256
+#define PART_ITEMS 8
+#define PART_TILE (SMX_BLOCK * PART_ITEMS)
+#define PART_PER_LANE (SMX_MAX_PARTS / SMX_WARP)
 /* part = owner rank (shift == 0xFFFFFFFF: mix_owner(x) % world) or directory slice
  * ((mix_row(x) & dir_mask) >> shift).  With split0 != 0 (slice mode, `world` = 2 * split0 parts)
  * ops on column 0 go to parts split0 .. 2*split0-1: the partitioned chunk is then
@@ -1664,7 +1667,7 @@ __device__ __forceinline__ uint32_t part_of(uint32_t x, uint32_t y, uint32_t wor
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t world, uint32_t dir_mask,
                   uint32_t shift, uint32_t split0, ull* counts) {
-  __shared__ uint32_t hist[SMX_MAX_PARTS];
+  __shared__ uint32_t hist[2 * SMX_MAX_PARTS]; /* up to 256 slices + their column-0 twins */
   for (uint32_t k = threadIdx.x; k < world; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1676,6 +1679,7 @@ k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t w
 /* cursors[p] = first output index of part p = exclusive prefix of counts (<= 256 parts: one thread;
  * the read path uses it so that no host round trip sits between the count and the scatter) */
 __global__ void k_parts_prefix(const ull* counts, uint32_t parts, ull* cursors) {
+#ifdef SMX_HOSTSIM
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ull at = 0ull;
     for (uint32_t p = 0; p < parts; ++p) {
@@ -1683,6 +1687,29 @@ __global__ void k_parts_prefix(const ull* counts, uint32_t parts, ull* cursors) 
       at += counts[p];
     }
   }
+#else
+  /* one warp: lane l owns parts [8 l, 8 l + 8) — eight independent loads, a shuffle scan, eight stores */
+  const uint32_t lane = threadIdx.x;
+  ull c[PART_PER_LANE], sum = 0ull;
+#pragma unroll
+  for (int q = 0; q < PART_PER_LANE; ++q) {
+    const uint32_t p = lane * PART_PER_LANE + q;
+    c[q] = p < parts ? counts[p] : 0ull;
+    sum += c[q];
+  }
+  ull incl = sum;
+  for (uint32_t d = 1; d < SMX_WARP; d <<= 1) {
+    const ull t = __shfl_up_sync(SMX_FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  ull run = incl - sum;
+#pragma unroll
+  for (int q = 0; q < PART_PER_LANE; ++q) {
+    const uint32_t p = lane * PART_PER_LANE + q;
+    if (p < parts) cursors[p] = run;
+    run += c[q];
+  }
+#endif
 }
 /* Tiled partition: a block stages a tile of ops in shared memory sorted by part, reserves one
  * contiguous range per part with a single global atomic, and writes whole runs — so every
@@ -1692,9 +1719,6 @@ __global__ void k_parts_prefix(const ull* counts, uint32_t parts, ull* cursors) 
  * tile's x / y loads are issued before this tile is written out, the cursor atomics fly while the
  * tile is being staged, and every warp keeps its own copy of the (tiny) prefix table instead of
  * waiting at a barrier for one warp to build it. */
-#define PART_ITEMS 8
-#define PART_TILE (SMX_BLOCK * PART_ITEMS)
-#define PART_PER_LANE (SMX_MAX_PARTS / SMX_WARP)
 template <bool HAS_V, bool HAS_POS> /* shared memory only for what is used: 34 - 42 KB per block */
 __global__ void __launch_bounds__(SMX_BLOCK)
 k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, uint32_t n,
@@ -1832,9 +1856,28 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
   }
 }
 
-/* out[i] = vals[pos[i]]: un-permute routed answers into input order */
+/* out[i] = vals[pos[i]]: un-permute routed answers into input order.  A block takes one scatter tile
+ * (PART_TILE consecutive inputs): the tile's ops sit in one contiguous run per part of the routed
+ * order, so every sector of `vals` the block touches is used up by the block itself (L1), and a
+ * thread's PART_ITEMS loads are independent. */
 __global__ void __launch_bounds__(SMX_BLOCK)
-k_gather(uint32_t* out, const uint32_t* vals, const uint32_t* pos, uint32_t n) {
+k_gather(uint32_t* out, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ pos, uint32_t n) {
+  const ull base = (ull)blockIdx.x * PART_TILE;
+  uint32_t p[PART_ITEMS];
+#pragma unroll
+  for (int k = 0; k < PART_ITEMS; ++k) {
+    const ull i = base + (ull)k * SMX_BLOCK + threadIdx.x;
+    p[k] = i < n ? pos[i] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < PART_ITEMS; ++k) {
+    const ull i = base + (ull)k * SMX_BLOCK + threadIdx.x;
+    if (i < n) out[i] = vals[p[k]];
+  }
+}
+/* the same as a resident grid with a stride loop (kept as the B side of the A/B: SMX_GET_STRIDE_GATHER) */
+__global__ void __launch_bounds__(SMX_BLOCK)
+k_gather_stride(uint32_t* out, const uint32_t* vals, const uint32_t* pos, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     out[i] = vals[pos[i]];
 }
@@ -2251,7 +2294,12 @@ extern "C" void smx_launch_parts_prefix(smx_stream_t st, const unsigned long lon
 extern "C" void smx_launch_gather(smx_stream_t st, uint32_t* out, const uint32_t* vals,
                                   const uint32_t* pos, uint32_t n) {
   if (!n) return;
-  SMX_LAUNCH(k_gather, grid_for(n), SMX_BLOCK, st, out, vals, pos, n);
+  SMX_LAUNCH(k_gather, (uint32_t)(((ull)n + PART_TILE - 1) / PART_TILE), SMX_BLOCK, st, out, vals, pos, n);
+}
+extern "C" void smx_launch_gather_stride(smx_stream_t st, uint32_t* out, const uint32_t* vals,
+                                         const uint32_t* pos, uint32_t n) {
+  if (!n) return;
+  SMX_LAUNCH(k_gather_stride, grid_for(n), SMX_BLOCK, st, out, vals, pos, n);
 }
 
 extern "C" void smx_launch_route_offsets(smx_stream_t st, const uint64_t* offs, const uint32_t* pos,

@@ -533,3 +533,26 @@ def scenario_sliced_gets(make, n_rows: int = 3000, n_cols: int = 90, n_ops: int 
             m.dev_free(p)
     m.set_get_slices(1)
     m.close(); ref.close()
+
+
+def scenario_no_column0(make, n: int = 200000, n_rows: int = 40000, batches: int = 5):
+    """Streams that never touch column 0 (configs 2 and 5): with SMATRIX_WIDE_SLICES such a chunk is ordered over
+    256 slices without column-0 parts; a chunk in between that does write column 0 falls back to 128 + 128."""
+    import os
+    rng = np.random.default_rng(12)
+    m, ref = make(), checker()
+    for k in range(batches):
+        xs = (rng.integers(0, n_rows, n).astype(U32) * U32(2654435761))
+        ys = rng.integers(1, 60, n).astype(U32)
+        if k == 3:
+            ys[::17] = 0
+        vs = rng.integers(1, 2**32, n, dtype=np.uint64).astype(U32)
+        apply_both(m, ref, "incr" if k != 2 else "set", xs, ys, vs)
+    rows = np.unique(xs)
+    compare(m, ref, np.concatenate([rows, rows + U32(1)]), xs, ys)
+    wide = m.stat("wide_chunks")
+    if os.environ.get("SMATRIX_WIDE_SLICES", "0") == "1" and "SMATRIX_PARTITION_MIN" in os.environ:
+        assert wide >= batches - 1, "chunks without column 0 should have used 256 slices"
+    elif os.environ.get("SMATRIX_WIDE_SLICES", "0") != "1":
+        assert wide == 0
+    m.close(); ref.close()

@@ -14,8 +14,13 @@ U32 = np.uint32
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(params=["default", "chunk65536", "partitioned", "arena"])
+@pytest.fixture(params=["default", "chunk65536", "partitioned", "arena", "partitioned-wide"])
 def make(request, monkeypatch):
+    if request.param == "partitioned-wide":                # 256 slices for chunks without ops on column 0
+        monkeypatch.setenv("SMATRIX_PARTITION_MIN", "64")
+        monkeypatch.setenv("SMATRIX_SLICE_LOG2", "6")
+        monkeypatch.setenv("SMATRIX_DIR_LOG2", "14")
+        monkeypatch.setenv("SMATRIX_WIDE_SLICES", "1")
     if request.param == "arena":                           # slab + directory carved from a reserved arena
         monkeypatch.setenv("SMATRIX_ARENA_GIB", "2")
         monkeypatch.setenv("SMATRIX_DIR_LOG2", "12")
@@ -180,6 +185,10 @@ def test_device_pointer_batches():
     rl = m.rowlen_batch(t(np.arange(5100, dtype=U32)))
     assert (rl.cpu().numpy().view(U32) == ref.rowlen_many(np.arange(5100, dtype=U32))).all()
     m.close(); ref.close()
+
+
+def test_chunks_without_column0(make):
+    ps.scenario_no_column0(make)
 
 
 def test_sliced_gets(make):

@@ -16,8 +16,8 @@ def sim():
     return hb.build()
 
 
-@pytest.fixture(params=[(6, 1 << 26, 0), (10, 3000, 0), (4, 777, 0), (8, 5000, 1)],
-                ids=["dir64", "chunk3000", "dir16-chunk777", "partitioned"])
+@pytest.fixture(params=[(6, 1 << 26, 0), (10, 3000, 0), (4, 777, 0), (8, 5000, 1), (12, 4000, 2)],
+                ids=["dir64", "chunk3000", "dir16-chunk777", "partitioned", "partitioned-wide"])
 def make(request, sim, monkeypatch):
     dir_log2, chunk, partitioned = request.param
     monkeypatch.setenv("SMATRIX_DIR_LOG2", str(dir_log2))   # tiny directory: growth on every test
@@ -25,6 +25,8 @@ def make(request, sim, monkeypatch):
     if partitioned:                                         # chunks re-ordered by directory slice
         monkeypatch.setenv("SMATRIX_PARTITION_MIN", "16")
         monkeypatch.setenv("SMATRIX_SLICE_LOG2", "3")
+    if partitioned == 2:                                    # 256 slices for chunks without ops on column 0
+        monkeypatch.setenv("SMATRIX_WIDE_SLICES", "1")
     return lambda: SparseMatrix(_lib_path=sim)
 
 
@@ -103,6 +105,10 @@ def test_read_path_zipf(make):
 
 def test_batch_out(make):
     ps.scenario_batch_out(make, n=6000)
+
+
+def test_chunks_without_column0(make):
+    ps.scenario_no_column0(make, n=9000, n_rows=2500)
 
 
 def test_sliced_gets(make, monkeypatch):
