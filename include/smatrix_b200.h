@@ -17,8 +17,9 @@ extern "C" {
  * cudaMalloc'ing segments on demand), SMATRIX_CHUNK (ops per internal chunk, default 2^26),
  * SMATRIX_DIR_LOG2 (initial directory size), SMATRIX_PREAGG (warp pre-aggregation on/off),
  * SMATRIX_RECYCLE (free lists of vacated buckets on/off), SMATRIX_PRESIZE (distinct-row estimate
- * that sizes the directory before a chunk of new rows, on/off), SMATRIX_GET_SLICES (see
- * smatrix_b200_set_get_slices). */
+ * that sizes the directory before a chunk of new rows, on/off), SMATRIX_GET_SLICES / SMATRIX_GET_SLICE_MIN
+ * (see smatrix_b200_set_get_slices), SMATRIX_WIDE_SLICES (default 1: a write chunk without ops on column 0
+ * is ordered over 256 directory slices instead of 128 + their column-0 twins). */
 smatrix_t* smatrix_b200_open(const char* fname, int device);
 /* the same with the slab arena given explicitly (bytes; 0 = segments on demand) instead of through
  * $SMATRIX_ARENA_GIB — for hosts that open several handles with different needs from several threads */
@@ -72,10 +73,13 @@ uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 void smatrix_b200_set_kernel_timing(smatrix_t* self, int on);
 
 /* Point reads on device arrays (smatrix_get_batch): 0 = look every query up in input order; 1 (default,
- * $SMATRIX_GET_SLICES) = order a batch by directory slice first when it holds at least 2^20 queries and
- * at least two per row of the table (the directory entries of a slice then stay in L2 and are fetched
- * from DRAM once per row instead of once per query), answers are put back into input order; 2 = always.
- * The answers are the same in every mode. */
+ * $SMATRIX_GET_SLICES) = order a call's queries by directory slice first when there are at least
+ * $SMATRIX_GET_SLICE_MIN (2^22) of them and at least one per two rows of the table (the directory
+ * entries of a slice then stay in L2 and are fetched from DRAM once per row instead of once per query),
+ * answers are put back into input order; 2 = always.  The answers are the same in every mode.
+ * Measurement switches, OR-ed to the mode (B sides of the A/Bs in profiles/): 4 = bucket sectors with the
+ * ordinary L2 priority instead of evict-first, 8 = 256 slices instead of 128, 16 = look-ups by the
+ * resident-grid kernel of the input-order path, 32 = resident-grid gather. */
 void smatrix_b200_set_get_slices(smatrix_t* self, int mode);
 
 /* Pinned host memory (cudaHostAlloc) so that host-pointer batches overlap copy and update. */

@@ -126,6 +126,7 @@ struct smatrix_s {
   int get_slices;                            /* SMATRIX_GET_SLICES: 0 = point reads in input order, 1 (default) = by directory slice
                                               * when the batch revisits rows often enough, 2 = always */
   int get_flags;                             /* measurement switches of the slice-ordered look-up (SMX_GET_*) */
+  uint32_t get_slice_min;                    /* SMATRIX_GET_SLICE_MIN (2^22): smaller calls are looked up in input order */
   uint64_t n_sliced_gets;                    /* queries answered through the slice-ordered path */
   uint64_t n_wide_chunks;                    /* write chunks ordered over 256 slices (no ops on column 0) */
 
@@ -945,8 +946,11 @@ void smatrix_b200_apply_ordered_out(smatrix_t* s, int op, const uint32_t* d_xs, 
  * of once per QUERY.  Answers come out in slice order and k_gather puts them back through the
  * inverse permutation the scatter leaves; a tile's queries land in one contiguous run per slice, so
  * that gather reads whole sectors.  The cursors are prefixed on the device (k_parts_prefix): nothing
- * between the five launches waits for the host.  Costs one streaming pass each way (~28 B/query),
- * so it only pays when rows repeat: at q/R = 1 saved touches and added passes break even. */
+ * between the five launches waits for the host.  The look-ups run in k_get_tiled (blocks dispatched
+ * in query order; the resident-grid k_get drifts across slices and loses the effect: 11.5 vs 25.4
+ * Gops/s).  Besides the saved touches the slice order confines the directory accesses to 32 MB at a
+ * time (TLB reach), so it already pays at 0.3 - 0.65 queries per row.  Config 2, 500 M queries over
+ * 13 M rows / 1.51 B cells: 12.8 -> 25.4 Gops/s. */
 enum {
   SMX_GET_KEEP = 4,    /* bucket sectors with the ordinary L2 priority (default: evict-first, they are read once) */
   SMX_GET_WIDE = 8,    /* up to 256 slices instead of the write path's count (<= 2^SMATRIX_PARTS_LOG2 = 128) */
@@ -970,7 +974,10 @@ static int get_slices_pay(const smatrix_t* s, uint32_t n) {
   get_geometry(s, &parts_log, &shift);
   if (parts_log == 0) return 0; /* the whole directory is one slice */
   if (s->get_slices >= 2) return 1;
-  return n >= s->part_min && (uint64_t)n >= 2 * s->h_ctl->dir_used;
+  /* measured on the config-2 table (13 M rows, profiles/r2_summary.md): calls of 2^22 / 2^23 / 2^24 / 2^25 queries
+   * = 0.3 / 0.65 / 1.3 / 2.6 per row: +5 / +20 / +70 / +75 % over the input order; 2^20 queries: -20 % (five launches
+   * instead of one) */
+  return n >= s->get_slice_min && 2 * (uint64_t)n >= s->h_ctl->dir_used;
 }
 static void get_sliced(smatrix_t* s, const uint32_t* d_xs, const uint32_t* d_ys, uint32_t n, uint32_t* d_out) {
   uint32_t parts_log, shift;
@@ -1571,13 +1578,14 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   s->stage_max = env_u32("SMATRIX_STAGE", SMX_STAGE_MAX);
   if (s->stage_max < 1024) s->stage_max = 1024;
   s->get_slices = (int)env_u32("SMATRIX_GET_SLICES", 1);
+  s->get_slice_min = env_u32("SMATRIX_GET_SLICE_MIN", 1u << 22);
   s->get_flags = s->get_slices & SMX_GET_FLAGS;
   s->get_slices = (s->get_slices & 3) > 2 ? 2 : (s->get_slices & 3);
   s->part_min = env_u32("SMATRIX_PARTITION_MIN", 1u << 20);
   s->slice_log = env_u32("SMATRIX_SLICE_LOG2", 17);
   s->parts_log_max = env_u32("SMATRIX_PARTS_LOG2", 7);
   if (s->parts_log_max > 7) s->parts_log_max = 7; /* 2 x 128 = SMX_MAX_PARTS_H parts */
-  s->wide_slices = (int)env_u32("SMATRIX_WIDE_SLICES", 0);
+  s->wide_slices = (int)env_u32("SMATRIX_WIDE_SLICES", 1);
   s->arena_bytes = arena_bytes;
   if (s->arena_bytes) push_segment(s, (char*)dmalloc(s, s->arena_bytes), s->arena_bytes);
   s->dir_cap = 1ull << s->dir_log_min;

@@ -500,7 +500,7 @@ def scenario_sliced_gets(make, n_rows: int = 3000, n_cols: int = 90, n_ops: int 
     apply_both(m, ref, "incr", xs, ys, vs)
     import os
     can_slice = m.stat("dir_cap") > (1 << int(os.environ.get("SMATRIX_SLICE_LOG2", 17)))   # more than one slice
-    part_min = int(os.environ.get("SMATRIX_PARTITION_MIN", 1 << 20))
+    part_min = int(os.environ.get("SMATRIX_GET_SLICE_MIN", 1 << 22))
 
     def up(a):
         p = m.dev_alloc(max(a.nbytes, 8))
@@ -515,7 +515,7 @@ def scenario_sliced_gets(make, n_rows: int = 3000, n_cols: int = 90, n_ops: int 
         qx[2::7] += U32(1)                                             # rows nobody wrote
         want = ref.get_many(qx, qy)
         dx, dy, do = up(qx), up(qy), m.dev_alloc(4 * n + 8)
-        auto = can_slice and n >= 2 * m.stat("rows") and n >= part_min
+        auto = can_slice and 2 * n >= m.stat("rows") and n >= part_min
         # + the measurement switches: 4 = ordinary L2 priority for bucket sectors, 8 = the write path's slice
         # count, 16 = resident-grid look-up kernel
         for mode, sliced in ((0, False), (2, can_slice), (1, auto), (2 | 4, can_slice), (2 | 8, can_slice),
@@ -551,8 +551,8 @@ def scenario_no_column0(make, n: int = 200000, n_rows: int = 40000, batches: int
     rows = np.unique(xs)
     compare(m, ref, np.concatenate([rows, rows + U32(1)]), xs, ys)
     wide = m.stat("wide_chunks")
-    if os.environ.get("SMATRIX_WIDE_SLICES", "0") == "1" and "SMATRIX_PARTITION_MIN" in os.environ:
+    if os.environ.get("SMATRIX_WIDE_SLICES", "1") == "1" and os.environ.get("SMATRIX_SLICE_LOG2") in ("3", "6"):
         assert wide >= batches - 1, "chunks without column 0 should have used 256 slices"
-    elif os.environ.get("SMATRIX_WIDE_SLICES", "0") != "1":
+    elif os.environ.get("SMATRIX_WIDE_SLICES", "1") != "1":
         assert wide == 0
     m.close(); ref.close()

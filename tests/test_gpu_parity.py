@@ -31,6 +31,7 @@ def make(request, monkeypatch):
         monkeypatch.setenv("SMATRIX_PARTITION_MIN", "64")
         monkeypatch.setenv("SMATRIX_SLICE_LOG2", "6")
         monkeypatch.setenv("SMATRIX_DIR_LOG2", "10")
+        monkeypatch.setenv("SMATRIX_WIDE_SLICES", "0")     # 128 slices + column-0 twins for every chunk
     return lambda: SparseMatrix()
 
 

@@ -25,8 +25,8 @@ def make(request, sim, monkeypatch):
     if partitioned:                                         # chunks re-ordered by directory slice
         monkeypatch.setenv("SMATRIX_PARTITION_MIN", "16")
         monkeypatch.setenv("SMATRIX_SLICE_LOG2", "3")
-    if partitioned == 2:                                    # 256 slices for chunks without ops on column 0
-        monkeypatch.setenv("SMATRIX_WIDE_SLICES", "1")
+    # chunks without ops on column 0 use 256 slices (the default) or, in the first partitioned variant, 128 + twins
+    monkeypatch.setenv("SMATRIX_WIDE_SLICES", "1" if partitioned == 2 else "0")
     return lambda: SparseMatrix(_lib_path=sim)
 
 
@@ -112,7 +112,7 @@ def test_chunks_without_column0(make):
 
 
 def test_sliced_gets(make, monkeypatch):
-    monkeypatch.setenv("SMATRIX_PARTITION_MIN", "16")       # mode 1 needs >= this many queries ...
+    monkeypatch.setenv("SMATRIX_GET_SLICE_MIN", "16")       # mode 1 needs >= this many queries ...
     monkeypatch.setenv("SMATRIX_SLICE_LOG2", "3")           # ... and more than one directory slice
     ps.scenario_sliced_gets(make, n_rows=300, n_cols=40, n_ops=6000, sizes=(1, 2, 7, 8, 9, 15, 16, 17, 599, 600, 5001))
 
