@@ -492,6 +492,7 @@ def run_write_workload(job: Job, name: str):
     step_ms, kern_ms, prev_k = [], [], 0
     PHASES = ("partition", "upsert", "grow_plan", "slab", "migrate", "dir")
     prev_ph = [0.0] * len(PHASES) + [m.stat("rounds"), m.stat("launches")]
+    alloc0 = prev_alloc = m.stat("ns_alloc") / 1e6     # cudaMalloc time inside the timed steps (0 with an arena)
     for j in range(K):
         t_s = time.perf_counter()
         wl.incr(m, xs[j], ys[j])                # synchronous: returns when the device is done
@@ -501,9 +502,11 @@ def run_write_workload(job: Job, name: str):
         prev_k = k_now
         if a.phase_series and rank == 0:
             now = [m.stat("ns_" + k) / 1e6 for k in PHASES] + [m.stat("rounds"), m.stat("launches")]
+            al = m.stat("ns_alloc") / 1e6
             print(f"step {j}: {step_ms[-1]} ms; " + ", ".join(f"{k} {now[i] - prev_ph[i]:.2f}" for i, k in enumerate(PHASES))
-                  + f"; rounds {now[-2] - prev_ph[-2]}, launches {now[-1] - prev_ph[-1]}", file=sys.stderr)
-            prev_ph = now
+                  + f"; rounds {now[-2] - prev_ph[-2]}, launches {now[-1] - prev_ph[-1]}, cudaMalloc {al - prev_alloc:.2f} ms",
+                  file=sys.stderr)
+            prev_ph, prev_alloc = now, al
     ms_build = m.timer_stop_ms()
     job.barrier()
     wall1 = time.time()
@@ -512,6 +515,7 @@ def run_write_workload(job: Job, name: str):
     rounds = m.stat("rounds") - rounds0
     upsert_ns = m.stat("kernel_ns")
     phases = {k: round(m.stat("ns_" + k) / 1e6 / K, 3) for k in PHASES}
+    phases["cudaMalloc"] = round((m.stat("ns_alloc") / 1e6 - alloc0) / K, 3)
     route = m.route_stats() if world > 1 else None
     m.set_kernel_timing(False)
     clocks = job.sampler.window(wall0, wall1)

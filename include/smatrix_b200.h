@@ -64,7 +64,9 @@ enum {
                                 allocator's overhead (vacated buckets wait on the free lists)   */
   SMX_STAT_SPILLED = 23,    /* cells of big rows that did not fit their shared-memory tile during a re-placement */
   SMX_STAT_SLICED_GETS = 24,/* point reads answered in directory-slice order so far (see set_get_slices)  */
-  SMX_STAT_WIDE_CHUNKS = 25 /* write chunks without ops on column 0 that were ordered over 256 slices ($SMATRIX_WIDE_SLICES) */
+  SMX_STAT_WIDE_CHUNKS = 25,/* write chunks without ops on column 0 that were ordered over 256 slices ($SMATRIX_WIDE_SLICES) */
+  SMX_STAT_NS_ALLOC = 26,   /* host time inside cudaMalloc on behalf of this handle so far, ns */
+  SMX_STAT_ALLOCS = 27      /* number of those cudaMalloc calls */
 };
 uint64_t smatrix_b200_stat(smatrix_t* self, int which);
 

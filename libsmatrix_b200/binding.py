@@ -135,7 +135,7 @@ STAT = {"rows": 0, "nnz": 1, "dir_cap": 2, "slab_bytes": 3, "device_bytes": 4, "
         "rounds": 6, "row_grows": 7, "dir_grows": 8, "kernel_ns": 9, "ns_partition": 10, "ns_upsert": 11,
         "ns_grow_plan": 12, "ns_slab": 13, "ns_migrate": 14, "ns_dir": 15, "value_sum": 16,
         "live_bucket_bytes": 17, "free_bytes": 18, "recycled": 19, "h2d_bytes": 20, "d2h_bytes": 21, "bucket_bytes": 22, "spilled": 23,
-        "sliced_gets": 24, "wide_chunks": 25}
+        "sliced_gets": 24, "wide_chunks": 25, "ns_alloc": 26, "allocs": 27}
 
 _cache: dict[str, C.CDLL] = {}
 

@@ -129,6 +129,8 @@ struct smatrix_s {
   uint32_t get_slice_min;                    /* SMATRIX_GET_SLICE_MIN (2^22): smaller calls are looked up in input order */
   uint64_t n_sliced_gets;                    /* queries answered through the slice-ordered path */
   uint64_t n_wide_chunks;                    /* write chunks ordered over 256 slices (no ops on column 0) */
+  double alloc_ns;                           /* host time spent inside cudaMalloc by this handle */
+  uint64_t n_allocs;
 
   uint64_t n_launches, n_rounds, n_row_grows, n_dir_grows, n_recycled;
   uint64_t bucket_bytes;         /* slab bytes handed out for column buckets (fresh, not recycled) */
@@ -165,11 +167,14 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
   return (uint32_t)strtoul(v, NULL, 0);
 }
 
+static inline double now_ns(void);
 static void* dmalloc(smatrix_t* s, size_t bytes) {
   void* p = NULL;
-  (void)s;
+  const double t0 = now_ns();
   cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
   if (e != cudaSuccess) smx_die("out of device memory (%zu bytes): %s", bytes, cudaGetErrorString(e));
+  s->alloc_ns += now_ns() - t0; /* SMX_STAT_NS_ALLOC: cudaMalloc stalls for 2 - 150 ms on some hosts */
+  s->n_allocs++;
   return p;
 }
 
@@ -1599,6 +1604,14 @@ smatrix_t* smatrix_b200_open_arena(const char* fname, int device, size_t arena_b
   memset(s->h_ctl, 0, sizeof(smx_ctl_t));
   s->d_small = (uint32_t*)dmalloc(s, 64 * 4);
   CK(cudaHostAlloc((void**)&s->h_small, 64 * 4, cudaHostAllocDefault));
+  if (s->arena_bytes) {
+    /* a table with an arena is a bulk table: take the small cudaMalloc'ed scratch of the write path now (sketch
+     * bitmap, partition counters, spill list of the tile-wise re-placement) so that no batch ever waits for
+     * cudaMalloc — right after another table's arena went back to the driver a single call was seen to stall
+     * for 20 - 150 ms (config 3, first step: profiles/r2_summary.md) */
+    ensure_tmp(s, (size_t)1 << (SMX_SKETCH_BITS_LOG - 3), 3 * SMX_MAX_PARTS_H * 8);
+    s->d_spill = (unsigned long long*)dmalloc(s, (size_t)s->spill_cap * 16);
+  }
   CK(cudaStreamSynchronize(s->stream));
   if (fname) {
     s->fname = strdup(fname);
@@ -1763,6 +1776,8 @@ uint64_t smatrix_b200_stat(smatrix_t* s, int which) {
     case SMX_STAT_SPILLED: r = s->n_spilled; break;
     case SMX_STAT_SLICED_GETS: r = s->n_sliced_gets; break;
     case SMX_STAT_WIDE_CHUNKS: r = s->n_wide_chunks; break;
+    case SMX_STAT_NS_ALLOC: r = (uint64_t)s->alloc_ns; break;
+    case SMX_STAT_ALLOCS: r = s->n_allocs; break;
     case SMX_STAT_H2D_BYTES: r = s->h2d_bytes; break;
     case SMX_STAT_D2H_BYTES: r = s->d2h_bytes; break;
     case SMX_STAT_DIR_CAP: r = s->dir_cap; break;
