@@ -12,14 +12,17 @@
  *   k_grow_plan, k_free_push, k_migrate / _mid / _big
  *                       smatrix_rmap_resize + smatrix_mfree of the old map (:383-416, :151-166)
  *   k_dir_rehash, k_sketch_*   smatrix_cmap_resize (:715-741)
- *   k_get               smatrix_get (:174-185)
+ *   k_get, k_get_tiled  smatrix_get (:174-185): queries in input order (resident grid) / in directory-slice
+ *                       order (one block per 1024 consecutive queries, dispatched in order)
  *   k_rowlen            smatrix_rowlen (:212-223)
  *   k_row_counts, scan, k_getrow_inline / _fill / _chunks   smatrix_getrow (:189-210) for batches of rows
  *   k_set_max/mark/commit  last-writer-wins resolution for smatrix_set batches (:225-234 applied
  *                       sequentially)
  *   k_snap_units / _rows / _big   the row blocks of the .smx file (:454-482) in the loader's layout (:499-545)
- *   k_partition_count / _scatter  no counterpart: chunk ordering by directory slice, and the multi-GPU
- *                       route (every owner's run stored straight into that owner's inbox over NVLink)
+ *   k_partition_count / _scatter  no counterpart: chunk ordering by directory slice (writes and large read
+ *                       calls), and the multi-GPU route (every owner's run stored straight into that
+ *                       owner's inbox over NVLink)
+ *   k_parts_prefix, k_gather      cursors of the parts on the device; answers back into input order
  *
  * Concurrency rules the code relies on (DESIGN.md "Concurrency"):
  *   - cells and directory entries are only ever claimed 0 -> key by a 64-bit CAS and keys never

@@ -65,7 +65,9 @@ def test_committed_bench_lines_carry_the_contract_keys(n):
 ROUND2 = [("r2_bench_n1.json", "incr_mops_c2", 1), ("r2_bench_n1_steps20.json", "incr_mops_c2", 1),
           ("r2_bench_c3_n1.json", "incr_mops_c3", 1), ("r2_bench_c4_n1.json", "getrow_mpairs_c4", 1),
           ("r2_bench_n2.json", "incr_mops_c2", 2), ("r2_bench_n8.json", "incr_mops_c2", 8),
-          ("r2_bench_c5_n2.json", "incr_mops_c5", 2), ("r2_bench_c5_n8.json", "incr_mops_c5", 8)]
+          ("r2_bench_c5_n2.json", "incr_mops_c5", 2), ("r2_bench_c5_n8.json", "incr_mops_c5", 8),
+          # the final build of the round (256-slice write chunks, slice-ordered point reads)
+          ("r2h_bench_n1_steps20.json", "incr_mops_c2", 1), ("r2h_bench_c3_n1.json", "incr_mops_c3", 1)]
 
 
 @pytest.mark.parametrize("name,metric,n", ROUND2)
@@ -95,6 +97,10 @@ def test_round2_bench_lines(name, metric, n):
         assert r["nvlink"]["remote_bytes_per_rank_per_step"] > 0 and d["scaling"] in ("weak", "strong")
     if metric == "incr_mops_c2" and n == 1:
         assert r["random_sector"]["incr_frac"] > 0.4          # north_star: >= 40 % of the random-sector roofline
+    if name.startswith("r2h_"):
+        g = r["get"]        # the slice-ordered look-ups answered every query, with the answers of the input order, faster
+        assert g["sliced_fraction"] == 1.0 and g["input_order"]["same_answers"] and d["checks"]["get_orders_agree"]
+        assert d["get_mops"] > 1.5 * g["input_order"]["get_mops"]
 
 
 def test_full_scale_parity_record():
