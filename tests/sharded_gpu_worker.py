@@ -23,6 +23,8 @@ def main():
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     kind = os.environ.get("SMX_ROUTER_KIND", "c")     # c = the C router (product); torch-p2p / torch-nccl = fallback
+    sliced = kind == "c-sliced"                       # the C router, shards forced onto their slice-ordered paths
+    kind = "c" if sliced else kind
     p2p = kind != "torch-nccl"
     if kind == "c":
         m = ShardedSparseMatrix(rank, world, rank)
@@ -55,6 +57,8 @@ def main():
     got = m.get_batch(t(qx), t(qy)).cpu().numpy().view(U32)
     assert (got == ref.get_many(qx, qy)).all(), f"rank {rank}: sharded get mismatch"
     assert (m.get_batch(qx, qy) == got).all(), f"rank {rank}: host-array get differs from device-array get"
+    if sliced:
+        assert m.stat("sliced_gets") > 0 and m.stat("wide_chunks") > 0, (m.stat("sliced_gets"), m.stat("wide_chunks"))
     rows = np.unique(allx)[rank::world]
     got = m.rowlen_batch(t(rows)).cpu().numpy().view(U32)
     assert (got == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"

@@ -21,14 +21,20 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("kind", ["c", "torch-p2p", "torch-nccl"])
+KINDS = ["c", "torch-p2p", "torch-nccl", "c-sliced"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_row_sharding(world, kind):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29600 + world + 10 * ["c", "torch-p2p", "torch-nccl"].index(kind)
+    port = 29600 + world + 10 * KINDS.index(kind)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                WORLD_SIZE=str(world), SMX_ROUTER_KIND=kind)
+    if kind == "c-sliced":      # the C router with every owner ordering its inbox by directory slice: writes (256 slices
+        # for the order-free batch without column 0) and the runs of queries it answers for the asking ranks
+        env.update(SMATRIX_PARTITION_MIN="4096", SMATRIX_SLICE_LOG2="8", SMATRIX_GET_SLICE_MIN="1024")
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "sharded_gpu_worker.py")],
                               env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True) for r in range(world)]

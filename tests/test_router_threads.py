@@ -89,6 +89,8 @@ def _rank_main(sim, name, rank, world, errors, device_arrays):
         else:
             got = m.get_batch(qx, qy)
         assert (got == ref.get_many(qx, qy)).all(), f"rank {rank}: sharded get mismatch"
+        if os.environ.get("SMATRIX_GET_SLICE_MIN") == "64":      # the owners answered in directory-slice order
+            assert m.stat("sliced_gets") > 0 and m.stat("wide_chunks") > 0, (m.stat("sliced_gets"), m.stat("wide_chunks"))
         rows = np.unique(allx)[rank::world] if rank else np.unique(allx)           # overlapping requests are fine
         rows = np.concatenate([rows, np.array([7, 8, 9], U32)])                      # rows nobody has
         assert (m.rowlen_batch(rows) == ref.rowlen_many(rows)).all(), f"rank {rank}: sharded rowlen mismatch"
@@ -135,14 +137,19 @@ def _rank_main(sim, name, rank, world, errors, device_arrays):
 
 
 @pytest.mark.parametrize("device_arrays", [False, True], ids=["host-arrays", "device-arrays"])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, "2-sliced"])
 def test_c_router_ranks_as_threads(sim, world, device_arrays, monkeypatch):
+    if world == "2-sliced":     # the owners' shards order their inboxes by directory slice (writes: 256 slices for the
+        world = 2               # order-free batches without column 0; reads: every asking rank's run of queries)
+        monkeypatch.setenv("SMATRIX_PARTITION_MIN", "256")
+        monkeypatch.setenv("SMATRIX_SLICE_LOG2", "3")
+        monkeypatch.setenv("SMATRIX_GET_SLICE_MIN", "64")
     monkeypatch.setenv("SMATRIX_DIR_LOG2", "8")
     monkeypatch.setenv("SMATRIX_SHARD_PIECE", "4096")      # host slices are staged in several pieces ...
     monkeypatch.setenv("SMATRIX_SHARD_TAPER_MIN", "256")   # ... the last of them cut into 1/2, 1/4, 1/4
     monkeypatch.setenv("SMATRIX_SHARD_INBOX", "1024")      # the inboxes must grow on demand
     monkeypatch.setenv("SMATRIX_SHARD_TIMEOUT", "60")
-    name = f"smxtest_{os.getpid()}_{world}_{int(device_arrays)}"
+    name = f"smxtest_{os.getpid()}_{world}_{int(device_arrays)}_{os.environ.get('SMATRIX_GET_SLICE_MIN', 'd')}"
     errors: list = []
     ts = [threading.Thread(target=_rank_main, args=(sim, name, r, world, errors, device_arrays)) for r in range(world)]
     for t in ts:
