@@ -710,6 +710,7 @@ def run_write_workload(job: Job, name: str):
                    "chunk_ops": int(os.environ.get("SMATRIX_CHUNK", 1 << 26)),
                    "parallelism": f"row-hash shard x{world}, C router over peer memory" if world > 1 else "single GPU"},
         "get_mops": get_mops, "get_ms": ms_get, "get_hit_fraction": hits / G,
+        "get_mops_input_order": G * world / (ms_get0 * 1e-3) / 1e6,   # the same queries with set_get_slices(0)
         "nnz": nnz_total, "rows_present": rows_seen, "prefill_s": t_prefill,
         "table": stats, "clocks": clocks, "gpu_launches": launches, "upsert_rounds": rounds,
         "host_phase_ms_per_step": phases, "step_ms": step_ms, "step_upsert_kernel_ms": kern_ms,

@@ -953,9 +953,10 @@ void smatrix_b200_apply_ordered_out(smatrix_t* s, int op, const uint32_t* d_xs, 
  * that gather reads whole sectors.  The cursors are prefixed on the device (k_parts_prefix): nothing
  * between the five launches waits for the host.  The look-ups run in k_get_tiled (blocks dispatched
  * in query order; the resident-grid k_get drifts across slices and loses the effect: 11.5 vs 25.4
- * Gops/s).  Besides the saved touches the slice order confines the directory accesses to 32 MB at a
- * time (TLB reach), so it already pays at 0.3 - 0.65 queries per row.  Config 2, 500 M queries over
- * 13 M rows / 1.51 B cells: 12.8 -> 25.4 Gops/s. */
+ * Gops/s).  It already pays at 0.3 - 0.65 queries per row, where few entries are asked for twice —
+ * presumably because the directory accesses of a moment are confined to one slice's 32 MB instead
+ * of 4 GB (the input-order kernel moves ~0.6 fetches per query that no table access accounts for).
+ * Config 2, 500 M queries over 13 M rows / 1.51 B cells: 12.8 -> 25.4 Gops/s. */
 enum {
   SMX_GET_KEEP = 4,    /* bucket sectors with the ordinary L2 priority (default: evict-first, they are read once) */
   SMX_GET_WIDE = 8,    /* up to 256 slices instead of the write path's count (<= 2^SMATRIX_PARTS_LOG2 = 128) */
