@@ -46,11 +46,15 @@
 #define SMX_WARP 32
 #define SMX_LAUNCH(kern, grid, block, stream, ...) \
   kern<<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+/* opportunistic aggregation over whichever lanes happen to be converged here.  `key` is only read by the
+ * 32-lane CPU simulator (tests/hostsim/warp_sched.cpp), which has no instruction addresses to tell two inlined
+ * copies of a helper apart: lanes are grouped only if they agree on it */
+#define SMX_ACTIVEMASK(key) __activemask()
 #endif
 
 typedef unsigned long long ull;
 #define SMX_FULL 0xffffffffu
-#ifdef SMX_HOSTSIM
+#if defined(SMX_HOSTSIM) && SMX_WARP == 1
 #define SMX_BLOCK 1 /* sequential simulation: __syncthreads() is a no-op, so blocks have 1 thread */
 #else
 #define SMX_BLOCK (8 * SMX_WARP) /* 256 threads: 8 blocks/SM = 2048 resident threads */
@@ -153,7 +157,7 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x % SMX_WARP; }
 
 /* warp-aggregated "give me a unique index": one atomic per converged group of threads */
 __device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {
-  unsigned m = __activemask();
+  unsigned m = SMX_ACTIVEMASK(ctr);
   uint32_t lane = lane_id();
   int leader = __ffs(m) - 1;
   uint32_t base = 0;
@@ -162,7 +166,7 @@ __device__ __forceinline__ uint32_t agg_inc(uint32_t* ctr) {
   return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 }
 __device__ __forceinline__ void agg_inc64(ull* ctr) {
-  unsigned m = __activemask();
+  unsigned m = SMX_ACTIVEMASK(ctr);
   if ((int)lane_id() == __ffs(m) - 1) atomicAdd(ctr, (ull)__popc(m));
 }
 
@@ -217,7 +221,7 @@ __device__ __forceinline__ int dir_find(const smx_view_t& V, uint32_t x, bool cr
     if (old == 0ull) {
       /* occupancy counter of the slice: in a partitioned chunk nearly every row created at the same
        * time lives in the same slice, so the lanes that got here together add once for all of them */
-      const unsigned grp = __match_any_sync(__activemask(), sl);
+      const unsigned grp = __match_any_sync(SMX_ACTIVEMASK(0), sl);
       if ((int)lane_id() == __ffs(grp) - 1) atomicAdd(slice, (uint32_t)__popc(grp));
       h.key = x; h.meta = SMX_META_USED | SMX_INLINE_LOG;
       h.slots = 0; h.live = 0; h.c0 = 0; h.t0inv = 0; h.want = 0;
@@ -482,7 +486,7 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       /* take a vacated bucket of that class if there is one: one atomic per group of lanes that
        * want the same class (only pops run in this kernel; pushes happen in k_free_push) */
       {
-        const unsigned grp = __match_any_sync(__activemask(), newlog);
+        const unsigned grp = __match_any_sync(SMX_ACTIVEMASK(0), newlog);
         const int leader = __ffs(grp) - 1;
         const int cnt = __popc(grp), rank = __popc(grp & ((1u << lane) - 1u));
         int base = 0;
@@ -496,7 +500,7 @@ k_grow_plan(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
       }
       bytes = recycled ? 0ull : (8ull << newlog);
       if (caplog > SMX_INLINE_LOG) { /* the bucket this row vacates, per class (sizes the stacks) */
-        const unsigned grp = __match_any_sync(__activemask(), caplog);
+        const unsigned grp = __match_any_sync(SMX_ACTIVEMASK(0), caplog);
         if ((int)lane == __ffs(grp) - 1) atomicAdd(&V.ctl->grow_from[caplog], (uint32_t)__popc(grp));
       }
     }
@@ -539,7 +543,7 @@ k_free_push(smx_view_t V, smx_lists_t S, uint32_t n_grow) {
     const Hdr h = ld_hdr(V.dir + S.plan[j].entry);
     const uint32_t caplog = h.meta & SMX_META_CAPLOG;
     if (caplog <= SMX_INLINE_LOG) continue;
-    const unsigned grp = __match_any_sync(__activemask(), caplog);
+    const unsigned grp = __match_any_sync(SMX_ACTIVEMASK(0), caplog);
     const int leader = __ffs(grp) - 1;
     int base = 0;
     if ((int)lane == leader) base = atomicAdd(&V.ctl->free_cnt[caplog], __popc(grp));
@@ -1682,7 +1686,7 @@ k_partition_count(const uint32_t* xs, const uint32_t* ys, uint32_t n, uint32_t w
 /* cursors[p] = first output index of part p = exclusive prefix of counts (<= 256 parts: one thread;
  * the read path uses it so that no host round trip sits between the count and the scatter) */
 __global__ void k_parts_prefix(const ull* counts, uint32_t parts, ull* cursors) {
-#ifdef SMX_HOSTSIM
+#if defined(SMX_HOSTSIM) && SMX_WARP == 1
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ull at = 0ull;
     for (uint32_t p = 0; p < parts; ++p) {
@@ -1767,7 +1771,7 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
     }
     __syncthreads(); /* (1) the tile's histogram is complete */
     /* reserve the runs: one global atomic per non-empty part, not waited for until the tile is staged */
-#ifndef SMX_HOSTSIM
+#if !defined(SMX_HOSTSIM) || SMX_WARP > 1
     ull gb = 0ull;
     if (threadIdx.x < world && h[threadIdx.x]) gb = atomicAdd(&cursors[threadIdx.x], (ull)h[threadIdx.x]);
 #endif
@@ -1816,7 +1820,7 @@ k_partition_scatter(const uint32_t* xs, const uint32_t* ys, const uint32_t* vs, 
         }
       }
     }
-#ifdef SMX_HOSTSIM
+#if defined(SMX_HOSTSIM) && SMX_WARP == 1
     for (uint32_t k = threadIdx.x; k < world; k += blockDim.x)
       gdelta[k] = (h[k] ? atomicAdd(&cursors[k], (ull)h[k]) : 0ull) - myoff[k];
 #else

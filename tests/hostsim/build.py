@@ -18,17 +18,23 @@ def build(defines: list[str] | None = None, suffix: str = "") -> str:
 
 def _build(SO: str, defines: list[str], suffix: str) -> str:
     srcs = [os.path.join(CSRC, "smx_kernels.cu"), os.path.join(CSRC, "smx_host.c"),
-            os.path.join(HERE, "fake_runtime.cpp"), os.path.join(CSRC, "smx_router.c"), os.path.join(HERE, "hostsim.h"),
-            os.path.join(CSRC, "smx_internal.h")]
+            os.path.join(HERE, "fake_runtime.cpp"), os.path.join(CSRC, "smx_router.c"),
+            os.path.join(HERE, "warp_sched.cpp"),      # the fiber scheduler of the 32-lane variant (-DSMX_SIM_WARP32)
+            os.path.join(HERE, "hostsim.h"), os.path.join(CSRC, "smx_internal.h")]
     if os.path.exists(SO) and all(os.path.getmtime(s) < os.path.getmtime(SO) for s in srcs):
         return SO
     common = ["-O1", "-g", "-fPIC", "-DSMX_HOSTSIM", f"-I{HERE}", f"-I{CSRC}", "-Wall",
               "-Wno-unknown-pragmas", "-Wno-unused-function"] + defines
     objs = []
-    for src, cc, extra in ((srcs[0], "g++", ["-x", "c++", "-std=c++17"]),
+    # -fno-gnu-unique: static locals of templates / inline functions (the kernels' "shared memory") would otherwise be
+    # STB_GNU_UNIQUE, i.e. ONE object per process shared by every variant of this library that a test session loads —
+    # with arrays sized by SMX_BLOCK (1 here, 256 in the 32-lane variant)
+    cxx = ["-std=c++17", "-fno-gnu-unique"]
+    for src, cc, extra in ((srcs[0], "g++", ["-x", "c++"] + cxx),
                            (srcs[1], "gcc", ["-std=gnu11"]),
-                           (srcs[2], "g++", ["-std=c++17"]),
-                           (srcs[3], "gcc", ["-std=gnu11"])):
+                           (srcs[2], "g++", cxx),
+                           (srcs[3], "gcc", ["-std=gnu11"]),
+                           (srcs[4], "g++", cxx)):
         o = os.path.join(HERE, os.path.basename(src) + suffix + ".o")
         subprocess.run([cc] + common + extra + ["-c", src, "-o", o], check=True)
         objs.append(o)
