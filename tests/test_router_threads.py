@@ -136,9 +136,17 @@ def _rank_main(sim, name, rank, world, errors, device_arrays):
         errors.append(f"rank {rank}: {e!r}\n{traceback.format_exc()}")
 
 
+@pytest.fixture(scope="module")
+def sim32():
+    from hostsim import build as hb
+    return hb.build(defines=["-DSMX_SIM_WARP32"], suffix="_warp32")
+
+
 @pytest.mark.parametrize("device_arrays", [False, True], ids=["host-arrays", "device-arrays"])
-@pytest.mark.parametrize("world", [2, 3, "2-sliced"])
-def test_c_router_ranks_as_threads(sim, world, device_arrays, monkeypatch):
+@pytest.mark.parametrize("world", [2, 3, "2-sliced", "2-sliced-warp32"])
+def test_c_router_ranks_as_threads(sim, sim32, world, device_arrays, monkeypatch):
+    if world == "2-sliced-warp32":   # the same on the 32-lane lock-step simulator: the route's partition kernels, the
+        sim, world = sim32, "2-sliced"  # gathers and the shards' kernels with their warp collectives, one fiber scheduler per rank
     if world == "2-sliced":     # the owners' shards order their inboxes by directory slice (writes: 256 slices for the
         world = 2               # order-free batches without column 0; reads: every asking rank's run of queries)
         monkeypatch.setenv("SMATRIX_PARTITION_MIN", "256")
@@ -149,7 +157,7 @@ def test_c_router_ranks_as_threads(sim, world, device_arrays, monkeypatch):
     monkeypatch.setenv("SMATRIX_SHARD_TAPER_MIN", "256")   # ... the last of them cut into 1/2, 1/4, 1/4
     monkeypatch.setenv("SMATRIX_SHARD_INBOX", "1024")      # the inboxes must grow on demand
     monkeypatch.setenv("SMATRIX_SHARD_TIMEOUT", "60")
-    name = f"smxtest_{os.getpid()}_{world}_{int(device_arrays)}_{os.environ.get('SMATRIX_GET_SLICE_MIN', 'd')}"
+    name = f"smxtest_{os.getpid()}_{world}_{int(device_arrays)}_{os.environ.get('SMATRIX_GET_SLICE_MIN', 'd')}_{int(sim is sim32)}"
     errors: list = []
     ts = [threading.Thread(target=_rank_main, args=(sim, name, r, world, errors, device_arrays)) for r in range(world)]
     for t in ts:
