@@ -73,3 +73,12 @@ def test_batch_out_and_cf_read_side(make):
 def test_chunks_without_column0(make, monkeypatch):
     monkeypatch.setenv("SMATRIX_WIDE_SLICES", "1")
     ps.scenario_no_column0(make, n=9000, n_rows=2500)
+
+
+def test_snapshot_export_kernels(sim32, tmp_path, monkeypatch):
+    """K9: the row blocks of the .smx file are laid out by k_snap_* (one warp per row, linear probing in the reference's
+    y % size layout) — both directions against the reference's own file mode, and a round trip with big rows."""
+    import snapshot_suite as ss
+    monkeypatch.setenv("SMATRIX_DIR_LOG2", "6")
+    ss.scenario_snapshot_interchange(lambda f: SparseMatrix(f, _lib_path=sim32), tmp_path)
+    ss.scenario_snapshot_roundtrip_big(lambda f: SparseMatrix(f, _lib_path=sim32), tmp_path, n_rows=1500)
