@@ -1,6 +1,7 @@
 """Randomised stress of the host logic on the serial simulator (tests/hostsim): random knob
 settings (directory size, chunk size, partition threshold / slice size, pre-aggregation, recycling,
-directory pre-sizing, tile re-placement with tiny tiles and short spill lists, arena mode) x random
+directory pre-sizing, tile re-placement with tiny tiles and short spill lists, arena mode, 256-slice chunks,
+point reads in slice order with their measurement switches; a fifth of the runs on the 32-lane simulator) x random
 op mixes (incr / decr / set, column-0 rates, key widths, batch sizes, *_batch_out) against the
 checker.  Not part of the test suite; run it after touching smx_host.c:   python scripts/fuzz_hostlogic.py [runs] [seed]"""
 import os, sys, time
@@ -15,6 +16,21 @@ from conftest import safe_stream
 U32 = np.uint32
 sim = hb.build()
 sim_small = hb.build(defines=["-DMIG_TILE_LOG=3u"], suffix="_smalltiles")   # tiny re-placement tiles: cells spill all the time
+sim32 = hb.build(defines=["-DSMX_SIM_WARP32"], suffix="_warp32")             # 32-lane lock-step warps (slow)
+from libsmatrix_b200.matrix import DevPtr
+
+
+def device_gets(m, qx, qy):
+    """smatrix_get_batch on arrays in the simulator's device memory: the path that may order the queries by slice"""
+    n = len(qx)
+    ptrs = [m.dev_alloc(4 * n + 8) for _ in range(3)]
+    m.memcpy(ptrs[0], qx.ctypes.data, 4 * n); m.memcpy(ptrs[1], qy.ctypes.data, 4 * n)
+    m.get_batch(DevPtr(ptrs[0], n), DevPtr(ptrs[1], n), DevPtr(ptrs[2], n))
+    out = np.empty(n, U32)
+    m.memcpy(out.ctypes.data, ptrs[2], 4 * n)
+    for p in ptrs:
+        m.dev_free(p)
+    return out
 runs = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else int(time.time())
 print("seed0", seed0, flush=True)
@@ -25,8 +41,11 @@ for run in range(runs):
              "SMATRIX_PARTS_LOG2": int(rng.integers(1, 9)), "SMATRIX_PREAGG": int(rng.integers(0, 2)),
              "SMATRIX_STAGE": int(rng.choice([1024, 5000, 1 << 23])), "SMATRIX_RECYCLE": int(rng.integers(0, 2)),
              "SMATRIX_PRESIZE": int(rng.integers(0, 2)), "SMATRIX_MIGRATE_TILES": int(rng.integers(0, 2)),
-             "SMATRIX_SPILL_CAP": int(rng.choice([1, 64, 1 << 16])), "SMATRIX_ARENA_GIB": int(rng.choice([0, 0, 1]))}
-    lib = sim_small if rng.random() < 0.5 else sim
+             "SMATRIX_SPILL_CAP": int(rng.choice([1, 64, 1 << 16])), "SMATRIX_ARENA_GIB": int(rng.choice([0, 0, 1])),
+             "SMATRIX_WIDE_SLICES": int(rng.integers(0, 2)), "SMATRIX_GET_SLICE_MIN": int(rng.choice([2, 100, 1 << 22])),
+             "SMATRIX_GET_SLICES": int(rng.choice([0, 1, 1, 2, 2 | 4, 2 | 8, 2 | 16, 2 | 32, 1 | 4 | 8 | 16 | 32]))}
+    r = rng.random()
+    lib = sim32 if r < 0.2 else (sim_small if r < 0.6 else sim)
     for k, v in knobs.items():
         os.environ[k] = str(v)
     m, ref = SparseMatrix(_lib_path=lib), ps.checker()
@@ -55,6 +74,8 @@ for run in range(runs):
             qx = np.concatenate([ax[-4000:], rng.integers(0, 2**32, 200, dtype=np.uint64).astype(U32)])
             qy = np.concatenate([ay[-4000:], rng.integers(0, 2**32, 200, dtype=np.uint64).astype(U32)])
             ps.compare(m, ref, np.concatenate([np.unique(ax), qx[-10:]]), qx, qy)
+            got = device_gets(m, qx, qy)
+            assert (got == ref.get_many(qx, qy)).all(), f"device-array get: {int((got != ref.get_many(qx, qy)).sum())} mismatches"
         m.close(); ref.close()
     except Exception as e:      # noqa: BLE001
         print("FAILED:", desc, "->", repr(e), flush=True)
